@@ -1,0 +1,178 @@
+"""Synthetic RGB-D input for the DI-Fusion hot path (numpy, host side; no dataset ships with the reference).
+
+Scenes follow SURVEY.md section 8(d):
+
+* ``S0``  sphere r=1.2 m centred (0,0,2) seen from the origin, 32^3 PLIVox grid at 0.1 m.
+* ``S1``  box room + sphere, 8x5x6 m bounds, 200-frame yaw orbit; 27k points per 640x480 frame.
+
+The frame pipeline restates the *arithmetic* of the reference's pre-processing that decides
+which points reach ``integrate_keyframe`` (it is not the kd-tree pre-processing itself, which is
+out of scope): nearest 1/2 sub-sampling and pin-hole unprojection with scaled
+intrinsics (reference ``system/tracker.py:88-97``, ``ext/imgproc/imgproc.cu:5-24``), depth clipping
+(``main.py:67-68``) and the 2 cm box filter (``tracker.py:13-23``).  Normals are analytic.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+# ICL-NUIM intrinsics, reference dataset/production/icl_nuim.py:16
+ICL_FX, ICL_FY, ICL_CX, ICL_CY = 481.2, 480.0, 319.5, 239.5
+IMG_W, IMG_H = 640, 480
+
+
+@dataclass
+class Scene:
+    name: str
+    bound_min: list
+    bound_max: list
+    voxel_size: float
+    prune_min_vox_obs: int
+    ignore_count_th: float
+    encoder_count_th: float = 600.0
+    sphere_c: tuple = (0.0, 0.0, 2.0)
+    sphere_r: float = 1.2
+    room: tuple | None = None            # (xmin, xmax, ymin, ymax, zmin, zmax) or None
+    depth_cut: tuple = (0.5, 5.0)
+    extra: dict = field(default_factory=dict)
+
+    def map_args(self):
+        import argparse
+        return argparse.Namespace(bound_min=list(self.bound_min), bound_max=list(self.bound_max),
+                                  voxel_size=self.voxel_size, prune_min_vox_obs=self.prune_min_vox_obs,
+                                  ignore_count_th=self.ignore_count_th, encoder_count_th=self.encoder_count_th,
+                                  optim_n_iters=0)
+
+
+def scene_S0() -> Scene:
+    return Scene("S0", [-1.6, -1.6, 0.4], [1.6, 1.6, 3.6], 0.1, 16, 16.0)
+
+
+def scene_S1(voxel_size: float = 0.05) -> Scene:
+    coarse = voxel_size >= 0.1
+    return Scene("S1", [-3.5, -2.5, -0.5], [4.5, 2.5, 5.5], voxel_size,
+                 16 if coarse else 2, 16.0 if coarse else 4.0,
+                 sphere_c=(0.3, 0.2, 2.0), sphere_r=0.6, room=(-2.0, 2.0, -1.5, 1.5, -1.0, 3.0))
+
+
+def yaw_pose(yaw_rad: float, t=(0.0, 0.0, 0.0)):
+    """Camera-to-world rotation (yaw about +y) and translation."""
+    c, s = np.cos(yaw_rad), np.sin(yaw_rad)
+    R = np.array([[c, 0.0, s], [0.0, 1.0, 0.0], [-s, 0.0, c]])
+    return R, np.asarray(t, dtype=float)
+
+
+def orbit_pose(frame: int, n_frames: int = 200):
+    """Smooth yaw sweep -20 deg -> +20 deg over the stream (<=0.32 deg and <=1 cm per frame), SURVEY 8(d) S1."""
+    ph = np.pi * (frame % (2 * n_frames)) / n_frames
+    yaw = -np.deg2rad(20.0) * np.cos(ph)
+    t = (0.25 * np.sin(ph), 0.05 * np.sin(2 * ph), -0.25 * np.sin(ph))
+    return yaw_pose(yaw, t)
+
+
+def render_depth(scene: Scene, R: np.ndarray, t: np.ndarray, noise_sigma: float = 0.0, seed: int = 0):
+    """Analytic ray cast: (H, W) float32 depth (NaN = invalid) and (H, W, 3) world-frame normals."""
+    u, v = np.meshgrid(np.arange(IMG_W, dtype=np.float64), np.arange(IMG_H, dtype=np.float64))
+    d_c = np.stack([(u - ICL_CX) / ICL_FX, (v - ICL_CY) / ICL_FY, np.ones_like(u)], axis=-1)   # z-depth param
+    d_w = d_c @ R.T
+    o = t.reshape(1, 1, 3)
+    best = np.full(u.shape, np.inf)
+    nrm = np.zeros(u.shape + (3,))
+
+    # sphere
+    c = np.asarray(scene.sphere_c, dtype=float)
+    oc = o - c
+    a = (d_w * d_w).sum(-1)
+    b = 2.0 * (d_w * oc).sum(-1)
+    cc = (oc * oc).sum(-1) - scene.sphere_r ** 2
+    disc = b * b - 4 * a * cc
+    ok = disc > 0
+    s = np.where(ok, (-b - np.sqrt(np.where(ok, disc, 0.0))) / (2 * a), np.inf)
+    ok &= s > 1e-6
+    s = np.where(ok, s, np.inf)
+    hit = o + d_w * np.where(np.isfinite(s), s, 0.0)[..., None]
+    n_s = (hit - c) / scene.sphere_r
+    upd = s < best
+    best = np.where(upd, s, best)
+    nrm = np.where(upd[..., None], n_s, nrm)
+
+    # room (seen from inside): nearest positive exit through each wall
+    if scene.room is not None:
+        lo = np.array(scene.room[0::2]); hi = np.array(scene.room[1::2])
+        for ax in range(3):
+            for bound, sign in ((lo[ax], 1.0), (hi[ax], -1.0)):
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    s = (bound - o[..., ax]) / d_w[..., ax]
+                p = o + d_w * np.where(np.isfinite(s), s, 0.0)[..., None]
+                inside = np.ones(u.shape, dtype=bool)
+                for ox in range(3):
+                    if ox != ax:
+                        inside &= (p[..., ox] >= lo[ox] - 1e-9) & (p[..., ox] <= hi[ox] + 1e-9)
+                ok = np.isfinite(s) & (s > 1e-6) & inside
+                s = np.where(ok, s, np.inf)
+                upd = s < best
+                best = np.where(upd, s, best)
+                n_w = np.zeros(3); n_w[ax] = sign
+                nrm = np.where(upd[..., None], n_w.reshape(1, 1, 3), nrm)
+
+    depth = best.copy()
+    if noise_sigma > 0:
+        depth = depth + np.random.default_rng(seed).normal(0.0, noise_sigma, depth.shape)
+    depth = depth.astype(np.float32)
+    bad = ~np.isfinite(best) | (depth < scene.depth_cut[0]) | (depth > scene.depth_cut[1])
+    depth[bad] = np.nan
+    return depth, nrm.astype(np.float32)
+
+
+def box_filter(points: np.ndarray, normals: np.ndarray, voxel: float = 0.02):
+    """Restates reference tracker.py:13-23 (point_box_filter): per-cell mean of points and normals,
+    output ordered by the sorted unique cell key."""
+    p32 = points.astype(np.float32)
+    mn = p32.min(0, keepdims=True) - np.float32(voxel * 0.5)
+    mx = p32.max(0, keepdims=True) + np.float32(voxel * 0.5)
+    coord = np.floor((p32 - mn) / np.float32(voxel)).astype(np.int64)
+    n = np.floor((mx - mn) / np.float32(voxel)).astype(np.int64)[0] + 16
+    key = coord[:, 0] + coord[:, 1] * n[0] + coord[:, 2] * n[0] * n[1]
+    _, inv = np.unique(key, return_inverse=True)
+    m = int(inv.max()) + 1
+    cnt = np.bincount(inv, minlength=m).astype(np.float64)
+    out_p = np.stack([np.bincount(inv, weights=p32[:, k].astype(np.float64), minlength=m) / cnt for k in range(3)], 1)
+    out_n = np.stack([np.bincount(inv, weights=normals[:, k].astype(np.float64), minlength=m) / cnt for k in range(3)], 1)
+    return out_p.astype(np.float32), out_n.astype(np.float32)
+
+
+def frame_points(scene: Scene, R: np.ndarray, t: np.ndarray, subsample: int = 2, noise_sigma: float = 0.0,
+                 seed: int = 0, box: float = 0.02):
+    """One 640x480 frame -> (pc_cam (N,3), normal_cam (N,3)) float32, as tracker.last_processed_pc would hold."""
+    depth, n_w = render_depth(scene, R, t, noise_sigma, seed)
+    d = depth[::subsample, ::subsample]                      # nearest, scale 0.5  (tracker.py:89-91)
+    n_w = n_w[::subsample, ::subsample]
+    h, w = d.shape
+    sc = 1.0 / subsample
+    fx, fy, cx, cy = (np.float32(ICL_FX * sc), np.float32(ICL_FY * sc), np.float32(ICL_CX * sc), np.float32(ICL_CY * sc))
+    uu, vv = np.meshgrid(np.arange(w, dtype=np.float32), np.arange(h, dtype=np.float32))
+    x = (uu - cx) / fx * d                                   # imgproc.cu:17-19
+    y = (vv - cy) / fy * d
+    pc = np.stack([x, y, d], -1).reshape(-1, 3)
+    n_c = (n_w.reshape(-1, 3).astype(np.float64) @ R).astype(np.float32)      # world -> camera frame
+    keep = ~np.isnan(pc[:, 0])
+    pc, n_c = pc[keep], n_c[keep]
+    if box > 0:
+        pc, n_c = box_filter(pc, n_c, box)
+        n_c = n_c / np.maximum(np.linalg.norm(n_c, axis=1, keepdims=True), 1e-12)
+    return pc.astype(np.float32), n_c.astype(np.float32)
+
+
+def to_world(pc_cam: np.ndarray, n_cam: np.ndarray, R: np.ndarray, t: np.ndarray):
+    """Isometry @ points as reference utils/motion_util.py:322-327 does it (fp32 matmul + translation)."""
+    R32, t32 = R.astype(np.float32), t.astype(np.float32)
+    return (pc_cam @ R32.T + t32[None, :]).astype(np.float32), (n_cam @ R32.T).astype(np.float32)
+
+
+def stream_frames(scene: Scene, n_frames: int, noise_sigma: float = 0.0):
+    """Yields (pc_cam, n_cam, R, t) for the orbit stream."""
+    for f in range(n_frames):
+        R, t = orbit_pose(f, 200)
+        pc, n = frame_points(scene, R, t, noise_sigma=noise_sigma, seed=f)
+        yield pc, n, R, t

@@ -1,0 +1,61 @@
+"""CPU: the oracle restatement (oracle/dif_oracle.py) against the golden fixtures that
+tests/golden/make_golden.py produced by executing the unmodified reference."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import close, fixture_args, frac_off
+from oracle import dif_oracle as O
+
+
+def test_decoder_kat(golden, oracle_weights):
+    fx = golden["decoder_kat"]
+    lat, xyz = torch.from_numpy(fx["latent"]), torch.from_numpy(fx["xyz"]).requires_grad_(True)
+    sdf, std = O.decoder_forward(oracle_weights.dec, lat, xyz)
+    assert close(sdf.detach().numpy(), fx["sdf"], 1e-5) and close(std.detach().numpy(), fx["std"], 1e-5)
+    g = torch.autograd.grad(sdf.sum(), xyz)[0].numpy()
+    assert frac_off(g, fx["dsdf_dxyz"]) < 2e-3            # ReLU-kink flips, see make_golden.py
+
+
+def test_encoder_kat(golden, oracle_weights):
+    fx = golden["encoder_kat"]
+    out = O.encoder_forward(oracle_weights.enc, torch.from_numpy(fx["xyzn"])).numpy()
+    assert close(out, fx["latent"], 1e-5)
+
+
+@pytest.mark.parametrize("name", ["s0_map", "s0_freeze", "s1_map"])
+def test_map_state(golden, oracle_weights, name):
+    fx = golden[name]
+    m = O.OracleMap(oracle_weights, fixture_args(fx))
+    for f in range(int(fx["n_frames"])):
+        mask = m.integrate_keyframe(fx[f"f{f}.xyz"], fx[f"f{f}.normal"])
+        n = fx[f"f{f}.xyz"].shape[0]
+        assert np.array_equal(np.packbits(mask), fx[f"f{f}.unq_mask"]) and mask.shape[0] == n
+        assert m.n_occupied == int(fx[f"f{f}.n_occupied"]) and m.latent_vecs.shape[0] == int(fx[f"f{f}.capacity"])
+        occ = np.nonzero(m.indexer != -1)[0]
+        assert np.array_equal(occ, fx[f"f{f}.occ_cells"]) and np.array_equal(m.indexer[occ], fx[f"f{f}.occ_slots"])
+        assert np.array_equal(m.latent_vecs_pos[:m.n_occupied][fx[f"f{f}.occ_slots"]], fx[f"f{f}.occ_cells"])
+        assert np.array_equal(m.voxel_obs_count[:m.n_occupied], fx[f"f{f}.obs_count"])
+        assert close(m.latent_vecs[fx[f"f{f}.latent_rows"]], fx[f"f{f}.latent"], 1e-5)
+        assert np.array_equal(m.updated_vec_id, fx[f"f{f}.updated_vec_id"])
+    sdf, std, valid, g = m.get_sdf(fx["q.xyz"], want_grad=True)
+    assert np.array_equal(np.packbits(valid), fx["q.valid"])
+    assert close(sdf, fx["q.sdf"], 1e-5) and close(std, fx["q.std"], 1e-5)
+    assert frac_off(g, fx["q.grad"]) < 2e-3
+    if "hg.H" in fx.files:
+        H, gv, E = O.compute_sdf_Hg(m, fx["hg.R_last"], fx["hg.t_last"], fx["hg.R_delta"], fx["hg.t_delta"], fx["hg.obs"])
+        assert np.abs(H - fx["hg.H"]).max() <= 1e-4 * np.abs(fx["hg.H"]).max()
+        assert np.abs(gv - fx["hg.g"]).max() <= 1e-4 * np.abs(fx["hg.g"]).max()
+        assert close(E, float(fx["hg.E"]), 1e-5)
+        _, _, E2 = O.compute_sdf_Hg(m, fx["hg.R_last"], fx["hg.t_last"], fx["hg.R_delta"], fx["hg.t_delta"], fx["hg.obs"], no_grad=True)
+        assert close(E2, float(fx["hg.E_nograd"]), 1e-5)
+    if "mesh.res" in fx.files:
+        foc, mp, hs, hd, _ = m.mesh_cubes(int(fx["mesh.res"]), fast=True, no_cache=True)
+        assert np.array_equal(foc, fx["mesh.focused"]) and np.array_equal(mp, fx["mesh.mapping"])
+        sel = fx["mesh.sel"]
+        assert close(hs[sel], fx["mesh.sdf_sel"], 1e-5) and close(hd[sel], fx["mesh.std_sel"], 1e-5)
+        assert abs(hs.astype(np.float64).sum() - float(fx["mesh.sdf_sum"])) < 1e-2
+        from oracle import mc_oracle
+        tri, fid, std3 = mc_oracle.marching_cubes_interp(m.indexer.reshape(m.n_xyz), foc, mp, hs, hd, int(4e6), m.n_xyz,
+                                                         float(fx["mesh.max_std"]))
+        assert abs(tri.shape[0] - int(fx["mesh.n_tri_oracle_mc"])) <= 8      # threshold flips on ~1e-6 sdf noise
