@@ -1,0 +1,97 @@
+"""ctypes binding of libdifusion_b200.so (C ABI: include/difusion_b200.h).
+
+The product path has NO CPU fallback: if the CUDA library is missing or fails to load, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libdifusion_b200.so"
+
+DIF_STAT_COUNT = 8
+STAT_N_KEPT, STAT_N_NEW, STAT_N_SAMPLES, STAT_N_UPDATED, STAT_N_OCCUPIED, STAT_FLAGS, STAT_N_FOCUSED = range(7)
+
+
+class MapView(C.Structure):
+    """struct dif_map_view"""
+    _fields_ = [("indexer", C.c_void_p), ("latent_vecs", C.c_void_p), ("latent_vecs_pos", C.c_void_p),
+                ("voxel_obs_count", C.c_void_p), ("slot_dirty", C.c_void_p), ("n_occupied", C.c_void_p),
+                ("capacity", C.c_int64), ("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32),
+                ("bound_min", C.c_float * 3), ("voxel_size", C.c_float), ("prune_min_vox_obs", C.c_int32),
+                ("ignore_count_th", C.c_float), ("encoder_count_th", C.c_float)]
+
+
+_P, _I64, _I32, _F, _SZ = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_size_t
+_MV = C.POINTER(MapView)
+
+# name -> (restype, argtypes); this table is also what tests/test_abi.py checks against include/difusion_b200.h
+SIGNATURES = {
+    "dif_abi_version": (C.c_int, []),
+    "dif_last_error": (C.c_char_p, []),
+    "dif_decoder_prepared_bytes": (_SZ, []),
+    "dif_encoder_prepared_bytes": (_SZ, []),
+    "dif_prepare_decoder": (C.c_int, [_P, _P, _P]),
+    "dif_prepare_encoder": (C.c_int, [_P, _P, _P]),
+    "dif_integrate_persist_bytes": (_SZ, [_I64, _I64]),
+    "dif_integrate_scratch_bytes": (_SZ, [_I64]),
+    "dif_integrate": (C.c_int, [_MV, _P, _P, _P, _I64, _P, _P, _SZ, _P, _SZ, _P, _P]),
+    "dif_decode": (C.c_int, [_P, _P, _P, _P, _I64, _P, _F, _P, _P, _P, _P, _P]),
+    "dif_encode": (C.c_int, [_P, _P, _I64, _P, _P]),
+    "dif_map_query": (C.c_int, [_MV, _P, _I64, _P, _P, _P, _P]),
+    "dif_icp_scratch_bytes": (_SZ, [_I64]),
+    "dif_icp_linearize": (C.c_int, [_MV, _P, _P, _I64, C.POINTER(C.c_float), _F, C.c_int, _P, _SZ, _P, _P]),
+    "dif_mesh_select_scratch_bytes": (_SZ, [_I64, _I64]),
+    "dif_mesh_select": (C.c_int, [_MV, _P, _I64, _P, _P, _P, _P, _P, _SZ, _P]),
+    "dif_mesh_decode_scratch_bytes": (_SZ, [_I64, C.c_int]),
+    "dif_mesh_decode": (C.c_int, [_MV, _P, _P, _I64, C.c_int, C.c_int, _P, _P, _P, _SZ, _P, _P]),
+    "dif_marching_cubes": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _I64, _P, _I64, _P, _P, C.c_int, _F, _P, _P, _P, _I64, _P, _P]),
+    "dif_groupby_sum": (C.c_int, [_P, _P, _I64, _I32, _I64, _P, _P, _P]),
+}
+
+_lib = None
+
+
+class DifusionLibraryError(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded library; raises (loudly) when it has not been built - there is no fallback path."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise DifusionLibraryError(
+                f"{LIB_PATH} not found: build it with `python -m difusion_b200.build` (nvcc, sm_100a). "
+                "difusion_b200 has no CPU or PyTorch fallback.")
+        try:
+            h = C.CDLL(str(LIB_PATH))
+        except OSError as e:
+            raise DifusionLibraryError(f"cannot load {LIB_PATH}: {e}") from e
+        for name, (res, args) in SIGNATURES.items():
+            f = getattr(h, name)
+            f.restype, f.argtypes = res, args
+        if h.dif_abi_version() != 1:
+            raise DifusionLibraryError("ABI version mismatch")
+        _lib = h
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().dif_last_error().decode() if rc == -3 else {-1: "invalid argument", -2: "workspace too small"}.get(rc, "?")
+        raise DifusionLibraryError(f"{what} failed with code {rc}: {msg}")
+
+
+def ptr(t):
+    """Device pointer of a (contiguous) torch tensor, or None."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "difusion_b200 kernels need contiguous tensors"
+    return t.data_ptr()
+
+
+def stream_ptr(device=None):
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream

@@ -1,0 +1,68 @@
+// Shared device helpers of libdifusion_b200 (sm_100a).  No torch, no thrust: plain CUDA runtime.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/difusion_b200.h"
+
+#define DIF_L 29                 // latent dim
+#define DIF_NUM_SMS 148          // B200
+
+namespace dif {
+
+extern thread_local char g_last_error[256];
+
+inline int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_last_error, sizeof(g_last_error), "%s: %s", what, cudaGetErrorString(e));
+        return DIF_E_LAUNCH;
+    }
+    return DIF_OK;
+}
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// Carves a caller-provided workspace into aligned sub-buffers.
+struct Carver {
+    char* base; size_t off;
+    explicit Carver(void* p) : base((char*)p), off(0) {}
+    template <class T> T* take(size_t count) { T* r = (T*)(base + off); off += align_up(count * sizeof(T)); return r; }
+};
+
+// Map geometry passed by value to kernels.
+struct Grid {
+    int nx, ny, nz;
+    float bx, by, bz, vs;
+    __host__ __device__ int64_t cells() const { return (int64_t)nx * ny * nz; }
+};
+
+inline Grid make_grid(const dif_map_view* m) {
+    Grid g; g.nx = m->nx; g.ny = m->ny; g.nz = m->nz;
+    g.bx = m->bound_min[0]; g.by = m->bound_min[1]; g.bz = m->bound_min[2]; g.vs = m->voxel_size;
+    return g;
+}
+
+// (p - bound_min) / voxel_size exactly as the reference's CPU tensors compute it: one fp32 subtract, one fp32 true
+// division (system/map.py:366-367, :565).  Explicit _rn intrinsics stop nvcc from contracting or replacing the divide.
+__device__ __forceinline__ float3 normalize_point(const Grid& g, float x, float y, float z) {
+    return make_float3(__fdiv_rn(__fsub_rn(x, g.bx), g.vs), __fdiv_rn(__fsub_rn(y, g.by), g.vs), __fdiv_rn(__fsub_rn(z, g.bz), g.vs));
+}
+
+// linear id = z + nz*y + nz*ny*x  (map.py:287-292)
+__device__ __forceinline__ int lin_id(const Grid& g, int ix, int iy, int iz) { return iz + g.nz * (iy + g.ny * ix); }
+
+__device__ __forceinline__ bool in_grid(const Grid& g, int ix, int iy, int iz) {
+    return (unsigned)ix < (unsigned)g.nx && (unsigned)iy < (unsigned)g.ny && (unsigned)iz < (unsigned)g.nz;
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace dif

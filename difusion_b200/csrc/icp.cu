@@ -1,0 +1,183 @@
+// Fused point-to-implicit ICP linearisation: pose transform -> PLIVox lookup -> decoder forward (+ backward wrt xyz) ->
+// residual / Jacobian / Huber -> 6x6 normal equations, one launch, one 44-double result.
+//   replaces reference system/tracker.py:174-218 (compute_sdf_Hg) + system/map.py:559-579 (get_sdf) + the autograd
+//   backward of network/di_decoder.py.  SURVEY rows a-8, a-9, A.8, A.9.
+// The reference runs ~15 torch launches + 2 boolean-mask syncs for the lookup, cuBLAS forward, an autograd backward that
+// also builds parameter gradients, and three host syncs (.cpu() x2, .item()) per Gauss-Newton iteration.
+#include "mlp_simt.cuh"
+
+namespace dif {
+
+struct MapRO { const int64_t* indexer; const float* latent; const float* obs; Grid g; float ignore_th; };
+struct Pose { float Rc[9], tc[3], Rd[9], td[3], Rl[9]; };      // composite (last*delta), delta, last rotation
+
+constexpr int ICP_VALS = 32;     // 21 upper-tri H + 6 g + E + M, padded
+
+__global__ void __launch_bounds__(MLP_THREADS) icp_linearize_kernel(
+        MapRO m, const float* __restrict__ P, const float* __restrict__ obs, int n, Pose pose, float huber_k, int want_grad,
+        float* __restrict__ partials, unsigned int* __restrict__ done_counter, double* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DecoderSmem& s = *reinterpret_cast<DecoderSmem*>(smem_raw);
+    __shared__ float q_s[3 * MLP_T];
+    __shared__ float r_s[MLP_T], inv_std_s[MLP_T];
+    __shared__ int slot_s[MLP_T];
+    __shared__ bool is_last;
+    float acc[29];                               // meaningful on lane 0 of warp 0 only
+#pragma unroll
+    for (int j = 0; j < 29; ++j) acc[j] = 0.f;
+
+    const int n_tiles = (n + MLP_T - 1) / MLP_T;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int base = tile * MLP_T;
+        if (threadIdx.x < MLP_T) {
+            const int t = threadIdx.x, i = base + t;
+            int slot = -1; float rx = 0.f, ry = 0.f, rz = 0.f;
+            if (i < n) {
+                const float x = obs[3 * i], y = obs[3 * i + 1], z = obs[3 * i + 2];
+                // cur = (last . delta) @ obs  (tracker.py:181, motion_util.py:322-327)
+                const float wx = fmaf(z, pose.Rc[2], fmaf(y, pose.Rc[1], x * pose.Rc[0])) + pose.tc[0];
+                const float wy = fmaf(z, pose.Rc[5], fmaf(y, pose.Rc[4], x * pose.Rc[3])) + pose.tc[1];
+                const float wz = fmaf(z, pose.Rc[8], fmaf(y, pose.Rc[7], x * pose.Rc[6])) + pose.tc[2];
+                q_s[t] = fmaf(z, pose.Rd[2], fmaf(y, pose.Rd[1], x * pose.Rd[0])) + pose.td[0];             // delta @ obs (:196)
+                q_s[MLP_T + t] = fmaf(z, pose.Rd[5], fmaf(y, pose.Rd[4], x * pose.Rd[3])) + pose.td[1];
+                q_s[2 * MLP_T + t] = fmaf(z, pose.Rd[8], fmaf(y, pose.Rd[7], x * pose.Rd[6])) + pose.td[2];
+                const float3 p = normalize_point(m.g, wx, wy, wz);
+                const int ix = (int)ceilf(p.x) - 1, iy = (int)ceilf(p.y) - 1, iz = (int)ceilf(p.z) - 1;
+                if (p.x == p.x && p.y == p.y && p.z == p.z && in_grid(m.g, ix, iy, iz)) {
+                    const int64_t sl = m.indexer[lin_id(m.g, ix, iy, iz)];
+                    if (sl >= 0 && m.obs[sl] > m.ignore_th) slot = (int)sl;
+                }
+                rx = __fsub_rn(__fsub_rn(p.x, (float)ix), 0.5f); ry = __fsub_rn(__fsub_rn(p.y, (float)iy), 0.5f); rz = __fsub_rn(__fsub_rn(p.z, (float)iz), 0.5f);
+            }
+            slot_s[t] = slot;
+            s.cat[(96 + 29) * MLP_TP + t] = slot >= 0 ? rx : 0.f;
+            s.cat[(96 + 30) * MLP_TP + t] = slot >= 0 ? ry : 0.f;
+            s.cat[(96 + 31) * MLP_TP + t] = slot >= 0 ? rz : 0.f;
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < MLP_T * 32; idx += MLP_THREADS) {
+            const int t = idx / 32, j = idx % 32;
+            if (j < DIF_L) { const int sl = slot_s[t]; s.cat[(96 + j) * MLP_TP + t] = sl >= 0 ? __ldg(m.latent + (int64_t)sl * DIF_L + j) : 0.f; }
+        }
+        __syncthreads();
+        decoder_forward_tile(P, s);
+        if (threadIdx.x < MLP_T) {
+            const int t = threadIdx.x;
+            const float sdf = tanhf(s.pre[t]);
+            const float sd = 0.05f + 0.5f * softplus_ref(s.pre[MLP_T + t]);
+            const float inv = 1.f / sd;
+            r_s[t] = sdf / sd;                                   // tracker.py:186
+            inv_std_s[t] = inv;
+            s.seed[t] = (1.f - sdf * sdf) * inv;                 // d r / d pre_sdf   (std detached)
+        }
+        __syncthreads();
+        if (want_grad) decoder_backward_tile(P, s, 0);
+        if (threadIdx.x < MLP_T) {
+            const int t = threadIdx.x;
+            const bool valid = slot_s[t] >= 0;
+            float v[29];
+#pragma unroll
+            for (int j = 0; j < 29; ++j) v[j] = 0.f;
+            if (valid) {
+                const float r = r_s[t];
+                float w = 1.f;
+                if (huber_k > 0.f) { const float ar = fabsf(r); if (ar > huber_k) w = huber_k / ar; }       // tracker.py:59-65
+                v[27] = r * (r * w);                             // energy term  (:210)
+                v[28] = 1.f;
+                if (want_grad) {
+                    // G = d r / d p_world = gx / voxel_size ; A = G @ R_last^T as coded (:197-198) ; B = q x A (:199)
+                    const float gx = s.gx[t] / m.g.vs, gy = s.gx[MLP_T + t] / m.g.vs, gz = s.gx[2 * MLP_T + t] / m.g.vs;
+                    float J[6];
+                    J[0] = gx * pose.Rl[0] + gy * pose.Rl[1] + gz * pose.Rl[2];
+                    J[1] = gx * pose.Rl[3] + gy * pose.Rl[4] + gz * pose.Rl[5];
+                    J[2] = gx * pose.Rl[6] + gy * pose.Rl[7] + gz * pose.Rl[8];
+                    const float qx = q_s[t], qy = q_s[MLP_T + t], qz = q_s[2 * MLP_T + t];
+                    J[3] = qy * J[2] - qz * J[1];
+                    J[4] = qz * J[0] - qx * J[2];
+                    J[5] = qx * J[1] - qy * J[0];
+                    int k = 0;
+#pragma unroll
+                    for (int a = 0; a < 6; ++a)
+#pragma unroll
+                        for (int b = a; b < 6; ++b) v[k++] = (w * J[a]) * J[b];       // H = sum (wJ)^T J  (:215)
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) v[21 + a] = J[a] * (r * w);           // g = sum J (w r)    (:216)
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 29; ++j) acc[j] += warp_sum(v[j]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int j = 0; j < 29; ++j) partials[blockIdx.x * ICP_VALS + j] = acc[j];
+        __threadfence();
+        is_last = atomicAdd(done_counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x < 32) {
+        __threadfence();
+        double tot = 0.0;
+        if (threadIdx.x < 29) for (unsigned b = 0; b < gridDim.x; ++b) tot += (double)__ldcg(partials + b * ICP_VALS + threadIdx.x);
+        const double M = __shfl_sync(0xffffffffu, tot, 28);
+        const double scale = M > 0.0 ? 1.0 / M : 0.0;              // error_scale = 1/M (:209)
+        if (threadIdx.x < 21) {
+            int a = 0, rem = threadIdx.x;
+            while (rem >= 6 - a) { rem -= 6 - a; ++a; }
+            const int b = a + rem;
+            out[a * 6 + b] = tot * scale; out[b * 6 + a] = tot * scale;
+        } else if (threadIdx.x < 27) out[36 + threadIdx.x - 21] = tot * scale;
+        else if (threadIdx.x == 27) out[42] = tot * scale;
+        else if (threadIdx.x == 28) out[43] = M;
+        if (threadIdx.x == 0) *done_counter = 0u;
+    }
+}
+
+}  // namespace dif
+
+using namespace dif;
+
+extern "C" {
+
+size_t dif_icp_scratch_bytes(int64_t n) {
+    (void)n;
+    return align_up((size_t)DIF_NUM_SMS * 3 * ICP_VALS * sizeof(float)) + 256;
+}
+
+int dif_icp_linearize(const dif_map_view* map, const void* decoder_prepared, const float* obs_xyz, int64_t n, const float* pose_host,
+                      float huber_k, int want_grad, void* scratch, size_t scratch_sz, double* out_dev, void* stream) {
+    if (!map || !decoder_prepared || !pose_host || !scratch || !out_dev || n < 0 || n >= (int64_t(1) << 31) || (n > 0 && !obs_xyz)) return DIF_E_INVALID;
+    if (scratch_sz < dif_icp_scratch_bytes(n)) return DIF_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    MapRO m{map->indexer, map->latent_vecs, map->voxel_obs_count, make_grid(map), map->ignore_count_th};
+    const float *Rl = pose_host, *tl = pose_host + 9, *Rd = pose_host + 12, *td = pose_host + 21;
+    Pose p;
+    for (int i = 0; i < 3; ++i) {
+        double t = tl[i];
+        for (int j = 0; j < 3; ++j) {
+            double a = 0;
+            for (int k = 0; k < 3; ++k) a += (double)Rl[3 * i + k] * Rd[3 * k + j];
+            p.Rc[3 * i + j] = (float)a;
+            t += (double)Rl[3 * i + j] * td[j];
+        }
+        p.tc[i] = (float)t;
+    }
+    for (int i = 0; i < 9; ++i) { p.Rd[i] = Rd[i]; p.Rl[i] = Rl[i]; }
+    for (int i = 0; i < 3; ++i) p.td[i] = td[i];
+    Carver c(scratch);
+    float* partials = c.take<float>((size_t)DIF_NUM_SMS * 3 * ICP_VALS);
+    unsigned int* counter = c.take<unsigned int>(1);
+    cudaMemsetAsync(counter, 0, sizeof(unsigned int), st);
+    cudaMemsetAsync(out_dev, 0, 44 * sizeof(double), st);
+    const int64_t n_tiles = (n + MLP_T - 1) / MLP_T;
+    int grid = (int)(n_tiles < DIF_NUM_SMS * 3 ? n_tiles : DIF_NUM_SMS * 3);
+    if (grid < 1) grid = 1;
+    const size_t smem = sizeof(DecoderSmem);
+    cudaFuncSetAttribute(icp_linearize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    icp_linearize_kernel<<<grid, MLP_THREADS, smem, st>>>(m, (const float*)decoder_prepared, obs_xyz, (int)n, p, huber_k, want_grad,
+                                                          partials, counter, out_dev);
+    return check_launch("icp_linearize_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,498 @@
+// Sparse PLIVox index: voxelise / prune / allocate / focus / 8-offset gather / fuse, get_sdf lookup, mesh block selection.
+//   replaces reference system/map.py:366-452 (integrate_keyframe stages 1-2), :559-575 (get_sdf lookup),
+//   :627-635 (mesh block selection).  SURVEY rows a-2, a-3, a-4, a-6, a-8, A.1-A.5, A.12.
+//
+// Design: the reference finds unique cells with two sort-based torch.unique calls, eight boolean-mask compactions and
+// two full-grid scratch tensors per frame (map.py:374,383,394,407).  Here the dense grid itself is the sort: cells are
+// marked in a bitmap (1 bit per cell) and an ordered popcount scan hands out slots in ascending linear id, which is
+// exactly the order the reference's sorted unique produces (map.py:383-387,556).  All per-frame scratch is
+// self-cleaning, so no O(grid) memset is paid per frame.  HBM-bound integer work: coalesced point streams, 4/8-byte
+// random lookups into indexer/obs_count, warp-aggregated atomics for compaction.
+#include "mlp_simt.cuh"
+
+namespace dif {
+
+constexpr int CHUNK_WORDS = 1024;            // bitmap words per block in the ordered scan (256 threads x 4 words)
+constexpr int SCAN_THREADS = 256;
+
+enum { CTR_N_SAMPLES = 0, CTR_N_TOUCHED = 1, CTR_BASE_SLOT = 2, CTR_OVERFLOW = 3, CTR_N_NEW = 4, CTR_COUNT = 8 };
+
+struct MapDev {          // by-value copy of dif_map_view for kernels
+    int64_t* indexer; float* latent; int64_t* pos; float* obs; uint8_t* dirty; int32_t* n_occ; int64_t capacity;
+    Grid g; int prune; float ignore_th, enc_th;
+};
+static MapDev to_dev(const dif_map_view* m) {
+    MapDev d; d.indexer = m->indexer; d.latent = m->latent_vecs; d.pos = m->latent_vecs_pos; d.obs = m->voxel_obs_count;
+    d.dirty = m->slot_dirty; d.n_occ = m->n_occupied; d.capacity = m->capacity; d.g = make_grid(m);
+    d.prune = m->prune_min_vox_obs; d.ignore_th = m->ignore_count_th; d.enc_th = m->encoder_count_th;
+    return d;
+}
+
+struct Persist { uint32_t* cell_count; uint32_t* bitmap; uint32_t* slot_cnt; float* slot_sum; };
+static size_t persist_bytes(int64_t n_cells, int64_t capacity) {
+    return align_up(n_cells * 4) + align_up(((n_cells + 31) / 32) * 4) + align_up(capacity * 4) + align_up(capacity * DIF_L * 4);
+}
+static Persist carve_persist(void* p, int64_t n_cells, int64_t capacity) {
+    Carver c(p); Persist r;
+    r.cell_count = c.take<uint32_t>(n_cells); r.bitmap = c.take<uint32_t>((n_cells + 31) / 32);
+    r.slot_cnt = c.take<uint32_t>(capacity); r.slot_sum = c.take<float>(capacity * DIF_L);
+    return r;
+}
+
+struct Scratch { float* p_hat; int32_t* cell; uint8_t* kept; int32_t* s_pt; int32_t* s_slot; uint8_t* s_off; int32_t* touched;
+                 int32_t* chunk_sum; int32_t* ctr; };
+static size_t scratch_bytes(int64_t n, int64_t n_chunks_max) {
+    return align_up(n * 12) + align_up(n * 4) + align_up(n) + 2 * align_up(8 * n * 4) + align_up(8 * n) + align_up(8 * n * 4) +
+           align_up((n_chunks_max + 1) * 4) + align_up(CTR_COUNT * 4);
+}
+static Scratch carve_scratch(void* p, int64_t n, int64_t n_chunks_max) {
+    Carver c(p); Scratch r;
+    r.p_hat = c.take<float>(n * 3); r.cell = c.take<int32_t>(n); r.kept = c.take<uint8_t>(n);
+    r.s_pt = c.take<int32_t>(8 * n); r.s_slot = c.take<int32_t>(8 * n); r.s_off = c.take<uint8_t>(8 * n);
+    r.touched = c.take<int32_t>(8 * n); r.chunk_sum = c.take<int32_t>(n_chunks_max + 1); r.ctr = c.take<int32_t>(CTR_COUNT);
+    return r;
+}
+// the scan needs at most this many chunks whatever the grid: callers size scratch for 2^31 cells / 32 / CHUNK_WORDS
+constexpr int64_t MAX_CHUNKS = (int64_t(1) << 31) / 32 / CHUNK_WORDS;
+
+// ------------------------------------------------------------------------------------------------ K1 voxelise + histogram
+__global__ void voxelize_kernel(MapDev m, const float* __restrict__ xyz, int n, float* __restrict__ p_hat,
+                                int32_t* __restrict__ cell, uint32_t* __restrict__ cell_count, int32_t* __restrict__ stats) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float3 p = normalize_point(m.g, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    p_hat[3 * i] = p.x; p_hat[3 * i + 1] = p.y; p_hat[3 * i + 2] = p.z;
+    // cell = ceil(p) - 1: a point exactly on a face belongs to the lower cell (map.py:368)
+    const int ix = (int)ceilf(p.x) - 1, iy = (int)ceilf(p.y) - 1, iz = (int)ceilf(p.z) - 1;
+    int c = -1;
+    if (p.x == p.x && p.y == p.y && p.z == p.z && in_grid(m.g, ix, iy, iz)) {
+        c = lin_id(m.g, ix, iy, iz);
+        if (m.prune > 0) atomicAdd(cell_count + c, 1u);
+    } else {
+        atomicOr(stats + DIF_STAT_FLAGS, 1);      // the reference does not bounds-check (map.py:313); we drop and flag
+    }
+    cell[i] = c;
+}
+
+// ------------------------------------------------------------------------------------------------ K2 prune + mark new cells
+__device__ __forceinline__ void mark_if_empty(const MapDev& m, uint32_t* bitmap, int ix, int iy, int iz) {
+    const int c = lin_id(m.g, clampi(ix, 0, m.g.nx - 1), clampi(iy, 0, m.g.ny - 1), clampi(iz, 0, m.g.nz - 1));
+    if (m.indexer[c] == -1) atomicOr(bitmap + (c >> 5), 1u << (c & 31));
+}
+
+__global__ void prune_mark_kernel(MapDev m, int n, const int32_t* __restrict__ cell, const uint32_t* __restrict__ cell_count,
+                                  uint8_t* __restrict__ kept, uint8_t* __restrict__ unq_mask, uint32_t* __restrict__ bitmap,
+                                  int32_t* __restrict__ stats) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool k = false;
+    if (i < n) {
+        const int c = cell[i];
+        k = c >= 0 && (m.prune <= 0 || cell_count[c] > (uint32_t)m.prune);      // strict '>' (map.py:375)
+        kept[i] = k;
+        if (unq_mask) unq_mask[i] = k;
+        if (k && m.indexer[c] == -1) {
+            // E = (E0 U N6(E0)) restricted to empty cells, neighbours clamped to the grid (map.py:385-386, :545-557)
+            const int iz = c % m.g.nz, iy = (c / m.g.nz) % m.g.ny, ix = c / (m.g.nz * m.g.ny);
+            atomicOr(bitmap + (c >> 5), 1u << (c & 31));
+            mark_if_empty(m, bitmap, ix - 1, iy, iz); mark_if_empty(m, bitmap, ix + 1, iy, iz);
+            mark_if_empty(m, bitmap, ix, iy - 1, iz); mark_if_empty(m, bitmap, ix, iy + 1, iz);
+            mark_if_empty(m, bitmap, ix, iy, iz - 1); mark_if_empty(m, bitmap, ix, iy, iz + 1);
+        }
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, k);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(stats + DIF_STAT_N_KEPT, __popc(b));
+}
+
+// ------------------------------------------------------------------------------------------------ ordered bitmap scan
+__global__ void bitmap_count_kernel(const uint32_t* __restrict__ bitmap, int64_t n_words, int32_t* __restrict__ chunk_sum) {
+    __shared__ int warp_tot[SCAN_THREADS / 32];
+    const int64_t w0 = (int64_t)blockIdx.x * CHUNK_WORDS + threadIdx.x * 4;
+    int c = 0;
+    if (w0 + 3 < n_words) {
+        const uint4 v = *reinterpret_cast<const uint4*>(bitmap + w0);
+        c = __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+    } else {
+        for (int j = 0; j < 4; ++j) if (w0 + j < n_words) c += __popc(bitmap[w0 + j]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) warp_tot[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int j = 0; j < SCAN_THREADS / 32; ++j) t += warp_tot[j];
+        chunk_sum[blockIdx.x] = t;
+    }
+}
+
+// single block: exclusive scan of chunk sums in place; publishes base slot / total / overflow; bumps n_occupied.
+__global__ void bitmap_scan_kernel(int32_t* __restrict__ chunk_sum, int n_chunks, int32_t* __restrict__ n_occ, int64_t capacity,
+                                   int32_t* __restrict__ ctr, int32_t* __restrict__ stats, int is_alloc) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < n_chunks; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < n_chunks ? chunk_sum[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += u; }
+        if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = warp_tot[threadIdx.x], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, wi, o); if (threadIdx.x >= o) wi += u; }
+            warp_tot[threadIdx.x] = wi - w;
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        if (i < n_chunks) chunk_sum[i] = carry + warp_tot[threadIdx.x >> 5] + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + warp_tot[31] + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const int total = carry_s;
+        if (is_alloc) {
+            const int base_slot = *n_occ;
+            const int overflow = (int64_t)base_slot + total > capacity;
+            ctr[CTR_BASE_SLOT] = base_slot; ctr[CTR_OVERFLOW] = overflow; ctr[CTR_N_NEW] = overflow ? 0 : total;
+            if (!overflow) *n_occ = base_slot + total; else atomicOr(stats + DIF_STAT_FLAGS, 2);
+            stats[DIF_STAT_N_NEW] = overflow ? 0 : total;
+            stats[DIF_STAT_N_OCCUPIED] = overflow ? base_slot : base_slot + total;
+        } else {
+            ctr[CTR_N_NEW] = total;
+        }
+    }
+}
+
+// rank of this thread's first set bit inside the chunk (threads own 4 consecutive words => ascending linear id order)
+__device__ __forceinline__ int block_exclusive_scan(int c, int* warp_tot) {
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += u; }
+    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    int off = 0;
+    for (int j = 0; j < (int)(threadIdx.x >> 5); ++j) off += warp_tot[j];
+    return off + incl - c;
+}
+
+// K3c: hand out slots in ascending linear id (map.py:283,318-319), initialise the new rows (map.py:269-277), clear the bitmap.
+__global__ void alloc_assign_kernel(MapDev m, uint32_t* __restrict__ bitmap, int64_t n_words, const int32_t* __restrict__ chunk_off,
+                                    const int32_t* __restrict__ ctr) {
+    __shared__ int warp_tot[SCAN_THREADS / 32];
+    const int64_t w0 = (int64_t)blockIdx.x * CHUNK_WORDS + threadIdx.x * 4;
+    uint32_t w[4]; int c = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { w[j] = (w0 + j < n_words) ? bitmap[w0 + j] : 0u; c += __popc(w[j]); }
+    int rank = block_exclusive_scan(c, warp_tot);
+    if (c == 0) return;
+    const bool overflow = ctr[CTR_OVERFLOW] != 0;
+    int slot = ctr[CTR_BASE_SLOT] + chunk_off[blockIdx.x] + rank;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t bits = w[j];
+        if (!bits) continue;
+        bitmap[w0 + j] = 0u;
+        while (bits && !overflow) {
+            const int b = __ffs(bits) - 1; bits &= bits - 1;
+            const int64_t lin = (w0 + j) * 32 + b;
+            m.indexer[lin] = slot; m.pos[slot] = lin; m.obs[slot] = 0.f;
+            float* row = m.latent + (int64_t)slot * DIF_L;
+#pragma unroll
+            for (int q = 0; q < DIF_L; ++q) row[q] = 0.f;
+            ++slot;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K4 focus + 8-offset gather
+// T = { cell : allocated and obs_count < encoder_count_th }  (map.py:409-411), evaluated after this call's allocation.
+__device__ __forceinline__ int target_slot(const MapDev& m, int lin) {
+    const int64_t s = m.indexer[lin];
+    return (s >= 0 && m.obs[s] < m.enc_th) ? (int)s : -1;
+}
+
+__global__ void gather_kernel(MapDev m, int n, const float* __restrict__ p_hat, const int32_t* __restrict__ cell,
+                              const uint8_t* __restrict__ kept, uint32_t* __restrict__ cell_count, uint32_t* __restrict__ slot_cnt,
+                              int32_t* __restrict__ s_pt, int32_t* __restrict__ s_slot, uint8_t* __restrict__ s_off,
+                              int32_t* __restrict__ touched, int32_t* __restrict__ ctr, int32_t* __restrict__ stats) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int slots[8]; int cnt = 0; bool focused = false;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) slots[k] = -1;
+    if (i < n) {
+        const int c = cell[i];
+        if (c >= 0) cell_count[c] = 0u;                       // self-clean the histogram (every reader ran in K2)
+        if (kept[i]) {
+            const Grid& g = m.g;
+            const int iz = c % g.nz, iy = (c / g.nz) % g.ny, ix = c / (g.nz * g.ny);
+            // focus mask: primary cell in T U N6(T) (map.py:389-397).  A clamped neighbour of t collapses onto t itself, so
+            // membership is: P in T, or an in-bounds face neighbour of P is in T.
+            focused = target_slot(m, c) >= 0
+                || (ix > 0 && target_slot(m, c - g.nz * g.ny) >= 0) || (ix < g.nx - 1 && target_slot(m, c + g.nz * g.ny) >= 0)
+                || (iy > 0 && target_slot(m, c - g.nz) >= 0) || (iy < g.ny - 1 && target_slot(m, c + g.nz) >= 0)
+                || (iz > 0 && target_slot(m, c - 1) >= 0) || (iz < g.nz - 1 && target_slot(m, c + 1) >= 0);
+            if (focused) {
+                const float px = p_hat[3 * i], py = p_hat[3 * i + 1], pz = p_hat[3 * i + 2];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {                 // offsets in the order of map.py:186-189
+                    const float ox = (k & 4) ? 0.5f : -0.5f, oy = (k & 2) ? 0.5f : -0.5f, oz = (k & 1) ? 0.5f : -0.5f;
+                    const int cx = clampi((int)ceilf(__fadd_rn(px, ox)) - 1, 0, g.nx - 1);
+                    const int cy = clampi((int)ceilf(__fadd_rn(py, oy)) - 1, 0, g.ny - 1);
+                    const int cz = clampi((int)ceilf(__fadd_rn(pz, oz)) - 1, 0, g.nz - 1);
+                    const int s = target_slot(m, lin_id(g, cx, cy, cz));
+                    slots[k] = s;
+                    cnt += s >= 0;
+                }
+            }
+        }
+    }
+    // warp-aggregated reservation in the sample list
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+    const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
+    int base = 0;
+    if (lane == 31 && warp_total) base = atomicAdd(ctr + CTR_N_SAMPLES, warp_total);
+    base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+    const unsigned fb = __ballot_sync(0xffffffffu, focused);
+    if (lane == 0 && fb) atomicAdd(stats + DIF_STAT_N_FOCUSED, __popc(fb));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int s = slots[k];
+        if (s >= 0) {
+            s_pt[base] = i; s_slot[base] = s; s_off[base] = (uint8_t)k; ++base;
+            if (atomicAdd(slot_cnt + s, 1u) == 0u) touched[atomicAdd(ctr + CTR_N_TOUCHED, 1)] = s;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K5 encoder + per-PLIVox sum
+__global__ void __launch_bounds__(MLP_THREADS) encode_accumulate_kernel(
+        MapDev m, const float* __restrict__ encP, const float* __restrict__ p_hat, const float* __restrict__ normal,
+        const int32_t* __restrict__ s_pt, const int32_t* __restrict__ s_slot, const uint8_t* __restrict__ s_off,
+        const int32_t* __restrict__ ctr, float* __restrict__ slot_sum) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    EncoderSmem& s = *reinterpret_cast<EncoderSmem*>(smem_raw);
+    __shared__ int tile_slot[MLP_T];
+    const int n_samples = ctr[CTR_N_SAMPLES];
+    const int n_tiles = (n_samples + MLP_T - 1) / MLP_T;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int base = tile * MLP_T;
+        if (threadIdx.x < MLP_T) {
+            const int t = threadIdx.x, si = base + t;
+            float in[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            int slot = -1;
+            if (si < n_samples) {
+                const int i = s_pt[si], k = s_off[si];
+                slot = s_slot[si];
+                const Grid& g = m.g;
+                const float px = p_hat[3 * i], py = p_hat[3 * i + 1], pz = p_hat[3 * i + 2];
+                const float ox = (k & 4) ? 0.5f : -0.5f, oy = (k & 2) ? 0.5f : -0.5f, oz = (k & 1) ? 0.5f : -0.5f;
+                const float cx = (float)clampi((int)ceilf(__fadd_rn(px, ox)) - 1, 0, g.nx - 1);
+                const float cy = (float)clampi((int)ceilf(__fadd_rn(py, oy)) - 1, 0, g.ny - 1);
+                const float cz = (float)clampi((int)ceilf(__fadd_rn(pz, oz)) - 1, 0, g.nz - 1);
+                // rel = p - cell - 0.5, two separately rounded subtractions as in map.py:425
+                in[0] = __fsub_rn(__fsub_rn(px, cx), 0.5f); in[1] = __fsub_rn(__fsub_rn(py, cy), 0.5f); in[2] = __fsub_rn(__fsub_rn(pz, cz), 0.5f);
+                in[3] = normal[3 * i]; in[4] = normal[3 * i + 1]; in[5] = normal[3 * i + 2];
+            }
+            tile_slot[t] = slot;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) s.in[j * MLP_TP + t] = in[j];
+        }
+        __syncthreads();
+        encoder_forward_tile(encP, s);
+        for (int idx = threadIdx.x; idx < MLP_T * 32; idx += MLP_THREADS) {
+            const int t = idx / 32, j = idx % 32;
+            const int slot = tile_slot[t];
+            if (j < DIF_L && slot >= 0) atomicAdd(slot_sum + (int64_t)slot * DIF_L + j, s.out[j * MLP_TP + t]);
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K6 running-mean fusion
+// latent <- (sum + latent*n)/(n+cnt);  n <- n+cnt  (map.py:449-451), one warp per touched PLIVox; cleans slot_sum/slot_cnt.
+__global__ void fuse_kernel(MapDev m, const int32_t* __restrict__ touched, const int32_t* __restrict__ ctr,
+                            uint32_t* __restrict__ slot_cnt, float* __restrict__ slot_sum, int32_t* __restrict__ stats) {
+    const int n_touched = ctr[CTR_N_TOUCHED];
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { stats[DIF_STAT_N_SAMPLES] = ctr[CTR_N_SAMPLES]; stats[DIF_STAT_N_UPDATED] = n_touched; }
+    for (int w = warp; w < n_touched; w += n_warps) {
+        const int slot = touched[w];
+        const float cnt = (float)slot_cnt[slot];
+        const float n_old = m.obs[slot];
+        const float n_new = __fadd_rn(n_old, cnt);
+        __syncwarp();
+        if (lane < DIF_L) {
+            const int64_t o = (int64_t)slot * DIF_L + lane;
+            const float sum = __fadd_rn(slot_sum[o], __fmul_rn(m.latent[o], n_old));
+            m.latent[o] = __fdiv_rn(sum, n_new);
+            slot_sum[o] = 0.f;
+        }
+        __syncwarp();
+        if (lane == 0) { m.obs[slot] = n_new; slot_cnt[slot] = 0u; if (m.dirty) m.dirty[slot] = 1; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ get_sdf lookup
+__global__ void map_query_kernel(MapDev m, const float* __restrict__ xyz, int n, int32_t* __restrict__ slot_out,
+                                 float* __restrict__ rel_out, int32_t* __restrict__ n_valid) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = false;
+    if (i < n) {
+        const float3 p = normalize_point(m.g, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+        const int ix = (int)ceilf(p.x) - 1, iy = (int)ceilf(p.y) - 1, iz = (int)ceilf(p.z) - 1;
+        int slot = -1;
+        if (p.x == p.x && p.y == p.y && p.z == p.z && in_grid(m.g, ix, iy, iz)) {
+            const int64_t s = m.indexer[lin_id(m.g, ix, iy, iz)];
+            if (s >= 0 && m.obs[s] > m.ignore_th) slot = (int)s;      // strict '>' (map.py:571)
+        }
+        valid = slot >= 0;
+        slot_out[i] = slot;
+        // rel = p - cell - 0.5 (map.py:575)
+        rel_out[3 * i] = __fsub_rn(__fsub_rn(p.x, (float)ix), 0.5f);
+        rel_out[3 * i + 1] = __fsub_rn(__fsub_rn(p.y, (float)iy), 0.5f);
+        rel_out[3 * i + 2] = __fsub_rn(__fsub_rn(p.z, (float)iz), 0.5f);
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, valid);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(n_valid, __popc(b));
+}
+
+// ------------------------------------------------------------------------------------------------ mesh block selection
+__device__ __forceinline__ void mark_if_meshable(const MapDev& m, uint32_t* bitmap, int ix, int iy, int iz) {
+    const int c = lin_id(m.g, clampi(ix, 0, m.g.nx - 1), clampi(iy, 0, m.g.ny - 1), clampi(iz, 0, m.g.nz - 1));
+    const int64_t s = m.indexer[c];
+    if (s >= 0 && m.obs[s] > m.ignore_th) atomicOr(bitmap + (c >> 5), 1u << (c & 31));
+}
+
+__global__ void mesh_mark_kernel(MapDev m, const int32_t* __restrict__ updated, int64_t n_updated, int64_t* __restrict__ focused_out,
+                                 uint32_t* __restrict__ bitmap, int32_t* __restrict__ counts) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t k_total = updated ? n_updated : (int64_t)*m.n_occ;
+    if (i == 0) counts[0] = (int32_t)k_total;
+    if (i >= k_total) return;
+    const int64_t slot = updated ? updated[i] : i;
+    const int64_t c = m.pos[slot];
+    focused_out[i] = c;                                           // map.py:627
+    const int iz = c % m.g.nz, iy = (c / m.g.nz) % m.g.ny, ix = c / ((int64_t)m.g.nz * m.g.ny);
+    mark_if_meshable(m, bitmap, ix, iy, iz);                       // map.py:628-631
+    mark_if_meshable(m, bitmap, ix - 1, iy, iz); mark_if_meshable(m, bitmap, ix + 1, iy, iz);
+    mark_if_meshable(m, bitmap, ix, iy - 1, iz); mark_if_meshable(m, bitmap, ix, iy + 1, iz);
+    mark_if_meshable(m, bitmap, ix, iy, iz - 1); mark_if_meshable(m, bitmap, ix, iy, iz + 1);
+}
+
+__global__ void mesh_assign_kernel(MapDev m, uint32_t* __restrict__ bitmap, int64_t n_words, const int32_t* __restrict__ chunk_off,
+                                   const int32_t* __restrict__ ctr, int32_t* __restrict__ block_slots, int32_t* __restrict__ mapping,
+                                   int32_t* __restrict__ counts) {
+    __shared__ int warp_tot[SCAN_THREADS / 32];
+    if (blockIdx.x == 0 && threadIdx.x == 0) counts[1] = ctr[CTR_N_NEW];
+    const int64_t w0 = (int64_t)blockIdx.x * CHUNK_WORDS + threadIdx.x * 4;
+    uint32_t w[4]; int c = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { w[j] = (w0 + j < n_words) ? bitmap[w0 + j] : 0u; c += __popc(w[j]); }
+    int rank = block_exclusive_scan(c, warp_tot);
+    if (c == 0) return;
+    int b_idx = chunk_off[blockIdx.x] + rank;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t bits = w[j];
+        if (!bits) continue;
+        bitmap[w0 + j] = 0u;
+        while (bits) {
+            const int b = __ffs(bits) - 1; bits &= bits - 1;
+            const int slot = (int)m.indexer[(w0 + j) * 32 + b];
+            block_slots[b_idx] = slot; mapping[slot] = b_idx;      // map.py:633-635
+            ++b_idx;
+        }
+    }
+}
+
+}  // namespace dif
+
+using namespace dif;
+
+extern "C" {
+
+size_t dif_integrate_persist_bytes(int64_t n_cells, int64_t capacity) { return persist_bytes(n_cells, capacity); }
+size_t dif_integrate_scratch_bytes(int64_t max_points) { return scratch_bytes(max_points > 0 ? max_points : 1, MAX_CHUNKS); }
+
+int dif_integrate(const dif_map_view* map, const void* encoder_prepared, const float* xyz, const float* normal, int64_t n,
+                  uint8_t* unq_mask, void* persist, size_t persist_sz, void* scratch, size_t scratch_sz, int32_t* stats_dev, void* stream) {
+    if (!map || !encoder_prepared || !persist || !scratch || !stats_dev || n < 0 || n >= (int64_t(1) << 27)) return DIF_E_INVALID;
+    const MapDev m = to_dev(map);
+    const int64_t n_cells = m.g.cells();
+    if (n_cells <= 0 || n_cells >= (int64_t(1) << 31)) return DIF_E_INVALID;
+    if (persist_sz < persist_bytes(n_cells, m.capacity) || scratch_sz < scratch_bytes(n > 0 ? n : 1, MAX_CHUNKS)) return DIF_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const Persist P = carve_persist(persist, n_cells, m.capacity);
+    const Scratch S = carve_scratch(scratch, n > 0 ? n : 1, MAX_CHUNKS);
+    const int64_t n_words = (n_cells + 31) / 32;
+    const int n_chunks = (int)((n_words + CHUNK_WORDS - 1) / CHUNK_WORDS);
+    cudaMemsetAsync(S.ctr, 0, CTR_COUNT * sizeof(int32_t), st);
+    cudaMemsetAsync(stats_dev, 0, DIF_STAT_COUNT * sizeof(int32_t), st);
+    const int nb = (int)((n + 255) / 256);
+    if (n > 0) {
+        voxelize_kernel<<<nb, 256, 0, st>>>(m, xyz, (int)n, S.p_hat, S.cell, P.cell_count, stats_dev);
+        prune_mark_kernel<<<nb, 256, 0, st>>>(m, (int)n, S.cell, P.cell_count, S.kept, unq_mask, P.bitmap, stats_dev);
+    }
+    bitmap_count_kernel<<<n_chunks, SCAN_THREADS, 0, st>>>(P.bitmap, n_words, S.chunk_sum);
+    bitmap_scan_kernel<<<1, 1024, 0, st>>>(S.chunk_sum, n_chunks, m.n_occ, m.capacity, S.ctr, stats_dev, 1);
+    alloc_assign_kernel<<<n_chunks, SCAN_THREADS, 0, st>>>(m, P.bitmap, n_words, S.chunk_sum, S.ctr);
+    if (n > 0) {
+        gather_kernel<<<nb, 256, 0, st>>>(m, (int)n, S.p_hat, S.cell, S.kept, P.cell_count, P.slot_cnt, S.s_pt, S.s_slot, S.s_off,
+                                          S.touched, S.ctr, stats_dev);
+        const size_t smem = sizeof(EncoderSmem);
+        cudaFuncSetAttribute(encode_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const int64_t max_tiles = (8 * n + MLP_T - 1) / MLP_T;
+        const int grid = (int)(max_tiles < DIF_NUM_SMS * 4 ? max_tiles : DIF_NUM_SMS * 4);
+        encode_accumulate_kernel<<<grid, MLP_THREADS, smem, st>>>(m, (const float*)encoder_prepared, S.p_hat, normal, S.s_pt, S.s_slot,
+                                                                  S.s_off, S.ctr, P.slot_sum);
+        fuse_kernel<<<DIF_NUM_SMS * 2, 256, 0, st>>>(m, S.touched, S.ctr, P.slot_cnt, P.slot_sum, stats_dev);
+    }
+    return check_launch("dif_integrate");
+}
+
+int dif_map_query(const dif_map_view* map, const float* xyz, int64_t n, int32_t* slot_out, float* rel_out, int32_t* n_valid_dev, void* stream) {
+    if (!map || n < 0 || n >= (int64_t(1) << 31) || !n_valid_dev || (n > 0 && (!xyz || !slot_out || !rel_out))) return DIF_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(n_valid_dev, 0, sizeof(int32_t), st);
+    if (n > 0) map_query_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(to_dev(map), xyz, (int)n, slot_out, rel_out, n_valid_dev);
+    return check_launch("dif_map_query");
+}
+
+size_t dif_mesh_select_scratch_bytes(int64_t n_cells, int64_t capacity) {
+    (void)capacity;
+    return align_up(((n_cells + 31) / 32) * 4) + align_up((MAX_CHUNKS + 1) * 4) + align_up(CTR_COUNT * 4);
+}
+
+int dif_mesh_select(const dif_map_view* map, const int32_t* updated_slots, int64_t n_updated, int64_t* focused_ids_out,
+                    int32_t* block_slots_out, int32_t* mapping_out, int32_t* counts_dev, void* persist, size_t persist_sz, void* stream) {
+    if (!map || !focused_ids_out || !block_slots_out || !mapping_out || !counts_dev || !persist || n_updated < 0) return DIF_E_INVALID;
+    const MapDev m = to_dev(map);
+    const int64_t n_cells = m.g.cells();
+    if (persist_sz < dif_mesh_select_scratch_bytes(n_cells, m.capacity)) return DIF_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    Carver c(persist);
+    const int64_t n_words = (n_cells + 31) / 32;
+    uint32_t* bitmap = c.take<uint32_t>(n_words);                 // zero on entry, zero on exit
+    int32_t* chunk_sum = c.take<int32_t>(MAX_CHUNKS + 1);
+    int32_t* ctr = c.take<int32_t>(CTR_COUNT);
+    const int n_chunks = (int)((n_words + CHUNK_WORDS - 1) / CHUNK_WORDS);
+    cudaMemsetAsync(mapping_out, 0xFF, (size_t)m.capacity * sizeof(int32_t), st);
+    cudaMemsetAsync(counts_dev, 0, 2 * sizeof(int32_t), st);
+    const int64_t k_max = updated_slots ? n_updated : m.capacity;
+    if (k_max > 0) mesh_mark_kernel<<<(int)((k_max + 255) / 256), 256, 0, st>>>(m, updated_slots, n_updated, focused_ids_out, bitmap, counts_dev);
+    bitmap_count_kernel<<<n_chunks, SCAN_THREADS, 0, st>>>(bitmap, n_words, chunk_sum);
+    bitmap_scan_kernel<<<1, 1024, 0, st>>>(chunk_sum, n_chunks, m.n_occ, m.capacity, ctr, counts_dev, 0);
+    mesh_assign_kernel<<<n_chunks, SCAN_THREADS, 0, st>>>(m, bitmap, n_words, chunk_sum, ctr, block_slots_out, mapping_out, counts_dev);
+    return check_launch("dif_mesh_select");
+}
+
+}  // extern "C"

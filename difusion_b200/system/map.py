@@ -1,0 +1,444 @@
+"""``DenseIndexedMap`` - host-side mirror of the reference's sparse PLIVox latent map (reference system/map.py:158-723)
+for the fusion hot path: ``integrate_keyframe``, ``get_sdf``, ``extract_mesh``, ``save``/``load``, ``allocate_block`` and
+the public state attributes.  Same constructor, method names, argument meaning and return values, so it drops into the
+reference's SLAM loop (main.py:71-94); every computation is a call into libdifusion_b200.so (C ABI,
+include/difusion_b200.h) on the current CUDA stream.  There is no torch/CPU fallback path.
+
+Deliberate differences (documented in DESIGN.md):
+  * latent buffers are physically pre-sized (power-of-two, grown by doubling) while the public ``latent_vecs`` /
+    ``latent_vecs_pos`` / ``voxel_obs_count`` / ``voxel_optimized`` views keep the reference's capacity rule
+    (smallest power of two >= n_occupied, map.py:263-281) so shapes match the reference exactly;
+  * ``n_occupied`` lives on the device; the host value is fetched lazily (the reference syncs ~25 times per integrate);
+  * points outside the grid are dropped and reported (IndexError at the next host sync) instead of indexing out of
+    range (map.py:313 "will not check index overflow");
+  * the disabled latent-optimisation branch (do_optimize, map.py:456-516, never enabled by main.py:85-86) is not built.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import logging
+import threading
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..network import utility as net_util
+from . import ext as _ext
+
+LATENT_DIM = 29
+
+
+def _next_pow2(v: int) -> int:
+    p = 1
+    while p < v:
+        p *= 2
+    return p
+
+
+class MeshExtractCache:                                  # reference map.py:116-133
+    def __init__(self, owner):
+        self._owner = owner
+        self.vertices = None
+        self.vertices_flatten_id = None
+        self.vertices_std = None
+        self.device = owner.device
+
+    @property
+    def updated_vec_id(self) -> torch.Tensor:
+        """Sorted unique ids of PLIVoxes fused since the last extraction (map.py:303-308); kept as per-slot flags on the device."""
+        o = self._owner
+        return torch.nonzero(o._dirty[:o.n_occupied]).flatten()
+
+    def clear_updated_vec(self):
+        self._owner._dirty.zero_()
+
+    def clear_all(self):
+        self.vertices = None
+        self.vertices_flatten_id = None
+        self.vertices_std = None
+        self.clear_updated_vec()
+
+
+class TriangleMesh:
+    """What extract_mesh returns (the reference builds an open3d TriangleMesh, map.py:521-543; open3d is a GUI
+    dependency outside the hot path).  Fields mirror what the reference fills in."""
+
+    def __init__(self, vertices: np.ndarray, vertex_std: np.ndarray):
+        self.vertices = vertices.reshape(-1, 3).astype(float)
+        self.triangles = np.arange(self.vertices.shape[0], dtype=np.int32).reshape(-1, 3)
+        self.vertex_std = vertex_std.reshape(-1).astype(float)
+
+    def has_triangles(self):
+        return self.triangles.shape[0] > 0
+
+
+class DenseIndexedMap:
+    STATUS_CONF_BIT = 1 << 0
+    STATUS_SURF_BIT = 1 << 1
+
+    def __init__(self, model, args: argparse.Namespace, latent_dim: int, device: torch.device, enable_async: bool = False,
+                 optimization_device: torch.device = None, initial_capacity: int = 1 << 16):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise _lib.DifusionLibraryError("DenseIndexedMap needs a CUDA device: difusion_b200 has no CPU fallback")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        if latent_dim != LATENT_DIM:
+            raise ValueError(f"the kernels are built for latent_dim={LATENT_DIM} (ckpt/default/hyper.json)")
+        self._L = _lib.lib()
+        self.model = model
+        self.model.eval()
+        self._prep = net_util.prepared_for(model, device)
+        self.voxel_size = args.voxel_size
+        self.n_xyz = np.ceil((np.asarray(args.bound_max) - np.asarray(args.bound_min)) / args.voxel_size).astype(int).tolist()
+        logging.info(f"Map size Nx = {self.n_xyz[0]}, Ny = {self.n_xyz[1]}, Nz = {self.n_xyz[2]}")
+        self.args = args
+        self.bound_min = torch.tensor(args.bound_min, device=device).float()
+        self.bound_max = self.bound_min + self.voxel_size * torch.tensor(self.n_xyz, device=device)
+        self.latent_dim = latent_dim
+        self.device = device
+        self.extract_mesh_std_range = None
+        self._n_cells = int(np.prod(self.n_xyz))
+        if self._n_cells >= 2 ** 31:
+            raise ValueError("grid too large for 32-bit linear ids")
+
+        with torch.cuda.device(device):
+            self._indexer = torch.full((self._n_cells,), -1, dtype=torch.long, device=device)
+            self._n_occ_dev = torch.zeros(1, dtype=torch.int32, device=device)
+            self._stats_dev = torch.zeros(_lib.DIF_STAT_COUNT, dtype=torch.int32, device=device)
+            self._stats_host = torch.zeros(_lib.DIF_STAT_COUNT, dtype=torch.int32).pin_memory()
+        self._stats_event = torch.cuda.Event()
+        self._stats_pending = False
+        self._n_occ_host = 0
+        self._n_occ_ub = 0
+        self._cap_phys = 0
+        self._latent = self._pos = self._obs = self._optimized = self._dirty = None
+        self._persist = None
+        self._scratch = None
+        self._scratch_points = 0
+        self._mesh_persist = None
+        self._icp_scratch = None
+        self._icp_out = None
+        self._grow(max(1, _next_pow2(int(initial_capacity))))
+
+        self.modifying_lock = threading.Lock()
+        self.meshing_thread = None
+        self.meshing_thread_id = -1
+        self.meshing_stream = torch.cuda.Stream(device=device)
+        self.mesh_cache = MeshExtractCache(self)
+        self.last_integrate_stats = None
+
+    # ------------------------------------------------------------------ state (reference cold_vars, map.py:199-211)
+    def _grow(self, new_cap: int):
+        dev = self.device
+        with torch.cuda.device(dev):
+            lat = torch.zeros((new_cap, LATENT_DIM), dtype=torch.float32, device=dev)
+            pos = torch.full((new_cap,), -1, dtype=torch.long, device=dev)
+            obs = torch.zeros((new_cap,), dtype=torch.float32, device=dev)
+            opt = torch.zeros((new_cap,), dtype=torch.bool, device=dev)
+            dirty = torch.zeros((new_cap,), dtype=torch.uint8, device=dev)
+            if self._cap_phys:
+                c = self._cap_phys
+                lat[:c], pos[:c], obs[:c], opt[:c], dirty[:c] = self._latent, self._pos, self._obs, self._optimized, self._dirty
+            self._latent, self._pos, self._obs, self._optimized, self._dirty = lat, pos, obs, opt, dirty
+            self._cap_phys = new_cap
+            self._persist = torch.zeros(self._L.dif_integrate_persist_bytes(self._n_cells, new_cap), dtype=torch.uint8, device=dev)
+
+    def _sync_stats(self):
+        if self._stats_pending:
+            self._stats_event.synchronize()
+            self._stats_pending = False
+            st = self._stats_host.tolist()
+            self._n_occ_host = st[_lib.STAT_N_OCCUPIED]
+            self._n_occ_ub = self._n_occ_host
+            self.last_integrate_stats = dict(n_kept=st[0], n_new=st[1], n_samples=st[2], n_updated=st[3], n_occupied=st[4],
+                                             flags=st[5], n_focused=st[6])
+            if st[_lib.STAT_FLAGS] & 2:
+                raise RuntimeError("PLIVox capacity exhausted inside dif_integrate (internal sizing error)")
+            if st[_lib.STAT_FLAGS] & 1:
+                raise IndexError("integrate_keyframe: surface points outside the map bounds were dropped "
+                                 "(the reference indexes out of range here, map.py:313)")
+
+    @property
+    def n_occupied(self) -> int:
+        self._sync_stats()
+        return self._n_occ_host
+
+    @n_occupied.setter
+    def n_occupied(self, v: int):
+        self._sync_stats()
+        self._n_occ_host = self._n_occ_ub = int(v)
+        self._n_occ_dev.fill_(int(v))
+
+    def _cap_ref(self) -> int:
+        return max(1, _next_pow2(self.n_occupied))         # the reference's doubling rule, map.py:266-268
+
+    indexer = property(lambda self: self._indexer)
+    latent_vecs = property(lambda self: self._latent[:self._cap_ref()])
+    latent_vecs_pos = property(lambda self: self._pos[:self._cap_ref()])
+    voxel_obs_count = property(lambda self: self._obs[:self._cap_ref()])
+    voxel_optimized = property(lambda self: self._optimized[:self._cap_ref()])
+
+    @property
+    def cold_vars(self) -> dict:
+        return {"n_occupied": self.n_occupied, "indexer": self.indexer, "latent_vecs": self.latent_vecs,
+                "latent_vecs_pos": self.latent_vecs_pos, "voxel_obs_count": self.voxel_obs_count,
+                "voxel_optimized": self.voxel_optimized}
+
+    def save(self, path):                                   # map.py:239-243, same on-disk dict
+        with Path(path).open("wb") as f:
+            torch.save({k: (v.clone() if torch.is_tensor(v) else v) for k, v in self.cold_vars.items()}, f)
+
+    def load(self, path):                                   # map.py:245-249
+        with Path(path).open("rb") as f:
+            cv = torch.load(f, map_location=self.device)
+        n = int(cv["n_occupied"])
+        assert cv["indexer"].numel() == self._n_cells, "map bounds differ from the saved map"
+        if n > self._cap_phys:
+            self._grow(_next_pow2(n))
+        c = cv["latent_vecs"].size(0)
+        self._indexer.copy_(cv["indexer"])
+        self._latent.zero_(); self._pos.fill_(-1); self._obs.zero_(); self._optimized.zero_(); self._dirty.zero_()
+        self._latent[:c], self._pos[:c], self._obs[:c], self._optimized[:c] = cv["latent_vecs"], cv["latent_vecs_pos"], \
+            cv["voxel_obs_count"], cv["voxel_optimized"]
+        self.n_occupied = n
+
+    def _view(self) -> _lib.MapView:
+        a = self.args
+        v = _lib.MapView()
+        v.indexer, v.latent_vecs, v.latent_vecs_pos = self._indexer.data_ptr(), self._latent.data_ptr(), self._pos.data_ptr()
+        v.voxel_obs_count, v.slot_dirty, v.n_occupied = self._obs.data_ptr(), self._dirty.data_ptr(), self._n_occ_dev.data_ptr()
+        v.capacity = self._cap_phys
+        v.nx, v.ny, v.nz = self.n_xyz
+        bm = np.asarray(a.bound_min, dtype=np.float32)
+        v.bound_min[0], v.bound_min[1], v.bound_min[2] = float(bm[0]), float(bm[1]), float(bm[2])
+        v.voxel_size = float(np.float32(a.voxel_size))
+        v.prune_min_vox_obs = int(a.prune_min_vox_obs)
+        v.ignore_count_th = float(a.ignore_count_th)
+        v.encoder_count_th = float(a.encoder_count_th)
+        return v
+
+    # ------------------------------------------------------------------ addressing helpers (map.py:287-319)
+    def _linearize_id(self, xyz: torch.Tensor):
+        return xyz[:, 2] + self.n_xyz[-1] * xyz[:, 1] + (self.n_xyz[-1] * self.n_xyz[-2]) * xyz[:, 0]
+
+    def _unlinearize_id(self, idx: torch.Tensor):
+        return torch.stack([idx // (self.n_xyz[1] * self.n_xyz[2]), (idx // self.n_xyz[2]) % self.n_xyz[1], idx % self.n_xyz[2]], dim=-1)
+
+    def allocate_block(self, idx: torch.Tensor):
+        """map.py:310-319: append slots for the given (N,3) or (N,) cell ids in the given order (host-driven, rarely used)."""
+        if idx.ndimension() == 2 and idx.size(1) == 3:
+            idx = self._linearize_id(idx)
+        n0, k = self.n_occupied, idx.size(0)
+        if n0 + k > self._cap_phys:
+            self._grow(_next_pow2(n0 + k))
+        new_id = torch.arange(n0, n0 + k, device=self.device, dtype=torch.long)
+        self._pos[new_id] = idx
+        self._indexer[idx] = new_id
+        self.n_occupied = n0 + k
+
+    # ------------------------------------------------------------------ integrate (map.py:340-519)
+    def integrate_keyframe(self, surface_xyz: torch.Tensor, surface_normal: torch.Tensor, do_optimize: bool = False,
+                           async_optimize: bool = False):
+        assert surface_xyz.device == surface_normal.device == self.device, \
+            f"Device of map {self.device} and input observation {surface_xyz.device, surface_normal.device} must be the same."
+        if do_optimize and getattr(self.args, "optim_n_iters", 0) > 0:
+            raise NotImplementedError("latent optimisation (map.py:456-516) is outside the hot path and not built")
+        xyz = surface_xyz.detach().contiguous().float()
+        nrm = surface_normal.detach().contiguous().float()
+        n = xyz.size(0)
+        with self.modifying_lock:
+            # capacity: a call allocates at most 7 cells per point (own cell + 6 face neighbours)
+            ub = self._n_occ_ub + min(7 * n, self._n_cells)
+            if ub > self._cap_phys:
+                self._sync_stats()
+                ub = self._n_occ_host + min(7 * n, self._n_cells - self._n_occ_host)
+                if ub > self._cap_phys:
+                    torch.cuda.current_stream(self.device).synchronize()
+                    self._grow(_next_pow2(ub))
+            self._n_occ_ub = ub
+            if n > self._scratch_points:
+                self._scratch_points = max(n, 1 << 15)
+                self._scratch = torch.empty(self._L.dif_integrate_scratch_bytes(self._scratch_points), dtype=torch.uint8, device=self.device)
+            prune = self.args.prune_min_vox_obs > 0
+            unq = torch.empty(n, dtype=torch.uint8, device=self.device) if prune else None
+            view = self._view()
+            st = _lib.stream_ptr(self.device)
+            _lib.check(self._L.dif_integrate(ctypes.byref(view), self._prep.encoder.data_ptr(), xyz.data_ptr(), nrm.data_ptr(), n,
+                                             _lib.ptr(unq), self._persist.data_ptr(), self._persist.numel(), self._scratch.data_ptr(),
+                                             self._scratch.numel(), self._stats_dev.data_ptr(), st), "dif_integrate")
+            self._stats_host.copy_(self._stats_dev, non_blocking=True)
+            self._stats_event.record(torch.cuda.current_stream(self.device))
+            self._stats_pending = True
+        return unq.view(torch.bool) if prune else None
+
+    # ------------------------------------------------------------------ get_sdf (map.py:559-579)
+    def get_sdf(self, xyz: torch.Tensor):
+        """sdf (M,), std (M,), valid_mask (N,) - differentiable wrt ``xyz`` (the tracker calls autograd.grad on it)."""
+        sdf, std, valid = _GetSdfFn.apply(xyz, self)
+        return sdf, std, valid
+
+    def _query(self, xyz: torch.Tensor):
+        x = xyz.detach().contiguous().float()
+        n = x.size(0)
+        slot = torch.empty(n, dtype=torch.int32, device=self.device)
+        rel = torch.empty((n, 3), dtype=torch.float32, device=self.device)
+        nv = torch.empty(1, dtype=torch.int32, device=self.device)
+        view = self._view()
+        _lib.check(self._L.dif_map_query(ctypes.byref(view), x.data_ptr(), n, slot.data_ptr(), rel.data_ptr(), nv.data_ptr(),
+                                         _lib.stream_ptr(self.device)), "dif_map_query")
+        return slot, rel
+
+    # ------------------------------------------------------------------ fused ICP linearisation (tracker.py:174-218)
+    def icp_linearize(self, obs_xyz: torch.Tensor, R_last, t_last, R_delta, t_delta, huber_k: float = 5.0, want_grad: bool = True):
+        """One launch: returns a pinned-host-bound device tensor out[44] (fp64): H[36], g[6], energy, M."""
+        x = obs_xyz.detach().contiguous().float()
+        n = x.size(0)
+        if self._icp_scratch is None:
+            self._icp_scratch = torch.empty(self._L.dif_icp_scratch_bytes(n), dtype=torch.uint8, device=self.device)
+        out = torch.empty(44, dtype=torch.float64, device=self.device)
+        pose = (ctypes.c_float * 24)(*np.concatenate([np.asarray(R_last, np.float64).ravel(), np.asarray(t_last, np.float64).ravel(),
+                                                      np.asarray(R_delta, np.float64).ravel(), np.asarray(t_delta, np.float64).ravel()]).astype(np.float32).tolist())
+        view = self._view()
+        _lib.check(self._L.dif_icp_linearize(ctypes.byref(view), self._prep.decoder.data_ptr(), x.data_ptr(), n, pose,
+                                             float(huber_k) if huber_k else 0.0, int(want_grad), self._icp_scratch.data_ptr(),
+                                             self._icp_scratch.numel(), out.data_ptr(), _lib.stream_ptr(self.device)), "dif_icp_linearize")
+        return out
+
+    # ------------------------------------------------------------------ mesh extraction (map.py:581-723)
+    def _make_mesh_from_cache(self):
+        if self.mesh_cache.vertices is None:
+            return TriangleMesh(np.zeros((0, 3, 3), np.float32), np.zeros((0, 3), np.float32))
+        return TriangleMesh(self.mesh_cache.vertices, self.mesh_cache.vertices_std)
+
+    def mesh_cubes(self, voxel_resolution: int, fast: bool = True, updated_vec_id: torch.Tensor = None):
+        """Stages map.py:627-687 on the device: returns (focused_flatten_id (K,), vec_id_batch_mapping (cap,), high_sdf, high_std
+        (B,2r,2r,2r) [sdf already negated], block_slots (B,), counts dict).  updated_vec_id None == all occupied PLIVoxes."""
+        dev, L = self.device, self._L
+        st = _lib.stream_ptr(dev)
+        view = self._view()
+        if self._mesh_persist is None:
+            self._mesh_persist = torch.zeros(L.dif_mesh_select_scratch_bytes(self._n_cells, self._cap_phys), dtype=torch.uint8, device=dev)
+        k_max = self._cap_phys if updated_vec_id is None else int(updated_vec_id.numel())
+        upd = None if updated_vec_id is None else updated_vec_id.to(torch.int32).contiguous()
+        focused = torch.empty(max(k_max, 1), dtype=torch.long, device=dev)
+        block_slots = torch.empty(min(self._cap_phys, 7 * max(k_max, 1)), dtype=torch.int32, device=dev)
+        mapping = torch.empty(self._cap_phys, dtype=torch.int32, device=dev)
+        counts = torch.zeros(2, dtype=torch.int32, device=dev)
+        _lib.check(L.dif_mesh_select(ctypes.byref(view), _lib.ptr(upd), 0 if upd is None else upd.numel(), focused.data_ptr(),
+                                     block_slots.data_ptr(), mapping.data_ptr(), counts.data_ptr(), self._mesh_persist.data_ptr(),
+                                     self._mesh_persist.numel(), st), "dif_mesh_select")
+        K, B = counts.tolist()                               # host sync: output shapes depend on it
+        r = int(voxel_resolution)
+        hr = 2 * r
+        cube_sdf = torch.empty((B, hr, hr, hr), dtype=torch.float32, device=dev)
+        cube_std = torch.empty((B, hr, hr, hr), dtype=torch.float32, device=dev)
+        scratch = torch.empty(max(L.dif_mesh_decode_scratch_bytes(B, r), 256), dtype=torch.uint8, device=dev)
+        dcounts = torch.zeros(2, dtype=torch.int32, device=dev)
+        _lib.check(L.dif_mesh_decode(ctypes.byref(view), self._prep.decoder.data_ptr(), block_slots.data_ptr(), B, r, int(bool(fast)),
+                                     cube_sdf.data_ptr(), cube_std.data_ptr(), scratch.data_ptr(), scratch.numel(), dcounts.data_ptr(), st),
+                   "dif_mesh_decode")
+        return focused[:K], mapping, cube_sdf, cube_std, block_slots[:B], dcounts
+
+    def extract_mesh(self, voxel_resolution: int, max_n_triangles: int, fast: bool = True, max_std: float = 2000.0,
+                     extract_async: bool = False, no_cache: bool = False, interpolate: bool = True):
+        if not interpolate:
+            raise NotImplementedError("interpolate=False calls system.ext.marching_cubes, which the reference does not export "
+                                      "(map.py:693 vs ext/__init__.py:19)")
+        if self.meshing_thread is not None:                 # map.py:597-607
+            if not self.meshing_thread.is_alive():
+                self.meshing_thread = None
+                self.meshing_thread_id = -1
+                return self._make_mesh_from_cache()
+            elif not extract_async:
+                self.meshing_thread.join()
+                return self._make_mesh_from_cache()
+            else:
+                return None
+
+        with self.modifying_lock:                           # map.py:609-622
+            if no_cache:
+                updated = None
+                self.mesh_cache.clear_all()
+            else:
+                updated = self.mesh_cache.updated_vec_id
+                if updated.size(0) == 0:
+                    return self._make_mesh_from_cache() if not extract_async else None
+                self.mesh_cache.clear_updated_vec()
+            self._sync_stats()
+
+        def do_meshing(res):
+            torch.cuda.synchronize(self.device)
+            with torch.cuda.stream(self.meshing_stream):
+                focused, mapping, cube_sdf, cube_std, _, _ = self.mesh_cubes(res, fast, updated)
+                if cube_sdf.size(0) == 0:
+                    return
+                vertices, vertices_flatten_id, vertices_std = _ext.marching_cubes_interp(
+                    self.indexer.view(self.n_xyz), focused, mapping, cube_sdf, cube_std, max_n_triangles, self.n_xyz, max_std)
+                vertices = vertices * self.voxel_size + self.bound_min          # map.py:698
+                vertices = vertices.cpu().numpy()
+                vertices_std = vertices_std.cpu().numpy()
+                vertices_flatten_id = vertices_flatten_id.cpu().numpy()
+                c = self.mesh_cache
+                if c.vertices is None:
+                    c.vertices, c.vertices_flatten_id, c.vertices_std = vertices, vertices_flatten_id, vertices_std
+                else:                                        # map.py:708-714: drop cached triangles of re-meshed PLIVoxes
+                    keep = ~np.isin(c.vertices_flatten_id, np.unique(vertices_flatten_id))
+                    c.vertices = np.concatenate([c.vertices[keep], vertices], axis=0)
+                    c.vertices_flatten_id = np.concatenate([c.vertices_flatten_id[keep], vertices_flatten_id], axis=0)
+                    c.vertices_std = np.concatenate([c.vertices_std[keep], vertices_std], axis=0)
+
+        if extract_async:
+            self.meshing_thread = threading.Thread(target=do_meshing, args=(voxel_resolution,), daemon=True)
+            self.meshing_thread.start()
+            self.meshing_thread_id = self.meshing_thread.ident
+            return None
+        do_meshing(voxel_resolution)
+        return self._make_mesh_from_cache()
+
+
+class _GetSdfFn(torch.autograd.Function):
+    """map.py:559-579 as one differentiable op: lookup kernel -> compaction -> decoder forward(+backward) kernel.
+    backward: d/dxyz_world = (g_sdf * dsdf/drel + g_std * dstd/drel) / voxel_size, zero rows for invalid points."""
+
+    @staticmethod
+    def forward(ctx, xyz, m: DenseIndexedMap):
+        slot, rel = m._query(xyz)
+        valid = slot >= 0
+        idx = torch.nonzero(valid).flatten()                # host sync, as in the reference's boolean-mask indexing
+        M = idx.numel()
+        assert M > 0                                        # the reference asserts on an empty batch (utility.py:84-85)
+        rows = slot[idx].contiguous()
+        x = rel[idx].contiguous()
+        dev = xyz.device
+        sdf = torch.empty(M, dtype=torch.float32, device=dev)
+        std = torch.empty(M, dtype=torch.float32, device=dev)
+        need = xyz.requires_grad
+        g = torch.empty((M, 3), dtype=torch.float32, device=dev) if need else None
+        _lib.check(m._L.dif_decode(m._prep.decoder.data_ptr(), m._latent.data_ptr(), rows.data_ptr(), x.data_ptr(), M, None, 1.0,
+                                   sdf.data_ptr(), std.data_ptr(), _lib.ptr(g), None, _lib.stream_ptr(dev)), "dif_decode")
+        ctx.m, ctx.n = m, xyz.size(0)
+        ctx.save_for_backward(idx, rows, x, g if need else torch.empty(0, device=dev))
+        ctx.mark_non_differentiable(valid)
+        return sdf, std, valid
+
+    @staticmethod
+    def backward(ctx, g_sdf, g_std, _g_valid):
+        idx, rows, x, dsdf = ctx.saved_tensors
+        if dsdf.numel() == 0:
+            return None, None
+        m = ctx.m
+        grad_rel = g_sdf.unsqueeze(-1) * dsdf
+        if g_std is not None and bool((g_std != 0).any()):
+            M = x.size(0)
+            s0 = torch.empty(M, dtype=torch.float32, device=x.device); s1 = torch.empty_like(s0)
+            g0 = torch.empty((M, 3), dtype=torch.float32, device=x.device); g1 = torch.empty_like(g0)
+            _lib.check(m._L.dif_decode(m._prep.decoder.data_ptr(), m._latent.data_ptr(), rows.data_ptr(), x.data_ptr(), M, None, 1.0,
+                                       s0.data_ptr(), s1.data_ptr(), g0.data_ptr(), g1.data_ptr(), _lib.stream_ptr(x.device)), "dif_decode")
+            grad_rel = grad_rel + g_std.unsqueeze(-1) * g1
+        grad = torch.zeros((ctx.n, 3), dtype=torch.float32, device=x.device)
+        grad[idx] = grad_rel / m.voxel_size
+        return grad, None

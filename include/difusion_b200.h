@@ -1,0 +1,161 @@
+/* difusion_b200 - C ABI of the B200-native DI-Fusion hot path (libdifusion_b200.so, sm_100a).
+ *
+ * This is the drop-in boundary for the reference's per-frame fusion path.  The reference
+ * (huangjh-pub/di-fusion, paths below relative to its pytorch/ directory) implements that path as
+ * chains of torch ops inside system/map.py + system/tracker.py plus two pybind11 torch extensions
+ * (system/ext/__init__.py:15-44).  Every entry point here cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers + sizes + a CUDA stream handle passed as void* (cudaStream_t);
+ *     no torch types, no allocation, no host synchronisation inside any call (the reference ext ops
+ *     allocate their outputs and sync: mc_interp_kernel.cu:344-369, indexing.cu:76,96-97);
+ *   - every function returns 0 on success or a negative DIF_E_* code and is asynchronous on `stream`;
+ *   - scalars that the reference reads back with .item() are written to small device arrays that the
+ *     caller may copy when (and if) it needs them;
+ *   - re-entrant: no global mutable state; two host threads may drive two streams on disjoint buffers.
+ */
+#ifndef DIFUSION_B200_H
+#define DIFUSION_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIF_ABI_VERSION 1
+#define DIF_LATENT_DIM 29                 /* ckpt/default/hyper.json:34 "code_length" */
+
+enum {
+    DIF_OK = 0,
+    DIF_E_INVALID = -1,                   /* bad argument (null pointer, size, unsupported resolution)   */
+    DIF_E_WORKSPACE = -2,                 /* workspace smaller than dif_*_workspace_bytes() says        */
+    DIF_E_LAUNCH = -3                     /* CUDA launch error; text via dif_last_error()                */
+};
+
+/* ---- folded network weights -------------------------------------------------------------------------
+ * fp32 blobs, prepared once on the host (difusion_b200/weights.py) from the reference checkpoint:
+ *   decoder: weight-norm folded W_k = g_k v_k/||v_k||  (network/di_decoder.py:36-40)
+ *   encoder: eval BatchNorm folded into the 1x1 convs  (utils/pt_util.py:37-116,     SURVEY A.6)
+ * Layout (row-major [out][in], then bias):
+ *   decoder  W0[128][32] b0[128] W1[128][128] b1[128] W2[96][128] b2[96] W3[128][128] b3[128]
+ *            w4[128] b4[1] wu[128] bu[1]                         -> DIF_DECODER_BLOB_FLOATS
+ *            (input column order: latent 0..28, x, y, z  - network/utility.py:80;
+ *             layer-3 input order: h2 (96) first, then the 32 inputs - di_decoder.py:61-62)
+ *   encoder  W0[32][6] b0[32] W1[64][32] b1[64] W2[256][64] b2[256] W3[29][256] b3[29]
+ *                                                                -> DIF_ENCODER_BLOB_FLOATS
+ * dif_prepare_* expands a blob into the device-side form the kernels read (transposed fp32 copies,
+ * fp16 hi/lo split tiles in UMMA shared-memory layout). */
+#define DIF_DECODER_BLOB_FLOATS (128*32+128 + 128*128+128 + 96*128+96 + 128*128+128 + 128+1 + 128+1)
+#define DIF_ENCODER_BLOB_FLOATS (32*6+32 + 64*32+64 + 256*64+256 + 29*256+29)
+
+size_t dif_decoder_prepared_bytes(void);
+size_t dif_encoder_prepared_bytes(void);
+int dif_prepare_decoder(const float* blob_dev, void* prepared_dev, void* stream);
+int dif_prepare_encoder(const float* blob_dev, void* prepared_dev, void* stream);
+
+/* ---- map state --------------------------------------------------------------------------------------
+ * Device view of the reference's DenseIndexedMap.cold_vars (system/map.py:199-211).  The arrays are owned
+ * by the caller (torch tensors in the Python mirror) and stay readable as the reference's public
+ * attributes `indexer`, `latent_vecs`, `latent_vecs_pos`, `voxel_obs_count`. */
+typedef struct dif_map_view {
+    int64_t* indexer;            /* [nx*ny*nz]  -1 = empty, else slot; linear id = z + nz*y + nz*ny*x (map.py:287-292) */
+    float*   latent_vecs;        /* [capacity][29] */
+    int64_t* latent_vecs_pos;    /* [capacity]  slot -> linear id, -1 = unused */
+    float*   voxel_obs_count;    /* [capacity]  integer-valued fp32 */
+    uint8_t* slot_dirty;         /* [capacity]  1 = latent changed since the last mesh extraction (map.py:303-308) */
+    int32_t* n_occupied;         /* device scalar (the reference keeps a host int, map.py:200) */
+    int64_t  capacity;
+    int32_t  nx, ny, nz;
+    float    bound_min[3];
+    float    voxel_size;
+    int32_t  prune_min_vox_obs;  /* fusion-lr-kt.yaml:32 */
+    float    ignore_count_th;    /* :33 */
+    float    encoder_count_th;   /* :34 */
+} dif_map_view;
+
+/* ---- integrate_keyframe  (system/map.py:340-452; SURVEY rows a-2 .. a-6) -----------------------------
+ * One call = voxelise + prune + allocate (ascending linear id) + encoder-target focus + 8-offset gather +
+ * encoder MLP + per-PLIVox sum + running-mean fusion.  `persist` is scratch that must be zero-filled ONCE by
+ * the caller (and whenever it is re-allocated); the call leaves it zero-filled again.  `scratch` needs no init.
+ * unq_mask (nullable) receives the per-point prune mask the reference returns (map.py:375,519).
+ * stats_dev[DIF_STAT_COUNT] is written on the device. */
+enum {
+    DIF_STAT_N_KEPT = 0,         /* points surviving the prune                                    */
+    DIF_STAT_N_NEW = 1,          /* slots allocated by this call                                  */
+    DIF_STAT_N_SAMPLES = 2,      /* encoder samples gathered (map.py:434)                         */
+    DIF_STAT_N_UPDATED = 3,      /* PLIVoxes fused (len(surface_blatent_mapping), map.py:437)     */
+    DIF_STAT_N_OCCUPIED = 4,     /* n_occupied after the call                                     */
+    DIF_STAT_FLAGS = 5,          /* bit0: a point fell outside the grid (dropped); bit1: capacity exhausted */
+    DIF_STAT_N_FOCUSED = 6,      /* points passing the focus mask (map.py:389-397)                */
+    DIF_STAT_COUNT = 8
+};
+size_t dif_integrate_persist_bytes(int64_t n_cells, int64_t capacity);
+size_t dif_integrate_scratch_bytes(int64_t max_points);
+int dif_integrate(const dif_map_view* map, const void* encoder_prepared,
+                  const float* xyz /*[n][3] world*/, const float* normal /*[n][3] world*/, int64_t n,
+                  uint8_t* unq_mask /*[n] or NULL*/, void* persist, size_t persist_bytes,
+                  void* scratch, size_t scratch_bytes, int32_t* stats_dev, void* stream);
+
+/* ---- network evaluation  (network/utility.py:61-126 forward_model; di_decoder.py:55-86; di_encoder.py:26-30) --
+ * dif_decode: sdf/std (and optionally d sdf/d xyz, d std/d xyz) for n samples.  Sample i reads latent row
+ *   rows ? rows[i] : i   of `latent` (row stride 29 floats); rows[i] < 0 marks a padding sample (outputs 0).
+ *   out_index (nullable) scatters result i to position out_index[i]; sdf_sign multiplies sdf (map.py:687). */
+int dif_decode(const void* decoder_prepared, const float* latent, const int32_t* rows, const float* xyz /*[n][3]*/,
+               int64_t n, const int32_t* out_index, float sdf_sign,
+               float* sdf, float* std, float* dsdf_dxyz /*[n][3] or NULL*/, float* dstd_dxyz /*[n][3] or NULL*/, void* stream);
+int dif_encode(const void* encoder_prepared, const float* xyzn /*[n][6]*/, int64_t n, float* latent_out /*[n][29]*/, void* stream);
+
+/* ---- get_sdf lookup  (system/map.py:565-575; SURVEY a-8) ---------------------------------------------
+ * slot_out[i] = latent slot or -1 (empty cell, outside the grid, or obs_count <= ignore_count_th);
+ * rel_out[i]  = (xyz-bound_min)/voxel_size - cell - 0.5   (network coordinates);   n_valid_dev: device scalar. */
+int dif_map_query(const dif_map_view* map, const float* xyz, int64_t n, int32_t* slot_out, float* rel_out,
+                  int32_t* n_valid_dev, void* stream);
+
+/* ---- compute_sdf_Hg  (system/tracker.py:174-218; SURVEY a-9) ------------------------------------------
+ * Fused: transform obs by last*delta, lookup, decoder fwd (+bwd wrt xyz), r = sdf/std, J = [G R_last^T, q x .],
+ * Huber(k) (huber_k <= 0: no robust kernel), normal equations.  pose = {R_last[9], t_last[3], R_delta[9], t_delta[3]}
+ * row-major fp32 (host memory, copied at call time).  out_dev[44] (fp64): H[36] row-major, g[6], energy, M (valid count);
+ * already divided by M as the reference does.  want_grad = 0 reproduces no_grad=True (only energy and M are written). */
+size_t dif_icp_scratch_bytes(int64_t n);
+int dif_icp_linearize(const dif_map_view* map, const void* decoder_prepared, const float* obs_xyz /*[n][3] camera frame*/,
+                      int64_t n, const float* pose_host /*[24]*/, float huber_k, int want_grad,
+                      void* scratch, size_t scratch_bytes, double* out_dev /*[44]*/, void* stream);
+
+/* ---- mesh extraction  (system/map.py:624-691; SURVEY a-10, a-11) ---------------------------------------
+ * dif_mesh_select: which PLIVoxes to decode.  updated_slots == NULL means "all occupied" (no_cache=True, map.py:615).
+ *   focused_ids_out[K]   = latent_vecs_pos[updated]                      (map.py:627)
+ *   block_slots_out[B]   = slots of (focused U allocated 6-neighbours), ascending linear id, obs_count > ignore_count_th (:628-631)
+ *   mapping_out[capacity]= slot -> batch index or -1                     (:633-635; the reference sizes it max_slot+1)
+ *   counts_dev[2]        = {K, B}
+ * dif_mesh_decode: cube_sdf/std [B][2r][2r][2r]; fast != 0: r^3 low pass, trilinear x2 (align_corners), re-evaluate
+ *   |sdf| < 0.05 (map.py:655-682); sdf is stored negated (:687).  counts_dev[2] = {n_low, n_high}.
+ * dif_marching_cubes: system.ext.marching_cubes_interp (mc.cpp:3-16, mc_interp_kernel.cu:202-382).  Triangles in voxel
+ *   units; *count_dev = number produced (may exceed max_tri: the excess is dropped, as in the reference :308,375-379). */
+size_t dif_mesh_select_scratch_bytes(int64_t n_cells, int64_t capacity);
+int dif_mesh_select(const dif_map_view* map, const int32_t* updated_slots, int64_t n_updated,
+                    int64_t* focused_ids_out, int32_t* block_slots_out, int32_t* mapping_out, int32_t* counts_dev,
+                    void* persist, size_t persist_bytes, void* stream);
+size_t dif_mesh_decode_scratch_bytes(int64_t n_blocks, int r);
+int dif_mesh_decode(const dif_map_view* map, const void* decoder_prepared, const int32_t* block_slots, int64_t n_blocks,
+                    int r, int fast, float* cube_sdf, float* cube_std, void* scratch, size_t scratch_bytes,
+                    int32_t* counts_dev, void* stream);
+int dif_marching_cubes(const int64_t* indexer, int nx, int ny, int nz, const int64_t* valid_blocks, int64_t n_valid,
+                       const int32_t* vec_batch_mapping, int64_t mapping_len, const float* cube_sdf, const float* cube_std,
+                       int r, float max_std, float* tri /*[max_tri][3][3]*/, int64_t* tri_flatten_id /*[max_tri]*/,
+                       float* tri_std /*[max_tri][3]*/, int64_t max_tri, int32_t* count_dev, void* stream);
+
+/* ---- groupby_sum  (system/ext/indexing/indexing.cu:59-109; indexing.cpp:4) -----------------------------
+ * sum[indices[i]][:] += values[i][:];  count[indices[i]] += L  (the reference bumps the count once per column, :70).
+ * sum/count must be zero-filled by the caller (the reference allocates zeros, :96-97). */
+int dif_groupby_sum(const float* values /*[n][L]*/, const int64_t* indices /*[n]*/, int64_t n, int32_t L, int64_t C,
+                    float* sum /*[C][L]*/, int32_t* count /*[C]*/, void* stream);
+
+int dif_abi_version(void);
+const char* dif_last_error(void);        /* thread-local text of the last DIF_E_LAUNCH */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,88 @@
+"""CPU: the C-ABI library loads and exports every symbol include/difusion_b200.h declares; host-side logic."""
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT
+
+
+def _header_functions():
+    txt = (ROOT / "include" / "difusion_b200.h").read_text()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(dif_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from difusion_b200 import _lib, build
+    build.build()
+    L = _lib.lib()
+    names = _header_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in the header but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert set(_lib.SIGNATURES) == set(names)
+    assert L.dif_abi_version() == 1
+
+
+def test_workspace_queries_need_no_gpu():
+    from difusion_b200 import _lib
+    L = _lib.lib()
+    assert L.dif_decoder_prepared_bytes() >= 4 * 49408 * 2
+    assert L.dif_encoder_prepared_bytes() >= 4 * 26048
+    assert L.dif_integrate_scratch_bytes(30000) > 30000 * 12
+    assert L.dif_integrate_persist_bytes(1920000, 1 << 16) > 1920000 * 4
+    assert L.dif_mesh_decode_scratch_bytes(1000, 4) >= 1000 * 512 * 4
+    assert L.dif_icp_scratch_bytes(30000) > 0
+
+
+def test_struct_layout_matches_header():
+    from difusion_b200 import _lib
+    import ctypes
+    # 6 pointers + int64 + 3 int32 + 3 float + float + int32 + 2 float = 48 + 8 + 12 + 12 + 4 + 4 + 8 = 96
+    assert ctypes.sizeof(_lib.MapView) == 96
+    assert _lib.MapView.capacity.offset == 48 and _lib.MapView.nx.offset == 56 and _lib.MapView.bound_min.offset == 68
+
+
+def test_no_cpu_fallback():
+    from difusion_b200 import _lib
+    from difusion_b200.network import utility as net_util
+    from difusion_b200.system.map import DenseIndexedMap
+    from difusion_b200 import synthetic as S
+    model, _ = net_util.load_model(str(GOLDEN / "weights.npz"))
+    with pytest.raises(_lib.DifusionLibraryError):
+        DenseIndexedMap(model, S.scene_S0().map_args(), 29, torch.device("cpu"))
+
+
+def test_fold_matches_oracle(oracle_weights):
+    from difusion_b200 import weights
+    dec, enc = weights.load_npz_state(GOLDEN / "weights.npz")
+    blob = weights.fold_decoder(dec)
+    o = oracle_weights.dec
+    ref = np.concatenate([o.W[0].numpy().ravel(), o.b[0].numpy(), o.W[1].numpy().ravel(), o.b[1].numpy(), o.W[2].numpy().ravel(),
+                          o.b[2].numpy(), o.W[3].numpy().ravel(), o.b[3].numpy(), o.W[4].numpy().ravel(), o.b[4].numpy(),
+                          o.Wu.numpy().ravel(), o.bu.numpy()])
+    assert blob.shape == ref.shape and np.abs(blob - ref).max() < 1e-6
+    eblob = weights.fold_encoder(enc)
+    e = oracle_weights.enc
+    eref = np.concatenate([np.concatenate([e.W[k].numpy().ravel(), e.b[k].numpy()]) for k in range(4)])
+    assert eblob.shape == eref.shape and np.abs(eblob - eref).max() < 1e-6
+
+
+def test_isometry_matches_oracle_se3():
+    from difusion_b200.utils.motion_util import Isometry
+    from oracle import dif_oracle as O
+    xi = np.array([0.02, -0.01, 0.03, 0.05, -0.04, 0.02])
+    iso = Isometry.from_twist(xi)
+    R, t = O.se3_exp(xi)
+    assert np.allclose(iso.q.rotation_matrix, R, atol=1e-12) and np.allclose(iso.t, t, atol=1e-12)
+    a = Isometry.from_twist(xi * 0.3)
+    ab = iso.dot(a)
+    assert np.allclose(ab.matrix, iso.matrix @ a.matrix, atol=1e-12)
+    assert np.allclose(iso.inv().dot(iso).matrix, np.eye(4), atol=1e-12)
+    p = np.random.default_rng(0).normal(size=(5, 3))
+    assert np.allclose(iso @ p, p @ R.T + t)
+    assert np.allclose((iso @ torch.from_numpy(p).float()).numpy(), (p @ R.T + t).astype(np.float32), atol=1e-6)

@@ -1,0 +1,309 @@
+"""GPU: the CUDA path (through the reference-shaped Python API -> C ABI -> sm_100a kernels) against the golden fixtures
+produced by the unmodified reference, and against the oracle on seeded inputs.
+
+Parity bar (BASELINE.json north_star): integer / index state bit-exact; floats |a-b| <= 1e-4 + 1e-4|b|.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, close, fixture_args, frac_off
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def model():
+    from difusion_b200.network import utility as net_util
+    return net_util.load_model(str(GOLDEN / "weights.npz"))[0]
+
+
+def _t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def test_native_library_is_loaded():
+    from difusion_b200 import _lib
+    assert _lib.lib().dif_abi_version() == 1
+    assert "libdifusion_b200.so" in open("/proc/self/maps").read()
+
+
+def test_decoder_kat(golden, model, dev):
+    from difusion_b200.network import utility as net_util
+    fx = golden["decoder_kat"]
+    lat, xyz = _t(fx["latent"], dev), _t(fx["xyz"], dev).requires_grad_(True)
+    sdf, std = net_util.forward_model(model.decoder, latent_input=lat, xyz_input=xyz, no_detach=True)
+    assert sdf.shape == (4096, 1) and std.shape == (4096, 1)
+    assert close(sdf.detach().cpu().numpy()[:, 0], fx["sdf"], TOL) and close(std.detach().cpu().numpy()[:, 0], fx["std"], TOL)
+    g = torch.autograd.grad(sdf.sum(), xyz, retain_graph=True)[0].cpu().numpy()
+    assert frac_off(g, fx["dsdf_dxyz"]) < 2e-3                  # ReLU-kink flips (see tests/golden/make_golden.py)
+    g2 = torch.autograd.grad(std.sum(), xyz)[0].cpu().numpy()
+    assert frac_off(g2, fx["dstd_dxyz"]) < 2e-3
+    # network_input form + detach semantics (utility.py:78-80,118-119)
+    out = net_util.forward_model(model.decoder, network_input=torch.cat([lat, xyz.detach()], 1))
+    assert not out[0].requires_grad and close(out[0].cpu().numpy()[:, 0], fx["sdf"], TOL)
+
+
+def test_encoder_kat(golden, model, dev):
+    fx = golden["encoder_kat"]
+    out = model.encoder(_t(fx["xyzn"], dev)).cpu().numpy()
+    assert close(out, fx["latent"], TOL)
+
+
+def test_decoder_ragged_and_padding(golden, model, dev):
+    """sizes that are not a multiple of the tile, n=1, and negative rows (padding)."""
+    from difusion_b200 import _lib
+    from difusion_b200.network import utility as net_util
+    fx = golden["decoder_kat"]
+    prep = net_util.prepared_for(model, dev)
+    for n in (1, 31, 33, 1000):
+        sdf, std = net_util.forward_model(model.decoder, latent_input=_t(fx["latent"][:n], dev), xyz_input=_t(fx["xyz"][:n], dev))
+        assert close(sdf.cpu().numpy()[:, 0], fx["sdf"][:n], TOL) and close(std.cpu().numpy()[:, 0], fx["std"][:n], TOL)
+    n = 100
+    rows = torch.arange(n, dtype=torch.int32, device=dev)
+    rows[::3] = -1
+    lat, xyz = _t(fx["latent"][:n], dev), _t(fx["xyz"][:n], dev)
+    sdf = torch.full((n,), 7.0, device=dev); std = torch.full((n,), 7.0, device=dev)
+    _lib.check(_lib.lib().dif_decode(prep.decoder.data_ptr(), lat.data_ptr(), rows.data_ptr(), xyz.data_ptr(), n, None, -1.0,
+                                     sdf.data_ptr(), std.data_ptr(), None, None, _lib.stream_ptr(dev)), "dif_decode")
+    live = (rows >= 0).cpu().numpy()
+    assert close(-sdf.cpu().numpy()[live], fx["sdf"][:n][live], TOL) and np.all(sdf.cpu().numpy()[~live] == 0)
+
+
+@pytest.mark.parametrize("name", ["s0_map", "s0_freeze", "s1_map"])
+def test_map_against_reference_fixture(golden, model, dev, name):
+    from difusion_b200.system.map import DenseIndexedMap
+    from difusion_b200.system.tracker import SDFTracker
+    from difusion_b200.utils.motion_util import Isometry, Rotation
+    import argparse
+    fx = golden[name]
+    m = DenseIndexedMap(model, fixture_args(fx), 29, dev)
+    for f in range(int(fx["n_frames"])):
+        mask = m.integrate_keyframe(_t(fx[f"f{f}.xyz"], dev), _t(fx[f"f{f}.normal"], dev))
+        assert mask.dtype == torch.bool and np.array_equal(np.packbits(mask.cpu().numpy()), fx[f"f{f}.unq_mask"])
+        nocc = m.n_occupied
+        assert nocc == int(fx[f"f{f}.n_occupied"])
+        assert m.latent_vecs.size(0) == int(fx[f"f{f}.capacity"]) == m.latent_vecs_pos.size(0) == m.voxel_obs_count.size(0)
+        idx = m.indexer.cpu().numpy()
+        occ = np.nonzero(idx != -1)[0]
+        assert np.array_equal(occ, fx[f"f{f}.occ_cells"]) and np.array_equal(idx[occ], fx[f"f{f}.occ_slots"])       # bit-exact index
+        pos = m.latent_vecs_pos.cpu().numpy()
+        assert np.array_equal(pos[:nocc][fx[f"f{f}.occ_slots"]], fx[f"f{f}.occ_cells"]) and np.all(pos[nocc:] == -1)
+        assert np.array_equal(m.voxel_obs_count.cpu().numpy()[:nocc], fx[f"f{f}.obs_count"])                       # exact
+        lat = m.latent_vecs.cpu().numpy()
+        assert close(lat[fx[f"f{f}.latent_rows"]], fx[f"f{f}.latent"], TOL)
+        assert abs(lat[:nocc].astype(np.float64).sum() - float(fx[f"f{f}.latent_sum"])) < 1e-2
+        assert np.array_equal(m.mesh_cache.updated_vec_id.cpu().numpy(), fx[f"f{f}.updated_vec_id"])
+        st = m.last_integrate_stats
+        assert st["n_kept"] == int(mask.sum()) and st["n_updated"] >= 0
+
+    # get_sdf + autograd contract (map.py:559-579, tracker.py:183-194)
+    q = _t(fx["q.xyz"], dev).requires_grad_(True)
+    sdf, std, valid = m.get_sdf(q)
+    assert np.array_equal(np.packbits(valid.cpu().numpy()), fx["q.valid"])
+    assert close(sdf.detach().cpu().numpy(), fx["q.sdf"], TOL) and close(std.detach().cpu().numpy(), fx["q.std"], TOL)
+    r = sdf / std.detach()
+    grad = torch.autograd.grad(r, [q], grad_outputs=torch.ones_like(r))[0]
+    assert grad.shape == q.shape and bool((grad[~valid] == 0).all())
+    assert frac_off(grad[valid].cpu().numpy(), fx["q.grad"]) < 2e-3
+
+    if "hg.H" in fx.files:                                    # compute_sdf_Hg (tracker.py:174-218)
+        trk = SDFTracker(m, argparse.Namespace(sdf=dict(robust_kernel="huber", robust_k=5.0, subsample=0.5), rgb=None,
+                                               iter_config=[{"n": 50, "type": [["sdf"]]}]))
+        last = Isometry(q=Rotation(matrix=fx["hg.R_last"]), t=fx["hg.t_last"])
+        delta = Isometry(q=Rotation(matrix=fx["hg.R_delta"]), t=fx["hg.t_delta"])
+        H, g, E = trk.compute_sdf_Hg(0, last, delta, _t(fx["hg.obs"], dev), no_grad=False)
+        assert H.shape == (6, 6) and H.dtype == np.float64 and np.allclose(H, H.T)
+        assert np.abs(H - fx["hg.H"]).max() <= 2e-4 * np.abs(fx["hg.H"]).max()
+        assert np.abs(g - fx["hg.g"]).max() <= 2e-4 * np.abs(fx["hg.g"]).max()
+        assert close(E, float(fx["hg.E"]), TOL)
+        H2, g2, E2 = trk.compute_sdf_Hg(-1, last, delta, _t(fx["hg.obs"], dev), no_grad=True)
+        assert H2 is None and g2 is None and close(E2, float(fx["hg.E_nograd"]), TOL)
+
+    if "mesh.res" in fx.files:                                # mesh decode (map.py:624-687)
+        r = int(fx["mesh.res"])
+        focused, mapping, cs, cd, slots, cnt = m.mesh_cubes(r, fast=True, updated_vec_id=None)
+        assert np.array_equal(focused.cpu().numpy(), fx["mesh.focused"])
+        ref_map = fx["mesh.mapping"]
+        assert np.array_equal(mapping.cpu().numpy()[:ref_map.shape[0]], ref_map) and bool((mapping[ref_map.shape[0]:] == -1).all())
+        assert cs.shape == (int(fx["mesh.B"]), 2 * r, 2 * r, 2 * r)
+        sel = fx["mesh.sel"]
+        cs_n, cd_n = cs.cpu().numpy(), cd.cpu().numpy()
+        # the |sdf|<0.05 re-evaluation set can differ by threshold flips on 1e-6 noise (SURVEY 7 "discrete decisions")
+        assert frac_off(cs_n[sel], fx["mesh.sdf_sel"]) < 1e-3 and frac_off(cd_n[sel], fx["mesh.std_sel"]) < 1e-3
+        assert abs(cs_n.astype(np.float64).sum() - float(fx["mesh.sdf_sum"])) < 0.5
+        # MC on our own cubes: CUDA kernel vs the scalar restatement, identical inputs => identical triangle multiset
+        _assert_mc_equal(m.indexer.view(m.n_xyz), focused, mapping, cs, cd, m.n_xyz, float(fx["mesh.max_std"]))
+        mesh = m.extract_mesh(r, int(4e6), max_std=float(fx["mesh.max_std"]), no_cache=True)
+        assert abs(mesh.triangles.shape[0] - int(fx["mesh.n_tri_oracle_mc"])) <= 64
+        assert mesh.vertices.shape[0] == 3 * mesh.triangles.shape[0]
+
+
+def _sorted_tris(tri, fid, std):
+    key = np.concatenate([fid[:, None].astype(np.float64), tri.reshape(len(tri), 9).astype(np.float64)], 1)
+    order = np.lexsort(key.T[::-1])
+    return tri[order], fid[order], std[order]
+
+
+def _assert_mc_equal(indexer, focused, mapping, cs, cd, n_xyz, max_std, max_tri=int(4e6)):
+    from difusion_b200.system import ext
+    from oracle import mc_oracle
+    tri, fid, std = ext.marching_cubes_interp(indexer, focused, mapping, cs, cd, max_tri, n_xyz, max_std)
+    o_tri, o_fid, o_std = mc_oracle.marching_cubes_interp(indexer.cpu().numpy(), focused.cpu().numpy(), mapping.cpu().numpy(),
+                                                          cs.cpu().numpy(), cd.cpu().numpy(), max_tri, n_xyz, max_std)
+    assert tri.shape[0] == o_tri.shape[0] > 0
+    a = _sorted_tris(tri.cpu().numpy(), fid.cpu().numpy(), std.cpu().numpy())
+    b = _sorted_tris(o_tri, o_fid, o_std)
+    assert np.array_equal(a[1], b[1])
+    assert np.abs(a[0] - b[0]).max() <= 1e-6 and np.abs(a[2] - b[2]).max() <= 1e-6
+    return tri.shape[0]
+
+
+@pytest.mark.parametrize("r", [4, 5, 2])
+def test_marching_cubes_synthetic(dev, r):
+    """system.ext.marching_cubes_interp on analytic cubes: parity with the scalar restatement, max_std filter, overflow."""
+    from difusion_b200.system import ext
+    from test_oracle_mc import _sphere_cubes
+    n_xyz = [6, 5, 7]
+    indexer, mapping, sdf, std = _sphere_cubes(n_xyz, r, (3.0, 2.5, 3.5), 1.9, drop=(2, 2, 3))
+    rng = np.random.default_rng(0)
+    std = (std + rng.uniform(0, 0.1, std.shape)).astype(np.float32)
+    # leave some PLIVoxes out of the batch (mapping -1) and shuffle batch order
+    B = sdf.shape[0]
+    perm = rng.permutation(B)
+    keep = perm[: int(B * 0.9)]
+    mapping = np.full(B, -1, np.int32); mapping[keep] = np.arange(len(keep), dtype=np.int32)
+    sdf, std = sdf[keep], std[keep]
+    blocks = np.sort(rng.choice(B, int(B * 0.8), replace=False)).astype(np.int64)
+    blocks = blocks[indexer.reshape(-1)[blocks] != -1]
+    args = (_t(indexer, dev), _t(blocks, dev), _t(mapping, dev), _t(sdf, dev), _t(std, dev))
+    n_all = _assert_mc_equal(*args, n_xyz, 10.0)
+    n_f = _assert_mc_equal(*args, n_xyz, 0.15)
+    assert 0 < n_f < n_all
+    tri, fid, tstd = ext.marching_cubes_interp(*args, 50, n_xyz, 10.0)        # overflow: full untrimmed buffer (mc_interp_kernel.cu:375-379)
+    assert tri.shape == (50, 3, 3) and fid.shape == (50,) and tstd.shape == (50, 3)
+    with pytest.raises(RuntimeError):
+        ext.marching_cubes_interp(args[0].cpu(), *args[1:], 50, n_xyz, 10.0)
+
+
+def test_groupby_sum(dev):
+    from difusion_b200.system import ext
+    from difusion_b200.network import utility as net_util
+    g = torch.Generator().manual_seed(0)
+    v = torch.randn(5000, 29, generator=g)
+    idx = torch.randint(0, 37, (5000,), generator=g)
+    s, c = ext.groupby_sum(v.to(dev), idx.to(dev), 40)
+    ref = torch.zeros(40, 29).index_add_(0, idx, v)
+    assert close(s.cpu().numpy(), ref.numpy(), 1e-4)
+    assert np.array_equal(c.cpu().numpy(), 29 * np.bincount(idx.numpy(), minlength=40))       # indexing.cu:70 counts per column
+    assert c.dtype == torch.int32 and s.shape == (40, 29)
+    r = net_util.groupby_reduce(idx.to(dev), v.to(dev), op="sum")
+    assert close(r.cpu().numpy(), ref.numpy()[: int(idx.max()) + 1], 1e-4)
+
+
+def test_edge_cases(model, dev):
+    from difusion_b200.system.map import DenseIndexedMap
+    from difusion_b200 import synthetic as S
+    from oracle import dif_oracle as O
+    sc = S.scene_S0()
+    W = O.load_weights_npz(GOLDEN / "weights.npz")
+    # (1) points exactly on cell faces and on the grid border; prune disabled -> returns None (map.py:372-373)
+    args = sc.map_args(); args.prune_min_vox_obs = 0; args.ignore_count_th = 0.0
+    m = DenseIndexedMap(model, args, 29, dev)
+    o = O.OracleMap(W, args)
+    bm = np.asarray(args.bound_min, np.float32)
+    ijk = np.array([[1, 1, 1], [1, 2, 3], [31, 31, 31], [32, 32, 32], [5, 5, 5], [0.5, 0.5, 0.5], [31.99, 0.01, 16]], np.float32)
+    pts = (bm + ijk * np.float32(0.1)).astype(np.float32)
+    pts = np.concatenate([pts, pts + np.float32(1e-6), pts[:5] - np.float32(1e-6)])
+    pts = pts[np.all(np.ceil(o._normalize(pts)) - 1 >= 0, 1) & np.all(np.ceil(o._normalize(pts)) - 1 <= 31, 1)]
+    nrm = np.tile(np.array([[0, 0, 1.0]], np.float32), (len(pts), 1))
+    assert m.integrate_keyframe(_t(pts, dev), _t(nrm, dev)) is None and o.integrate_keyframe(pts, nrm) is None
+    assert m.n_occupied == o.n_occupied and np.array_equal(m.indexer.cpu().numpy(), o.indexer)
+    assert np.array_equal(m.voxel_obs_count.cpu().numpy(), o.voxel_obs_count)
+    assert close(m.latent_vecs.cpu().numpy(), o.latent_vecs, TOL)
+    # (2) everything pruned: nothing allocated, mask all False
+    m2 = DenseIndexedMap(model, sc.map_args(), 29, dev)
+    mask = m2.integrate_keyframe(_t(pts, dev), _t(nrm, dev))
+    assert not bool(mask.any()) and m2.n_occupied == 0 and bool((m2.indexer == -1).all()) and m2.latent_vecs.size(0) == 1
+    # (3) empty input
+    e = torch.zeros((0, 3), device=dev)
+    mask = m2.integrate_keyframe(e, e)
+    assert mask.numel() == 0 and m2.n_occupied == 0
+    # (4) out-of-bounds points are dropped and reported
+    far = _t(np.array([[100.0, 0, 0]], np.float32), dev)
+    m2.integrate_keyframe(far, far)
+    with pytest.raises(IndexError):
+        _ = m2.n_occupied
+    # (5) get_sdf on an empty map asserts like the reference (utility.py:84-85)
+    with pytest.raises(AssertionError):
+        m2.get_sdf(_t(pts, dev))
+    # (6) device mismatch assert (map.py:353)
+    with pytest.raises(AssertionError):
+        m2.integrate_keyframe(torch.zeros(3, 3), torch.zeros(3, 3))
+
+
+def test_capacity_growth_and_save_load(golden, model, dev, tmp_path):
+    """tiny physical capacity forces the doubling path; save/load round-trips the reference's cold_vars dict (map.py:239-249)."""
+    from difusion_b200.system.map import DenseIndexedMap
+    fx = golden["s0_map"]
+    m = DenseIndexedMap(model, fixture_args(fx), 29, dev, initial_capacity=4)
+    for f in range(int(fx["n_frames"])):
+        m.integrate_keyframe(_t(fx[f"f{f}.xyz"], dev), _t(fx[f"f{f}.normal"], dev))
+    f = int(fx["n_frames"]) - 1
+    assert m.n_occupied == int(fx[f"f{f}.n_occupied"])
+    assert np.array_equal(m.voxel_obs_count.cpu().numpy()[:m.n_occupied], fx[f"f{f}.obs_count"])
+    assert close(m.latent_vecs.cpu().numpy()[fx[f"f{f}.latent_rows"]], fx[f"f{f}.latent"], TOL)
+    p = tmp_path / "map.pt"
+    m.save(p)
+    cv = torch.load(p)
+    assert set(cv) == {"n_occupied", "indexer", "latent_vecs", "latent_vecs_pos", "voxel_obs_count", "voxel_optimized"}
+    assert cv["latent_vecs"].shape == (int(fx[f"f{f}.capacity"]), 29) and cv["voxel_optimized"].dtype == torch.bool
+    m2 = DenseIndexedMap(model, fixture_args(fx), 29, dev)
+    m2.load(p)
+    assert m2.n_occupied == m.n_occupied and torch.equal(m2.indexer, m.indexer) and torch.equal(m2.latent_vecs, m.latent_vecs)
+    q = _t(fx["q.xyz"], dev)
+    a, b = m.get_sdf(q), m2.get_sdf(q)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2])
+
+
+def test_large_batch_properties(model, dev):
+    """At BASELINE config-3 sizes (2^20 here, 2^22 in bench.py) the oracle is too slow: use size-independent properties."""
+    from difusion_b200.network import utility as net_util
+    from oracle import dif_oracle as O
+    W = O.load_weights_npz(GOLDEN / "weights.npz")
+    g = torch.Generator().manual_seed(5)
+    n = 1 << 20
+    table = torch.randn(2048, 29, generator=g) * 0.2
+    rows = torch.randint(0, 2048, (n,), generator=g)
+    xyz = torch.rand(n, 3, generator=g) * 2 - 1
+    lat = table[rows]
+    sdf, std = net_util.forward_model(model.decoder, latent_input=lat.to(dev), xyz_input=xyz.to(dev))
+    sdf, std = sdf.cpu()[:, 0], std.cpu()[:, 0]
+    # (a) a seeded sub-sample against the oracle
+    pick = torch.randperm(n, generator=g)[:8192]
+    o_sdf, o_std = O.decoder_forward(W.dec, lat[pick], xyz[pick])
+    assert close(sdf[pick].numpy(), o_sdf.numpy(), TOL) and close(std[pick].numpy(), o_std.numpy(), TOL)
+    # (b) permutation equivariance: decode(perm(x)) == perm(decode(x)) bit for bit (no cross-sample coupling)
+    perm = torch.randperm(n, generator=g)
+    sdf_p, _ = net_util.forward_model(model.decoder, latent_input=lat[perm].to(dev), xyz_input=xyz[perm].to(dev))
+    assert torch.equal(sdf_p.cpu()[:, 0], sdf[perm])
+    # (c) ranges: tanh-bounded sdf, std > 0.05 (di_decoder.py:68,84)
+    assert float(sdf.abs().max()) <= 1.0 and float(std.min()) > 0.05
+    # (d) analytic gradient vs central finite differences on the CUDA forward
+    x0 = xyz[:4096].to(dev).requires_grad_(True)
+    s0, _ = net_util.forward_model(model.decoder, latent_input=lat[:4096].to(dev), xyz_input=x0, no_detach=True)
+    ga = torch.autograd.grad(s0.sum(), x0)[0].cpu()
+    h = 1e-3
+    for c in range(3):
+        d = torch.zeros(1, 3); d[0, c] = h
+        sp, _ = net_util.forward_model(model.decoder, latent_input=lat[:4096].to(dev), xyz_input=(xyz[:4096] + d).to(dev))
+        sm, _ = net_util.forward_model(model.decoder, latent_input=lat[:4096].to(dev), xyz_input=(xyz[:4096] - d).to(dev))
+        fd = ((sp - sm) / (2 * h)).cpu()[:, 0]
+        assert float((fd - ga[:, c]).abs().median()) < 2e-3
