@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py - frames/s of the DI-Fusion per-frame hot path (integrate + one decode) on a synthetic 640x480 stream.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): scene S1 (box room + sphere), 5 cm PLIVoxes (160x100x120 grid), the shipped
+encoder/decoder, a 200-frame yaw-sweep stream, integrate_interval = 1.  One STEP = one frame:
+    (a) point-to-implicit ICP linearisation of the frame against the map built so far
+        (decoder forward + backward wrt xyz + 6x6 normal equations; reference tracker.py:174-218 compute_sdf_Hg)   [frame >= 1]
+    (b) integrate_keyframe of the frame (voxelise/prune/allocate/gather/encoder/fuse; reference map.py:340-452).
+`value`  : frames/s with every frame's points already resident in HBM (device time, CUDA events per step).
+`e2e`    : the same steps through the reference-shaped Python API (DenseIndexedMap / SDFTracker) from PINNED HOST buffers:
+           H2D of the frame's points+normals inside the timed region, D2H of the 44-double ICP result and of the
+           integrate counters, host sync every frame (a tracking loop needs H,g on the host to update the pose).
+L2 is flushed (256 MiB write) between timed steps; per-step CUDA events exclude the flush.
+--impl reference: the CPU restatement of the reference's own Python path (oracle/dif_oracle.py; the reference has no CPU
+mode and its CUDA extensions cannot be built without its source tree on the box) on all host cores, same steps.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+ENC_FLOP = 52096.0           # encoder FLOP / sample
+DEC_FWD_FLOP = 98816.0       # decoder forward FLOP / sample
+DEC_BWD_FLOP = 91904.0       # decoder backward wrt xyz FLOP / sample
+STREAM_LEN = 200
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+def make_frames(n_frames: int):
+    from difusion_b200 import synthetic as S
+    sc = S.scene_S1(0.05)
+    frames = []
+    for f in range(n_frames):
+        R, t = S.orbit_pose(f % (2 * STREAM_LEN), STREAM_LEN)
+        pc, nc = S.frame_points(sc, R, t)
+        xw, nw = S.to_world(pc, nc, R, t)
+        frames.append(dict(pc=pc, xw=xw, nw=nw, R=R, t=t))
+    return sc, frames
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:          # noqa
+            self.err = str(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                self.samples.append((mhz, reasons, util))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": getattr(self, "max_mhz", None), "reasons": [], "samples": 0}
+        names = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+                 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+        mhz = sorted(s[0] for s in self.samples)
+        bits = 0
+        for s in self.samples:
+            bits |= s[1]
+        reasons = [n for b, n in names.items() if bits & b and n != "gpu_idle"]
+        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------- reference arm / cpu baseline
+def run_cpu_port(frames, sc, n_steps, warmup, threads):
+    """The oracle port of the reference's CPU path; returns seconds for n_steps frames (after `warmup` untimed frames on a scratch map)."""
+    import torch
+    from oracle import dif_oracle as O
+    torch.set_num_threads(threads)
+    W = O.load_weights_npz(ROOT / "tests" / "golden" / "weights.npz")
+
+    def step(m, f, fr):
+        if f >= 1:
+            O.compute_sdf_Hg(m, fr["R"], fr["t"], np.eye(3), np.zeros(3), fr["pc"], 5.0)
+        m.integrate_keyframe(fr["xw"], fr["nw"])
+    scratch = O.OracleMap(W, sc.map_args())
+    for f in range(warmup):
+        step(scratch, f, frames[f])
+    m = O.OracleMap(W, sc.map_args())
+    t0 = time.perf_counter()
+    for f in range(n_steps):
+        step(m, f, frames[f])
+    return time.perf_counter() - t0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=24, help="frames of the stream timed for cpu_baseline")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the decoder batch sweep (config 3) extras")
+    a = ap.parse_args()
+    K, Wm = a.steps, max(a.warmup, 0)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+    workload = "S1 box-room+sphere, 640x480 depth stream (200-frame yaw sweep, 1/2 subsample + 2cm box filter -> ~27-35k pts/frame), " \
+               "5cm PLIVoxes 160x100x120, shipped encoder/decoder, step = ICP linearise (decoder fwd+bwd+6x6) + integrate_keyframe"
+    config = {"workload": workload, "integrate_interval": 1, "frames": K, "l2": "flushed between timed steps (256 MiB write), per-step CUDA events",
+              "parallelism": f"replicas x{world}" if world > 1 else "single GPU"}
+
+    # ------------------------------------------------------------------ reference arm: CPU port on host cores, rank 0 only
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        sc, frames = make_frames(max(K, Wm))
+        sec = run_cpu_port(frames, sc, K, min(Wm, 2), cores)
+        v = K / sec
+        print(json.dumps({"impl": "reference", "metric": "frames/sec integrate+decode 640x480", "value": v, "unit": "frames/s", "n_gpus": a.gpus,
+                          "steps": K, "warmup": Wm, "ms_per_step": 1e3 * sec / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f32", "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
+                                           "sample": f"frames 0..{K - 1} of the stream, oracle/dif_oracle.py (torch CPU fp32 MLPs + numpy index work)"},
+                          "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank if world > 1 else 0)
+    torch.cuda.set_device(dev)
+    from difusion_b200 import _lib
+    from difusion_b200.network import utility as net_util
+    from difusion_b200.system.map import DenseIndexedMap
+    from difusion_b200.system.tracker import SDFTracker
+    from difusion_b200.utils.motion_util import Isometry, Rotation
+    L = _lib.lib()                                          # raises if the CUDA library is missing: no fallback
+    model, _ = net_util.load_model(str(ROOT / "tests" / "golden" / "weights.npz"))
+
+    n_need = max(K, Wm)
+    sc, frames = make_frames(n_need)
+    ident = Isometry()
+    poses = [Isometry(q=Rotation(matrix=fr["R"]), t=fr["t"]) for fr in frames]
+    trk_args = argparse.Namespace(sdf=dict(robust_kernel="huber", robust_k=5.0, subsample=0.5), rgb=None, iter_config=[{"n": 1, "type": [["sdf"]]}])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    # ------------------------------------------------------------------ device-resident arm (`value`)
+    d_frames = [dict(pc=torch.from_numpy(fr["pc"]).to(dev), xw=torch.from_numpy(fr["xw"]).to(dev), nw=torch.from_numpy(fr["nw"]).to(dev)) for fr in frames]
+
+    def dev_step(m, f, hooks=None):
+        fr, dfr = frames[f], d_frames[f]
+        if f >= 1:
+            if hooks:
+                L.dif_profile_hook(1, hooks[0].cuda_event, hooks[1].cuda_event)
+            m.icp_linearize(dfr["pc"], fr["R"], fr["t"], np.eye(3), np.zeros(3), huber_k=5.0, want_grad=True)
+        if hooks:
+            L.dif_profile_hook(0, hooks[2].cuda_event, hooks[3].cuda_event)
+        m.integrate_keyframe(dfr["xw"], dfr["nw"])
+
+    scratch_map = DenseIndexedMap(model, sc.map_args(), 29, dev, initial_capacity=1 << 19)
+    for f in range(Wm):
+        dev_step(scratch_map, f)
+    torch.cuda.synchronize(dev)
+    del scratch_map
+
+    m = DenseIndexedMap(model, sc.map_args(), 29, dev, initial_capacity=1 << 19)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(K)]
+    for row in ev:                       # torch creates the CUDA event lazily: record once so .cuda_event is a live handle
+        for e in row:
+            e.record()
+    sampler = ClockSampler(dev.index or 0)
+    barrier()
+    sampler.start()
+    L.dif_launch_count(1)
+    for f in range(K):
+        flush.zero_()
+        ev[f][0].record()
+        dev_step(m, f, hooks=ev[f][2:6])
+        ev[f][1].record()
+    barrier()
+    launches = int(L.dif_launch_count(1))
+    step_ms = [ev[f][0].elapsed_time(ev[f][1]) for f in range(K)]
+    icp_ms = [ev[f][2].elapsed_time(ev[f][3]) for f in range(1, K)]
+    enc_ms = [ev[f][4].elapsed_time(ev[f][5]) for f in range(K)]
+    total_ms = float(sum(step_ms))
+    n_occ = m.n_occupied
+    stats_dev = m.last_integrate_stats
+
+    # per-kernel algorithmic work (needs the per-frame sample counts: replay the counters cheaply through a second map)
+    m2 = DenseIndexedMap(model, sc.map_args(), 29, dev, initial_capacity=1 << 19)
+    enc_samples, icp_samples = [], []
+    for f in range(K):
+        if f >= 1:
+            o = m2.icp_linearize(d_frames[f]["pc"], frames[f]["R"], frames[f]["t"], np.eye(3), np.zeros(3), 5.0, True)
+            icp_samples.append(float(o[43].item()))
+        m2.integrate_keyframe(d_frames[f]["xw"], d_frames[f]["nw"])
+        _ = m2.n_occupied
+        enc_samples.append(m2.last_integrate_stats["n_samples"])
+    del m2
+
+    # ------------------------------------------------------------------ end-to-end arm through the public API, host buffers
+    h_frames = [dict(pc=torch.from_numpy(fr["pc"]).pin_memory(), xw=torch.from_numpy(fr["xw"]).pin_memory(), nw=torch.from_numpy(fr["nw"]).pin_memory())
+                for fr in frames]
+    h2d = d2h = 0
+    m3 = DenseIndexedMap(model, sc.map_args(), 29, dev, initial_capacity=1 << 19)
+    trk = SDFTracker(m3, trk_args)
+    ev2 = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
+    barrier()
+    wall0 = time.perf_counter()
+    for f in range(K):
+        flush.zero_()
+        ev2[f][0].record()
+        hf = h_frames[f]
+        pc = hf["pc"].to(dev, non_blocking=True); xw = hf["xw"].to(dev, non_blocking=True); nw = hf["nw"].to(dev, non_blocking=True)
+        if f >= 1:
+            H, g, E = trk.compute_sdf_Hg(0, poses[f], ident, pc, no_grad=False)        # D2H of 44 doubles + sync inside
+        m3.integrate_keyframe(xw, nw)
+        _ = m3.n_occupied                                                               # D2H of the integrate counters + sync
+        ev2[f][1].record()
+        h2d += 3 * hf["pc"].numel() * 4
+        d2h += (44 * 8 if f >= 1 else 0) + 8 * 4
+    barrier()
+    sampler.stop_flag = True
+    e2e_wall = time.perf_counter() - wall0
+    e2e_ms = float(sum(ev2[f][0].elapsed_time(ev2[f][1]) for f in range(K)))
+    assert m3.n_occupied == n_occ, "e2e and device-resident arms diverged"
+
+    # max over ranks
+    if world > 1:
+        tt = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms = tt.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    enc_flop = ENC_FLOP * float(sum(enc_samples))
+    icp_flop = (DEC_FWD_FLOP + DEC_BWD_FLOP) * float(sum(icp_samples))
+    enc_t, icp_t = sum(enc_ms) * 1e-3, sum(icp_ms) * 1e-3
+    dom = "encode_accumulate_kernel" if enc_t >= icp_t else "icp_linearize_kernel"
+    dflop, dt, dn = (enc_flop, enc_t, len(enc_ms)) if enc_t >= icp_t else (icp_flop, icp_t, len(icp_ms))
+    achieved = dflop / dt / 1e12 if dt > 0 else 0.0
+    roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / pk["tf_sustained"], "traffic": None, "peak_source": pk["src"] + ", bf16 sustained (kernel timed inside a long step)",
+                "avg_launch_ms": 1e3 * dt / max(dn, 1), "algorithmic_flop_per_launch": dflop / max(dn, 1),
+                "share_of_step": dt / (total_ms * 1e-3),
+                "note": "fp32 SIMT path this round (exact-fp32 parity path); algorithmic FLOPs per SURVEY 8(d)",
+                "other": {"encode_accumulate_kernel": {"ms_total": sum(enc_ms), "tflops": enc_flop / enc_t / 1e12 if enc_t else 0, "samples": int(sum(enc_samples))},
+                          "icp_linearize_kernel": {"ms_total": sum(icp_ms), "tflops": icp_flop / icp_t / 1e12 if icp_t else 0, "samples": int(sum(icp_samples))}}}
+
+    # ------------------------------------------------------------------ config 3 extras: decoder batch sweep (samples/s)
+    sweep = {}
+    if not a.no_sweep:
+        prep = net_util.prepared_for(model, dev)
+        table = m._latent[:max(n_occ, 1)]
+        g = torch.Generator(device="cpu").manual_seed(0)
+        for p2 in (14, 16, 18, 20, 22):
+            n = 1 << p2
+            rows = torch.randint(0, max(n_occ, 1), (n,), generator=g, dtype=torch.int32).to(dev)
+            xyz = (torch.rand(n, 3, generator=g) * 2 - 1).to(dev)
+            sdf = torch.empty(n, device=dev); std = torch.empty(n, device=dev)
+            def run():
+                _lib.check(L.dif_decode(prep.decoder.data_ptr(), table.data_ptr(), rows.data_ptr(), xyz.data_ptr(), n, None, 1.0,
+                                        sdf.data_ptr(), std.data_ptr(), None, None, _lib.stream_ptr(dev)), "dif_decode")
+            for _ in range(3):
+                run()
+            best = 1e30
+            for _ in range(5):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); run(); e1.record(); torch.cuda.synchronize(dev)
+                best = min(best, e0.elapsed_time(e1))
+            sps = n / (best * 1e-3)
+            sweep[f"2^{p2}"] = {"samples_per_s": sps, "tflops_algorithmic": sps * DEC_FWD_FLOP / 1e12,
+                                "frac_of_bf16_burst_peak": sps * DEC_FWD_FLOP / 1e12 / pk["tf_burst"]}
+
+    # ------------------------------------------------------------------ cpu baseline: the oracle port on the host cores (bounded sample)
+    ns = min(a.cpu_sample, K)
+    cpu_sec = run_cpu_port(frames, sc, ns, 1, cores)
+    cpu = {"value": ns / cpu_sec, "unit": "frames/s", "cores": cores, "kind": "port",
+           "sample": f"frames 0..{ns - 1} of the same stream (the most expensive prefix: most PLIVoxes still below encoder_count_th), "
+                     f"oracle/dif_oracle.py on torch CPU fp32 with {cores} threads"}
+    gpu_prefix_ms = float(sum(step_ms[:ns]))
+
+    out = {"metric": "frames/sec integrate+decode 640x480", "value": world * K / (total_ms * 1e-3), "unit": "frames/s", "n_gpus": world,
+           "steps": K, "warmup": Wm, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic", "config": config, "clocks": sampler.summary(),
+           "e2e": {"value": world * K / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K,
+                   "ms_per_step": e2e_ms / K, "wall_ms_per_step_incl_flush": 1e3 * e2e_wall / K},
+           "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+           "same_prefix": {"frames": ns, "gpu_frames_per_s": ns / (gpu_prefix_ms * 1e-3), "cpu_frames_per_s": ns / cpu_sec},
+           "map": {"n_occupied": n_occ, "last_integrate": stats_dev}, "decoder_sweep": sweep}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

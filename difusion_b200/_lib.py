@@ -29,6 +29,8 @@ _MV = C.POINTER(MapView)
 # name -> (restype, argtypes); this table is also what tests/test_abi.py checks against include/difusion_b200.h
 SIGNATURES = {
     "dif_abi_version": (C.c_int, []),
+    "dif_profile_hook": (C.c_int, [C.c_int, _P, _P]),
+    "dif_launch_count": (C.c_uint64, [C.c_int]),
     "dif_last_error": (C.c_char_p, []),
     "dif_decoder_prepared_bytes": (_SZ, []),
     "dif_encoder_prepared_bytes": (_SZ, []),

@@ -13,6 +13,16 @@ namespace dif {
 
 extern thread_local char g_last_error[256];
 
+// Optional measurement hooks (bench.py): one-shot CUDA-event brackets around a named kernel, and a launch counter.
+struct ProfHook { cudaEvent_t start, stop; };
+extern thread_local ProfHook g_prof[DIF_PROF_COUNT];
+extern thread_local uint64_t g_launches;
+inline void prof_begin(int which, cudaStream_t st) { if (g_prof[which].start) cudaEventRecord(g_prof[which].start, st); }
+inline void prof_end(int which, cudaStream_t st) {
+    if (g_prof[which].stop) { cudaEventRecord(g_prof[which].stop, st); g_prof[which].start = nullptr; g_prof[which].stop = nullptr; }
+}
+#define DIF_COUNT_LAUNCH(n) (dif::g_launches += (n))
+
 inline int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

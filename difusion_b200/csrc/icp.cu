@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(MLP_THREADS) icp_linearize_kernel(
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DecoderSmem& s = *reinterpret_cast<DecoderSmem*>(smem_raw);
     __shared__ float q_s[3 * MLP_T];
-    __shared__ float r_s[MLP_T], inv_std_s[MLP_T];
+    __shared__ float r_s[MLP_T];
     __shared__ int slot_s[MLP_T];
     __shared__ bool is_last;
     float acc[29];                               // meaningful on lane 0 of warp 0 only
@@ -67,7 +67,6 @@ __global__ void __launch_bounds__(MLP_THREADS) icp_linearize_kernel(
             const float sd = 0.05f + 0.5f * softplus_ref(s.pre[MLP_T + t]);
             const float inv = 1.f / sd;
             r_s[t] = sdf / sd;                                   // tracker.py:186
-            inv_std_s[t] = inv;
             s.seed[t] = (1.f - sdf * sdf) * inv;                 // d r / d pre_sdf   (std detached)
         }
         __syncthreads();
@@ -175,8 +174,11 @@ int dif_icp_linearize(const dif_map_view* map, const void* decoder_prepared, con
     if (grid < 1) grid = 1;
     const size_t smem = sizeof(DecoderSmem);
     cudaFuncSetAttribute(icp_linearize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    prof_begin(DIF_PROF_ICP, st);
     icp_linearize_kernel<<<grid, MLP_THREADS, smem, st>>>(m, (const float*)decoder_prepared, obs_xyz, (int)n, p, huber_k, want_grad,
                                                           partials, counter, out_dev);
+    prof_end(DIF_PROF_ICP, st);
+    DIF_COUNT_LAUNCH(1);
     return check_launch("icp_linearize_kernel");
 }
 

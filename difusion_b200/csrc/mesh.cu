@@ -298,6 +298,7 @@ int dif_mesh_decode(const dif_map_view* map, const void* decoder_prepared, const
     if (rc) return rc;
     const int64_t total = n_blocks * h3;
     upsample_select_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(low_sdf, low_std, n_blocks, lr, cube_sdf, cube_std, list, n_sel);
+    DIF_COUNT_LAUNCH(2);
     rc = launch_decode_lattice(P, map->latent_vecs, block_slots, n_blocks, hr, step_h, (float)sa, list, n_sel, total, -1.f, cube_sdf, cube_std, st);
     if (rc) return rc;
     write_counts_kernel<<<1, 1, 0, st>>>(counts_dev, (int32_t)(n_blocks * l3), n_sel);
@@ -315,7 +316,10 @@ int dif_marching_cubes(const int64_t* indexer, int nx, int ny, int nz, const int
     McArgs a{indexer, nx, ny, nz, valid_blocks, n_valid, vec_batch_mapping, mapping_len, cube_sdf, cube_std, r, max_std,
              tri, tri_flatten_id, tri_std, max_tri, count_dev};
     const int64_t cap = (int64_t)DIF_NUM_SMS * 16;
+    prof_begin(DIF_PROF_MC, st);
     marching_cubes_kernel<<<(unsigned)(n_valid < cap ? n_valid : cap), MC_THREADS, 0, st>>>(a);
+    prof_end(DIF_PROF_MC, st);
+    DIF_COUNT_LAUNCH(1);
     return check_launch("marching_cubes_kernel");
 }
 
@@ -324,6 +328,7 @@ int dif_groupby_sum(const float* values, const int64_t* indices, int64_t n, int3
     if (n == 0) return DIF_OK;
     const int64_t total = n * L;
     groupby_sum_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(values, indices, n, L, C, sum, count);
+    DIF_COUNT_LAUNCH(1);
     return check_launch("groupby_sum_kernel");
 }
 

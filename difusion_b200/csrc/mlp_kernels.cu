@@ -5,6 +5,8 @@
 namespace dif {
 
 thread_local char g_last_error[256] = "";
+thread_local ProfHook g_prof[DIF_PROF_COUNT] = {};
+thread_local uint64_t g_launches = 0;
 
 // ---------------------------------------------------------------------------------------------- prepare
 __global__ void prepare_decoder_kernel(const float* __restrict__ blob, float* __restrict__ P) {
@@ -156,6 +158,7 @@ int launch_decode(DecodeArgs a, int64_t n_max, cudaStream_t st) {
     if (n_max <= 0) return DIF_OK;
     const int64_t n_tiles = (n_max + MLP_T - 1) / MLP_T;
     const size_t smem = sizeof(DecoderSmem);
+    prof_begin(DIF_PROF_DECODE, st);
     if (a.grad) {
         cudaFuncSetAttribute(decode_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         decode_simt_kernel<true><<<grid_for_tiles(n_tiles, 3), MLP_THREADS, smem, st>>>(a);
@@ -163,6 +166,8 @@ int launch_decode(DecodeArgs a, int64_t n_max, cudaStream_t st) {
         cudaFuncSetAttribute(decode_simt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         decode_simt_kernel<false><<<grid_for_tiles(n_tiles, 3), MLP_THREADS, smem, st>>>(a);
     }
+    prof_end(DIF_PROF_DECODE, st);
+    DIF_COUNT_LAUNCH(1);
     return check_launch("decode_simt_kernel");
 }
 
@@ -188,6 +193,12 @@ using namespace dif;
 extern "C" {
 
 int dif_abi_version(void) { return DIF_ABI_VERSION; }
+int dif_profile_hook(int which, void* start_event, void* stop_event) {
+    if (which < 0 || which >= DIF_PROF_COUNT) return DIF_E_INVALID;
+    dif::g_prof[which].start = (cudaEvent_t)start_event; dif::g_prof[which].stop = (cudaEvent_t)stop_event;
+    return DIF_OK;
+}
+uint64_t dif_launch_count(int reset) { const uint64_t v = dif::g_launches; if (reset) dif::g_launches = 0; return v; }
 const char* dif_last_error(void) { return dif::g_last_error; }
 
 size_t dif_decoder_prepared_bytes(void) { return (size_t)DecW::FP32_END * sizeof(float); }
@@ -196,12 +207,14 @@ size_t dif_encoder_prepared_bytes(void) { return (size_t)EncW::FP32_END * sizeof
 int dif_prepare_decoder(const float* blob_dev, void* prepared_dev, void* stream) {
     if (!blob_dev || !prepared_dev) return DIF_E_INVALID;
     prepare_decoder_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(blob_dev, (float*)prepared_dev);
+    DIF_COUNT_LAUNCH(1);
     return check_launch("prepare_decoder_kernel");
 }
 
 int dif_prepare_encoder(const float* blob_dev, void* prepared_dev, void* stream) {
     if (!blob_dev || !prepared_dev) return DIF_E_INVALID;
     prepare_encoder_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(blob_dev, (float*)prepared_dev);
+    DIF_COUNT_LAUNCH(1);
     return check_launch("prepare_encoder_kernel");
 }
 
@@ -222,6 +235,7 @@ int dif_encode(const void* encoder_prepared, const float* xyzn, int64_t n, float
     cudaFuncSetAttribute(encode_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int64_t n_tiles = (n + MLP_T - 1) / MLP_T;
     encode_simt_kernel<<<grid_for_tiles(n_tiles, 4), MLP_THREADS, smem, (cudaStream_t)stream>>>((const float*)encoder_prepared, xyzn, n, latent_out);
+    DIF_COUNT_LAUNCH(1);
     return check_launch("encode_simt_kernel");
 }
 

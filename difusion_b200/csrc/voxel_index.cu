@@ -441,7 +441,9 @@ int dif_integrate(const dif_map_view* map, const void* encoder_prepared, const f
     if (n > 0) {
         voxelize_kernel<<<nb, 256, 0, st>>>(m, xyz, (int)n, S.p_hat, S.cell, P.cell_count, stats_dev);
         prune_mark_kernel<<<nb, 256, 0, st>>>(m, (int)n, S.cell, P.cell_count, S.kept, unq_mask, P.bitmap, stats_dev);
+        DIF_COUNT_LAUNCH(2);
     }
+    DIF_COUNT_LAUNCH(3);
     bitmap_count_kernel<<<n_chunks, SCAN_THREADS, 0, st>>>(P.bitmap, n_words, S.chunk_sum);
     bitmap_scan_kernel<<<1, 1024, 0, st>>>(S.chunk_sum, n_chunks, m.n_occ, m.capacity, S.ctr, stats_dev, 1);
     alloc_assign_kernel<<<n_chunks, SCAN_THREADS, 0, st>>>(m, P.bitmap, n_words, S.chunk_sum, S.ctr);
@@ -452,8 +454,11 @@ int dif_integrate(const dif_map_view* map, const void* encoder_prepared, const f
         cudaFuncSetAttribute(encode_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         const int64_t max_tiles = (8 * n + MLP_T - 1) / MLP_T;
         const int grid = (int)(max_tiles < DIF_NUM_SMS * 4 ? max_tiles : DIF_NUM_SMS * 4);
+        prof_begin(DIF_PROF_ENCODE, st);
         encode_accumulate_kernel<<<grid, MLP_THREADS, smem, st>>>(m, (const float*)encoder_prepared, S.p_hat, normal, S.s_pt, S.s_slot,
                                                                   S.s_off, S.ctr, P.slot_sum);
+        prof_end(DIF_PROF_ENCODE, st);
+        DIF_COUNT_LAUNCH(3);
         fuse_kernel<<<DIF_NUM_SMS * 2, 256, 0, st>>>(m, S.touched, S.ctr, P.slot_cnt, P.slot_sum, stats_dev);
     }
     return check_launch("dif_integrate");
@@ -463,7 +468,7 @@ int dif_map_query(const dif_map_view* map, const float* xyz, int64_t n, int32_t*
     if (!map || n < 0 || n >= (int64_t(1) << 31) || !n_valid_dev || (n > 0 && (!xyz || !slot_out || !rel_out))) return DIF_E_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(n_valid_dev, 0, sizeof(int32_t), st);
-    if (n > 0) map_query_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(to_dev(map), xyz, (int)n, slot_out, rel_out, n_valid_dev);
+    if (n > 0) { map_query_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(to_dev(map), xyz, (int)n, slot_out, rel_out, n_valid_dev); DIF_COUNT_LAUNCH(1); }
     return check_launch("dif_map_query");
 }
 
@@ -492,6 +497,7 @@ int dif_mesh_select(const dif_map_view* map, const int32_t* updated_slots, int64
     bitmap_count_kernel<<<n_chunks, SCAN_THREADS, 0, st>>>(bitmap, n_words, chunk_sum);
     bitmap_scan_kernel<<<1, 1024, 0, st>>>(chunk_sum, n_chunks, m.n_occ, m.capacity, ctr, counts_dev, 0);
     mesh_assign_kernel<<<n_chunks, SCAN_THREADS, 0, st>>>(m, bitmap, n_words, chunk_sum, ctr, block_slots_out, mapping_out, counts_dev);
+    DIF_COUNT_LAUNCH(k_max > 0 ? 4 : 3);
     return check_launch("dif_mesh_select");
 }
 

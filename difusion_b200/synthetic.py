@@ -71,9 +71,10 @@ def orbit_pose(frame: int, n_frames: int = 200):
     return yaw_pose(yaw, t)
 
 
-def render_depth(scene: Scene, R: np.ndarray, t: np.ndarray, noise_sigma: float = 0.0, seed: int = 0):
-    """Analytic ray cast: (H, W) float32 depth (NaN = invalid) and (H, W, 3) world-frame normals."""
-    u, v = np.meshgrid(np.arange(IMG_W, dtype=np.float64), np.arange(IMG_H, dtype=np.float64))
+def render_depth(scene: Scene, R: np.ndarray, t: np.ndarray, noise_sigma: float = 0.0, seed: int = 0, step: int = 1):
+    """Analytic ray cast of every `step`-th pixel of the 640x480 image: (H/step, W/step) float32 depth (NaN = invalid)
+    and world-frame normals.  step=2 equals rendering at full resolution followed by the tracker's nearest 1/2 sub-sampling."""
+    u, v = np.meshgrid(np.arange(0, IMG_W, step, dtype=np.float64), np.arange(0, IMG_H, step, dtype=np.float64))
     d_c = np.stack([(u - ICL_CX) / ICL_FX, (v - ICL_CY) / ICL_FY, np.ones_like(u)], axis=-1)   # z-depth param
     d_w = d_c @ R.T
     o = t.reshape(1, 1, 3)
@@ -145,9 +146,7 @@ def box_filter(points: np.ndarray, normals: np.ndarray, voxel: float = 0.02):
 def frame_points(scene: Scene, R: np.ndarray, t: np.ndarray, subsample: int = 2, noise_sigma: float = 0.0,
                  seed: int = 0, box: float = 0.02):
     """One 640x480 frame -> (pc_cam (N,3), normal_cam (N,3)) float32, as tracker.last_processed_pc would hold."""
-    depth, n_w = render_depth(scene, R, t, noise_sigma, seed)
-    d = depth[::subsample, ::subsample]                      # nearest, scale 0.5  (tracker.py:89-91)
-    n_w = n_w[::subsample, ::subsample]
+    d, n_w = render_depth(scene, R, t, noise_sigma, seed, step=subsample)    # nearest, scale 0.5  (tracker.py:89-91)
     h, w = d.shape
     sc = 1.0 / subsample
     fx, fy, cx, cy = (np.float32(ICL_FX * sc), np.float32(ICL_FY * sc), np.float32(ICL_CX * sc), np.float32(ICL_CY * sc))

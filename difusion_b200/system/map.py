@@ -109,11 +109,11 @@ class DenseIndexedMap:
             self._indexer = torch.full((self._n_cells,), -1, dtype=torch.long, device=device)
             self._n_occ_dev = torch.zeros(1, dtype=torch.int32, device=device)
             self._stats_dev = torch.zeros(_lib.DIF_STAT_COUNT, dtype=torch.int32, device=device)
-            self._stats_host = torch.zeros(_lib.DIF_STAT_COUNT, dtype=torch.int32).pin_memory()
-        self._stats_event = torch.cuda.Event()
-        self._stats_pending = False
+        # integrate results come back through a small ring of pinned buffers; the host only waits when it needs a value
+        self._stats_ring = [(torch.zeros(_lib.DIF_STAT_COUNT, dtype=torch.int32).pin_memory(), torch.cuda.Event()) for _ in range(8)]
+        self._stats_inflight = []            # [(ring index, max new slots of that call)]
+        self._stats_next = 0
         self._n_occ_host = 0
-        self._n_occ_ub = 0
         self._cap_phys = 0
         self._latent = self._pos = self._obs = self._optimized = self._dirty = None
         self._persist = None
@@ -147,20 +147,30 @@ class DenseIndexedMap:
             self._cap_phys = new_cap
             self._persist = torch.zeros(self._L.dif_integrate_persist_bytes(self._n_cells, new_cap), dtype=torch.uint8, device=dev)
 
-    def _sync_stats(self):
-        if self._stats_pending:
-            self._stats_event.synchronize()
-            self._stats_pending = False
-            st = self._stats_host.tolist()
+    def _retire_stats(self, block: bool):
+        """Consume finished integrate results (all of them when block=True)."""
+        err = None
+        while self._stats_inflight:
+            buf, ev = self._stats_ring[self._stats_inflight[0][0]]
+            if block:
+                ev.synchronize()
+            elif not ev.query():
+                break
+            self._stats_inflight.pop(0)
+            st = buf.tolist()
             self._n_occ_host = st[_lib.STAT_N_OCCUPIED]
-            self._n_occ_ub = self._n_occ_host
             self.last_integrate_stats = dict(n_kept=st[0], n_new=st[1], n_samples=st[2], n_updated=st[3], n_occupied=st[4],
                                              flags=st[5], n_focused=st[6])
             if st[_lib.STAT_FLAGS] & 2:
-                raise RuntimeError("PLIVox capacity exhausted inside dif_integrate (internal sizing error)")
-            if st[_lib.STAT_FLAGS] & 1:
-                raise IndexError("integrate_keyframe: surface points outside the map bounds were dropped "
+                err = RuntimeError("PLIVox capacity exhausted inside dif_integrate (internal sizing error)")
+            elif st[_lib.STAT_FLAGS] & 1:
+                err = IndexError("integrate_keyframe: surface points outside the map bounds were dropped "
                                  "(the reference indexes out of range here, map.py:313)")
+        if err is not None:
+            raise err
+
+    def _sync_stats(self):
+        self._retire_stats(block=True)
 
     @property
     def n_occupied(self) -> int:
@@ -170,7 +180,7 @@ class DenseIndexedMap:
     @n_occupied.setter
     def n_occupied(self, v: int):
         self._sync_stats()
-        self._n_occ_host = self._n_occ_ub = int(v)
+        self._n_occ_host = int(v)
         self._n_occ_dev.fill_(int(v))
 
     def _cap_ref(self) -> int:
@@ -251,15 +261,15 @@ class DenseIndexedMap:
         nrm = surface_normal.detach().contiguous().float()
         n = xyz.size(0)
         with self.modifying_lock:
-            # capacity: a call allocates at most 7 cells per point (own cell + 6 face neighbours)
-            ub = self._n_occ_ub + min(7 * n, self._n_cells)
-            if ub > self._cap_phys:
-                self._sync_stats()
-                ub = self._n_occ_host + min(7 * n, self._n_cells - self._n_occ_host)
-                if ub > self._cap_phys:
-                    torch.cuda.current_stream(self.device).synchronize()
-                    self._grow(_next_pow2(ub))
-            self._n_occ_ub = ub
+            # capacity: a call allocates at most 7 cells per point (own cell + 6 face neighbours); calls still in flight
+            # are accounted with the same bound, so the host never has to wait for a count in the steady state
+            self._retire_stats(block=False)
+            worst = min(7 * n, self._n_cells)
+            if len(self._stats_inflight) >= len(self._stats_ring) - 1 or \
+                    self._n_occ_host + sum(w for _, w in self._stats_inflight) + worst > self._cap_phys:
+                self._retire_stats(block=True)
+                if self._n_occ_host + worst > self._cap_phys:
+                    self._grow(_next_pow2(self._n_occ_host + worst))
             if n > self._scratch_points:
                 self._scratch_points = max(n, 1 << 15)
                 self._scratch = torch.empty(self._L.dif_integrate_scratch_bytes(self._scratch_points), dtype=torch.uint8, device=self.device)
@@ -270,9 +280,11 @@ class DenseIndexedMap:
             _lib.check(self._L.dif_integrate(ctypes.byref(view), self._prep.encoder.data_ptr(), xyz.data_ptr(), nrm.data_ptr(), n,
                                              _lib.ptr(unq), self._persist.data_ptr(), self._persist.numel(), self._scratch.data_ptr(),
                                              self._scratch.numel(), self._stats_dev.data_ptr(), st), "dif_integrate")
-            self._stats_host.copy_(self._stats_dev, non_blocking=True)
-            self._stats_event.record(torch.cuda.current_stream(self.device))
-            self._stats_pending = True
+            buf, ev = self._stats_ring[self._stats_next]
+            buf.copy_(self._stats_dev, non_blocking=True)
+            ev.record(torch.cuda.current_stream(self.device))
+            self._stats_inflight.append((self._stats_next, worst))
+            self._stats_next = (self._stats_next + 1) % len(self._stats_ring)
         return unq.view(torch.bool) if prune else None
 
     # ------------------------------------------------------------------ get_sdf (map.py:559-579)

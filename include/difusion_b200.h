@@ -152,6 +152,14 @@ int dif_marching_cubes(const int64_t* indexer, int nx, int ny, int nz, const int
 int dif_groupby_sum(const float* values /*[n][L]*/, const int64_t* indices /*[n]*/, int64_t n, int32_t L, int64_t C,
                     float* sum /*[C][L]*/, int32_t* count /*[C]*/, void* stream);
 
+/* ---- measurement hooks (bench.py; not part of the reference's interface) -------------------------------------
+ * dif_profile_hook: bracket the NEXT launch of the named kernel on this host thread with the two CUDA events
+ *   (cudaEvent_t handles, recorded on the launch stream); one-shot, NULL/NULL disarms.
+ * dif_launch_count: kernels launched by this host thread since the last reset. */
+enum { DIF_PROF_ENCODE = 0, DIF_PROF_ICP = 1, DIF_PROF_DECODE = 2, DIF_PROF_MC = 3, DIF_PROF_COUNT = 4 };
+int dif_profile_hook(int which, void* start_event, void* stop_event);
+uint64_t dif_launch_count(int reset);
+
 int dif_abi_version(void);
 const char* dif_last_error(void);        /* thread-local text of the last DIF_E_LAUNCH */
 
