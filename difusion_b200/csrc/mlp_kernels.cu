@@ -1,6 +1,8 @@
 // Network entry points of the C ABI: weight preparation, dif_decode, dif_encode (fp32 SIMT tiles).
 //   replaces reference network/utility.py:61-126 (forward_model) + di_decoder.py:55-86 / di_encoder.py:26-30.
 #include "mlp_simt.cuh"
+#include "decode_args.cuh"
+#include <stdlib.h>
 
 namespace dif {
 
@@ -42,20 +44,6 @@ __global__ void prepare_encoder_kernel(const float* __restrict__ blob, float* __
 }
 
 // ---------------------------------------------------------------------------------------------- decode
-// Where a tile's samples come from.  mode 0: explicit arrays (forward_model replacement).  mode 1: dense lattice, sample
-// s -> PLIVox s / n3, lattice point s % n3 (map.py:644-653: the reference materialises B*l^3 x 32 inputs).  mode 2: the same
-// lattice addressed through a compacted list of global lattice indices whose length lives on the device (map.py:667-679).
-struct DecodeArgs {
-    const float* P; const float* latent; const int32_t* rows; const float* xyz; int64_t n;
-    const int32_t* out_index; float sdf_sign; float* sdf; float* std; float* grad; int grad_head;
-    int mode; int lat_n; float lat_step, lat_a; const uint32_t* list; const int32_t* n_dev;
-};
-
-__device__ __forceinline__ float lattice_coord(const DecodeArgs& a, int i) {
-    // get_samples(): idx * vsize + a, then - 0.5 into network coordinates (utility.py:143-147, map.py:645-646)
-    return __fsub_rn(__fadd_rn(__fmul_rn((float)i, a.lat_step), a.lat_a), 0.5f);
-}
-
 template <bool GRAD>
 __global__ void __launch_bounds__(MLP_THREADS) decode_simt_kernel(DecodeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -154,8 +142,20 @@ static int grid_for_tiles(int64_t n_tiles, int ctas_per_sm) {
     return (int)(n_tiles < cap ? (n_tiles > 0 ? n_tiles : 1) : cap);
 }
 
+size_t decoder_tc_image_bytes();
+int prepare_decoder_tc(const float* P, unsigned char* image, cudaStream_t st);
+
+// 0 = auto (tensor cores for forward-only launches of >= 1024 samples), 1 = force fp32 SIMT, 2 = force tensor cores
+static int decode_path_override() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("DIF_DECODE_PATH"); v = !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 't' ? 2 : 0)); }
+    return v;
+}
+
 int launch_decode(DecodeArgs a, int64_t n_max, cudaStream_t st) {
     if (n_max <= 0) return DIF_OK;
+    const int ov = decode_path_override();
+    if (!a.grad && ov != 1 && (ov == 2 || n_max >= 1024)) return launch_decode_tc(a.P, a, n_max, st);
     const int64_t n_tiles = (n_max + MLP_T - 1) / MLP_T;
     const size_t smem = sizeof(DecoderSmem);
     prof_begin(DIF_PROF_DECODE, st);
@@ -201,14 +201,16 @@ int dif_profile_hook(int which, void* start_event, void* stop_event) {
 uint64_t dif_launch_count(int reset) { const uint64_t v = dif::g_launches; if (reset) dif::g_launches = 0; return v; }
 const char* dif_last_error(void) { return dif::g_last_error; }
 
-size_t dif_decoder_prepared_bytes(void) { return (size_t)DecW::FP32_END * sizeof(float); }
+size_t dif_decoder_prepared_bytes(void) { return (size_t)DecW::FP32_END * sizeof(float) + decoder_tc_image_bytes(); }
 size_t dif_encoder_prepared_bytes(void) { return (size_t)EncW::FP32_END * sizeof(float); }
 
 int dif_prepare_decoder(const float* blob_dev, void* prepared_dev, void* stream) {
     if (!blob_dev || !prepared_dev) return DIF_E_INVALID;
     prepare_decoder_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(blob_dev, (float*)prepared_dev);
     DIF_COUNT_LAUNCH(1);
-    return check_launch("prepare_decoder_kernel");
+    int rc = check_launch("prepare_decoder_kernel");
+    if (rc) return rc;
+    return prepare_decoder_tc((const float*)prepared_dev, (unsigned char*)prepared_dev + (size_t)DecW::FP32_END * sizeof(float), (cudaStream_t)stream);
 }
 
 int dif_prepare_encoder(const float* blob_dev, void* prepared_dev, void* stream) {

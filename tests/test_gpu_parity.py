@@ -307,3 +307,29 @@ def test_large_batch_properties(model, dev):
         sm, _ = net_util.forward_model(model.decoder, latent_input=lat[:4096].to(dev), xyz_input=(xyz[:4096] - d).to(dev))
         fd = ((sp - sm) / (2 * h)).cpu()[:, 0]
         assert float((fd - ga[:, c]).abs().median()) < 2e-3
+
+
+def test_tensor_core_decoder_matches_fp32_path(golden, model, dev):
+    """tcgen05 forward (3-pass fp16 split, fp32 TMEM accumulation) vs the exact-fp32 SIMT kernel and vs the reference fixture.
+    Forward-only launches of >= 1024 samples take the tensor-core kernel; a launch that also asks for d/dxyz takes the SIMT kernel."""
+    from difusion_b200.network import utility as net_util
+    fx = golden["decoder_kat"]
+    for n in (4096, 1024, 3000, 1025):                       # full tiles, ragged tail, single CTA with one / two slots
+        lat, xyz = _t(fx["latent"][:n], dev), _t(fx["xyz"][:n], dev)
+        sdf_tc, std_tc = net_util.forward_model(model.decoder, latent_input=lat, xyz_input=xyz)
+        sdf_32, std_32 = net_util.forward_model(model.decoder, latent_input=lat, xyz_input=xyz.clone().requires_grad_(True), no_detach=True)
+        a, b = sdf_tc.cpu().numpy()[:, 0], sdf_32.detach().cpu().numpy()[:, 0]
+        assert np.abs(a - b).max() < 2e-5, np.abs(a - b).max()
+        assert np.abs(std_tc.cpu().numpy() - std_32.detach().cpu().numpy()).max() < 2e-5
+        assert close(a, fx["sdf"][:n], TOL) and close(std_tc.cpu().numpy()[:, 0], fx["std"][:n], TOL)
+    # many tiles per CTA (persistent loop, both TMEM slots, phase bits wrapping) + large-magnitude latents
+    g = torch.Generator().manual_seed(11)
+    n = 148 * 128 * 5 + 77
+    lat = torch.randn(n, 29, generator=g) * 0.5
+    xyz = torch.rand(n, 3, generator=g) * 2 - 1
+    sdf_tc, std_tc = net_util.forward_model(model.decoder, latent_input=lat.to(dev), xyz_input=xyz.to(dev))
+    from oracle import dif_oracle as O
+    W = O.load_weights_npz(GOLDEN / "weights.npz")
+    pick = torch.cat([torch.arange(0, 4096), torch.arange(n - 4096, n), torch.randperm(n, generator=g)[:8192]])
+    o_sdf, o_std = O.decoder_forward(W.dec, lat[pick], xyz[pick])
+    assert close(sdf_tc.cpu()[pick, 0].numpy(), o_sdf.numpy(), TOL) and close(std_tc.cpu()[pick, 0].numpy(), o_std.numpy(), TOL)
