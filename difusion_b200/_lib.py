@@ -31,6 +31,7 @@ SIGNATURES = {
     "dif_abi_version": (C.c_int, []),
     "dif_profile_hook": (C.c_int, [C.c_int, _P, _P]),
     "dif_launch_count": (C.c_uint64, [C.c_int]),
+    "dif_debug_tc_timing": (C.c_int, [_P]),
     "dif_last_error": (C.c_char_p, []),
     "dif_decoder_prepared_bytes": (_SZ, []),
     "dif_encoder_prepared_bytes": (_SZ, []),

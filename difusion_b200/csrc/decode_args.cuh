@@ -33,5 +33,6 @@ __device__ __forceinline__ void decode_sample_source(const DecodeArgs& a, int64_
 }
 
 int launch_decode_tc(const void* prepared, DecodeArgs a, int64_t n_max, cudaStream_t st);
+int set_tc_timing_buffer(unsigned long long* dev_buf);
 
 }  // namespace dif

@@ -18,8 +18,15 @@
 //               alternates between the two tiles layer by layer, so the tensor pipe runs tile B's layer while the
 //               4 epilogue warps of tile A convert its accumulator (mbarrier hand-offs, tcgen05.commit).
 //
-// Warp roles: warps 0-3 = epilogue/gather warpgroup of slot 0, warps 4-7 = slot 1, warp 8 = TMEM allocator + MMA issuer.
+// Warp roles (20 warps): warps 0-7 = epilogue of slot 0, warps 8-15 = epilogue of slot 1, warp 16 = TMEM allocator + MMA
+// issuer, warps 17/18 = gather producers of slot 0/1 (warp 19 idles).  Inside a slot, epilogue warp w owns TMEM lanes
+// 32*(w&3).. (its 32 samples) and the column half (w>>2)&1 of every accumulator, so each SM sub-partition always has four
+// epilogue warps to hide tcgen05.ld / conversion latency.  A producer warp gathers a whole 128-sample tile with
+// coalesced loads (one sample's 29 latent floats + xyz per load instruction, lane = input column), three 16-row
+// batches in flight, and runs one tile ahead of the tensor pipe.
 #include <cuda_fp16.h>
+
+#include <atomic>
 
 #include "decode_args.cuh"
 #include "mlp_simt.cuh"
@@ -29,7 +36,9 @@ namespace dif {
 namespace tc {
 
 constexpr int TILE = 128;
-constexpr int THREADS = 9 * 32;
+constexpr int THREADS = 20 * 32;
+constexpr int MMA_WARP = 16;
+constexpr int PRODUCER_WARP0 = 17;
 
 // ---- byte layout of the tensor-core section of the prepared decoder buffer == its image in shared memory ----------
 constexpr uint32_t W0_B = 128 * 32 * 2, W1_B = 128 * 128 * 2, W2_B = 96 * 128 * 2, W3_B = 128 * 128 * 2;
@@ -38,14 +47,20 @@ constexpr uint32_t PLANE_B = OFF_W3 + W3_B;                 // 98304: one precis
 constexpr uint32_t OFF_BIAS = 2 * PLANE_B;                  // b0[128] b1[128] b2[96] b3[128] fp32
 constexpr uint32_t BIAS_B = 480 * 4;
 constexpr uint32_t IMAGE_B = OFF_BIAS + BIAS_B;             // 198528 bytes copied global -> shared per CTA
-constexpr uint32_t OFF_X = IMAGE_B;                         // per slot: hi [4][128][8] halves, lo [4][128][8] halves
-constexpr uint32_t X_PLANE_B = 4 * TILE * 16;               // 8192
-constexpr uint32_t OFF_BAR = OFF_X + 4 * X_PLANE_B;         // 231296
-constexpr uint32_t SMEM_B = OFF_BAR + 64 + 16;
+constexpr uint32_t OFF_X = IMAGE_B;                         // per slot: hi [4 k-chunks][128 rows][8 halves], then lo
+constexpr uint32_t X_CHUNK_B = TILE * 16 + 16;              // 2064: +16 B skews the banks of the 4 k-chunks (conflict-free gather stores)
+constexpr uint32_t X_PLANE_B = 4 * X_CHUNK_B;               // 8256 (hi -> lo plane lands 16 banks away)
+constexpr uint32_t OFF_BAR = OFF_X + 4 * X_PLANE_B;
+constexpr uint32_t SMEM_B = OFF_BAR + 96 + 16;            // 11 barriers (88 B) + TMEM base pointer
 static_assert(SMEM_B <= 232448, "shared memory budget");
 static_assert(IMAGE_B % 16 == 0, "bulk copy granularity");
 
-enum { BAR_W = 0, BAR_X0 = 1, BAR_X1 = 2, BAR_ACC0 = 3, BAR_ACC1 = 4, BAR_A0 = 5, BAR_A1 = 6 };
+enum { BAR_W = 0, BAR_X0 = 1, BAR_X1 = 2, BAR_ACC0 = 3, BAR_ACC1 = 4, BAR_A0 = 5, BAR_A1 = 6, BAR_XF0 = 7, BAR_XF1 = 8, BAR_E0 = 9, BAR_E1 = 10 };
+
+// Head weights (sdf head w4, std head wu) of up to 8 prepared decoders live in the constant bank, so the last layer's dot
+// products use them as FFMA operands.  A prepared decoder records its slot in the word that follows its weight image.
+constexpr int HEAD_SLOTS = 8;
+__constant__ float c_head_w[HEAD_SLOTS][2][128];
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -54,16 +69,30 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarri
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok = 0;
-    while (!ok) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    }
+// Waiting warps must not steal issue / MIO slots from the working warps of their sub-partition: the hardware suspend of
+// try_wait is only ~40 cycles, so a bare retry loop makes 16+ idle warps hammer the barrier (ncu: 62 M try_wait executions
+// per launch, producer warp at 0.1 IPC).  The loop therefore backs off with nanosleep between probes.
+template <int SLEEP_NS>
+__device__ __forceinline__ void mbar_wait_ns(uint32_t bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra DONE;\n\t"
+                 "RETRY:\n\t"
+                 "nanosleep.u32 %2;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@!p bra RETRY;\n\t"
+                 "DONE:\n\t}\n" :: "r"(bar), "r"(parity), "n"(SLEEP_NS) : "memory");
 }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { mbar_wait_ns<96>(bar, parity); }
+__device__ __forceinline__ void mbar_wait_tight(uint32_t bar, uint32_t parity) { mbar_wait_ns<20>(bar, parity); }   // MMA issuer
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -79,14 +108,16 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
 // instruction descriptor, kind::f16: D=f32, A=B=f16, both K-major, M=128
 __device__ __forceinline__ constexpr uint32_t idesc_f16(int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24); }
 
-__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-                 :: "r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+                 :: "r"(d), "l"(a), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
-                 :: "r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc) : "memory");
+                 :: "r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// descriptor + byte offset (the start-address field holds addr >> 4 in the low 14 bits; offsets never carry out of it)
+__device__ __forceinline__ uint64_t desc_advance(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
 }
@@ -99,6 +130,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&v)[32]) {
                    "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
                    "=r"(v[30]), "=r"(v[31]) : "r"(addr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t addr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+                   "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
+                   "=r"(v[30]), "=r"(v[31]) : "r"(addr));
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t addr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) : "r"(addr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
 __device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t (&v)[16]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
@@ -113,28 +162,78 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
     hi = *reinterpret_cast<const uint32_t*>(&h); lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-// ---- MMA issue for one layer of one slot (single thread) -------------------------------------------------------------
+// ---- MMA issue for one layer of one slot (one elected lane) ------------------------------------------------------------
 // A planes (hi, lo) either in TMEM (column address) or in shared memory (x tile); three passes hi*hi, lo*hi, hi*lo.
-template <int N, int KSTEPS_T, int KSTEPS_S>
-__device__ __forceinline__ void issue_layer(uint32_t acc, uint32_t a_hi_t, uint32_t a_lo_t, uint32_t x_hi_s, uint32_t x_lo_s,
-                                            uint32_t w_hi_s, uint32_t w_lo_s) {
-    constexpr uint32_t idesc = idesc_f16(N);
-    constexpr uint32_t WK = N * 16;                         // bytes per 8-wide K chunk of the weight slab
-    constexpr uint32_t XK = TILE * 16;
+// Deliberately ROLLED loops: the whole kernel has to stay inside the instruction cache (an earlier fully unrolled version
+// was 350 KB of SASS and ran every warp at ~0.1 IPC); per MMA the loop costs a handful of uniform-datapath instructions,
+// far below the 48-64 cycles the tensor pipe needs per instruction.
+__device__ __forceinline__ void issue_layer(uint32_t idesc, uint32_t wk_bytes, int ksteps_t, int ksteps_s, uint32_t acc,
+                                            uint32_t a_hi_t, uint32_t a_lo_t, uint64_t x_hi_d, uint64_t x_lo_d, uint64_t w_hi_d, uint64_t w_lo_d) {
+    const uint32_t w_step = (2 * wk_bytes) >> 4, x_step = (2 * X_CHUNK_B) >> 4;      // descriptor increments per K=16 step
     uint32_t accumulate = 0;
-#pragma unroll
+#pragma unroll 1
     for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t a_t = pass == 1 ? a_lo_t : a_hi_t, a_s = pass == 1 ? x_lo_s : x_hi_s, w = pass == 2 ? w_lo_s : w_hi_s;
+        const uint32_t a_t = pass == 1 ? a_lo_t : a_hi_t;
+        const uint64_t a_s = pass == 1 ? x_lo_d : x_hi_d;
+        uint64_t w = pass == 2 ? w_lo_d : w_hi_d;
+#pragma unroll 4
+        for (int ks = 0; ks < ksteps_t; ++ks) { mma_ts(acc, a_t + ks * 8, w, idesc, accumulate); accumulate = 1; w += w_step; }
+#pragma unroll 2
+        for (int ks = 0; ks < ksteps_s; ++ks) { mma_ss(acc, a_s + (uint64_t)(ks * x_step), w, idesc, accumulate); accumulate = 1; w += w_step; }
+    }
+}
+
+// Optional phase timing (tools/tc_timing.py): cycles spent per role and phase, summed per warp into a global buffer.
+__device__ unsigned long long* g_tc_timing = nullptr;       // [gridDim][20 warps][8 counters]
+#define TC_T0() const long long _t0 = timing ? clock64() : 0
+#define TC_ACC(slot_idx, t_from) do { if (timing) { const long long _n = clock64(); tacc[slot_idx] += _n - (t_from); (t_from) = _n; } } while (0)
+
+// ---- gather producer helpers ------------------------------------------------------------------------------------------
+// One producer warp per slot, one SAMPLE PER LANE: 32 independent loads per lane are in flight at once and the whole
+// 32-row pass costs ~150 warp instructions (a warp-cooperative, coalesced variant needed ~70 instructions PER ROW of
+// shuffles and address arithmetic and made the single producer warp the bottleneck of the kernel).
+__device__ __forceinline__ void gather_load_row(const DecodeArgs& a, int64_t sidx, int64_t n_total, int n3, float inv_n, float (&x)[32], bool& valid) {
+    int64_t row, out; int li;
+    decode_sample_source(a, sidx, n_total, n3, row, out, li);
+    valid = row >= 0;
+    const float* lp = a.latent + (valid ? row : 0) * DIF_L;
 #pragma unroll
-        for (int ks = 0; ks < KSTEPS_T; ++ks) {
-            mma_ts(acc, a_t + ks * 8, smem_desc(w + ks * 2 * WK, WK, 128), idesc, accumulate);
-            accumulate = 1;
-        }
+    for (int j = 0; j < DIF_L; ++j) x[j] = __ldg(lp + j);
+    if (a.mode == 0) {
+        const float* xp = a.xyz + (valid ? sidx : 0) * 3;
+        x[29] = __ldg(xp); x[30] = __ldg(xp + 1); x[31] = __ldg(xp + 2);
+    } else {
+        // lattice point -> (i, j, k) with exact float reciprocals (indices < 2^12), utility.py:143-147
+        const int q1 = (int)(((float)li + 0.5f) * inv_n), q2 = (int)(((float)q1 + 0.5f) * inv_n);
+        x[29] = lattice_coord(a, q2); x[30] = lattice_coord(a, q1 - q2 * a.lat_n); x[31] = lattice_coord(a, li - q1 * a.lat_n);
+    }
+}
+// (hi, lo) fp16 split of one sample's 32 inputs -> its row of the layer-0 A tile (k-chunk-major core-matrix layout; consecutive
+// lanes write consecutive 16-byte slots: conflict free)
+__device__ __forceinline__ void gather_store_row(const float (&x)[32], bool valid, int row, unsigned char* x_hi_p) {
 #pragma unroll
-        for (int ks = 0; ks < KSTEPS_S; ++ks) {
-            mma_ss(acc, smem_desc(a_s + ks * 2 * XK, XK, 128), smem_desc(w + (KSTEPS_T + ks) * 2 * WK, WK, 128), idesc, accumulate);
-            accumulate = 1;
-        }
+    for (int c = 0; c < 4; ++c) {
+        uint4 h, l;
+        split_pair(valid ? x[8 * c + 0] : 0.f, valid ? x[8 * c + 1] : 0.f, h.x, l.x); split_pair(valid ? x[8 * c + 2] : 0.f, valid ? x[8 * c + 3] : 0.f, h.y, l.y);
+        split_pair(valid ? x[8 * c + 4] : 0.f, valid ? x[8 * c + 5] : 0.f, h.z, l.z); split_pair(valid ? x[8 * c + 6] : 0.f, valid ? x[8 * c + 7] : 0.f, h.w, l.w);
+        *reinterpret_cast<uint4*>(x_hi_p + c * X_CHUNK_B + row * 16) = h;
+        *reinterpret_cast<uint4*>(x_hi_p + X_PLANE_B + c * X_CHUNK_B + row * 16) = l;
+    }
+}
+
+// bias + ReLU + hi/lo split of NCOL (32 or 16) accumulator columns -> packed fp16 A-operand columns in TMEM
+template <int NCOL>
+__device__ __forceinline__ void convert_chunk(const uint32_t* v, const float* b, uint32_t a_hi, uint32_t a_lo) {
+    uint32_t hi[NCOL / 2], lo[NCOL / 2];
+#pragma unroll
+    for (int j = 0; j < NCOL / 2; ++j) {
+        const float2 bb = *reinterpret_cast<const float2*>(b + 2 * j);
+        split_pair(fmaxf(__uint_as_float(v[2 * j]) + bb.x, 0.f), fmaxf(__uint_as_float(v[2 * j + 1]) + bb.y, 0.f), hi[j], lo[j]);
+    }
+    if constexpr (NCOL == 32) {
+        tmem_st16(a_hi, *reinterpret_cast<const uint32_t(*)[16]>(hi)); tmem_st16(a_lo, *reinterpret_cast<const uint32_t(*)[16]>(lo));
+    } else {
+        tmem_st8(a_hi, hi); tmem_st8(a_lo, lo);
     }
 }
 
@@ -142,169 +241,229 @@ __global__ void __launch_bounds__(THREADS, 1) decode_tc_kernel(const unsigned ch
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bar0 = sbase + OFF_BAR;
-    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 64);
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 96);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     const int64_t n_total = a.n_dev ? (int64_t)*a.n_dev : a.n;
     const int64_t n_tiles = (n_total + TILE - 1) / TILE;
+    const bool timing = g_tc_timing != nullptr;
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tcur = timing ? clock64() : 0;
 
     if (threadIdx.x == 0) {
         mbar_init(bar0 + 8 * BAR_W, 1);
-        mbar_init(bar0 + 8 * BAR_X0, TILE); mbar_init(bar0 + 8 * BAR_X1, TILE);
+        mbar_init(bar0 + 8 * BAR_X0, 1); mbar_init(bar0 + 8 * BAR_X1, 1);          // producer warp -> MMA: layer-0 A tile ready
+        mbar_init(bar0 + 8 * BAR_XF0, 8); mbar_init(bar0 + 8 * BAR_XF1, 8);        // epilogue warps -> producer: x tile free again
+        mbar_init(bar0 + 8 * BAR_E0, 8); mbar_init(bar0 + 8 * BAR_E1, 8);          // epilogue warps -> MMA: last accumulator of the tile consumed
         mbar_init(bar0 + 8 * BAR_ACC0, 1); mbar_init(bar0 + 8 * BAR_ACC1, 1);
-        mbar_init(bar0 + 8 * BAR_A0, TILE); mbar_init(bar0 + 8 * BAR_A1, TILE);
+        mbar_init(bar0 + 8 * BAR_A0, 8); mbar_init(bar0 + 8 * BAR_A1, 8);          // one elected arrival per epilogue warp of the slot
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) {
+    if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_ptr_s)), "n"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_ptr_s;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_ptr_s, 0);      // provably warp-uniform for the MMA issuer
 
-    if (warp == 8) {
-        // ===================================================== weight load + MMA issuer (one elected lane)
+    if (warp == MMA_WARP) {
+        // ===================================================== weight load + MMA issuer
+        // The whole warp runs this loop with warp-uniform values (descriptors live in uniform registers); only the
+        // tcgen05 instructions themselves are executed by one elected lane.
         if (lane == 0) {
             mbar_expect_tx(bar0 + 8 * BAR_W, IMAGE_B);
             constexpr uint32_t CH = 32768;
             for (uint32_t off = 0; off < IMAGE_B; off += CH) bulk_g2s(sbase + off, image + off, (IMAGE_B - off) < CH ? (IMAGE_B - off) : CH, bar0 + 8 * BAR_W);
-            mbar_wait(bar0 + 8 * BAR_W, 0);
-            const uint32_t w_hi = sbase, w_lo = sbase + PLANE_B;
-            uint32_t ph_x[2] = {0, 0}, ph_a[2] = {0, 0};
-            for (int64_t it = 0;; ++it) {
-                const int64_t t0 = blockIdx.x + (int64_t)gridDim.x * (2 * it), t1 = t0 + gridDim.x;
-                const bool live[2] = {t0 < n_tiles, t1 < n_tiles};
-                if (!live[0]) break;
+        }
+        __syncwarp();
+        mbar_wait(bar0 + 8 * BAR_W, 0);
+        TC_ACC(0, tcur);                                   // [0] weight image load
+        uint64_t wd_hi[4], wd_lo[4], xd_hi[2], xd_lo[2];
+        {
+            const uint32_t offs[4] = {OFF_W0, OFF_W1, OFF_W2, OFF_W3};
+            const uint32_t wk[4] = {128 * 16, 128 * 16, 96 * 16, 128 * 16};
 #pragma unroll
-                for (int layer = 0; layer < 4; ++layer) {
+            for (int l = 0; l < 4; ++l) { wd_hi[l] = smem_desc(sbase + offs[l], wk[l], 128); wd_lo[l] = smem_desc(sbase + PLANE_B + offs[l], wk[l], 128); }
 #pragma unroll
-                    for (int s = 0; s < 2; ++s) {
-                        if (!live[s]) continue;
-                        const uint32_t acc = tmem + s * 256, a_hi = acc + 128, a_lo = acc + 192;
-                        const uint32_t x_hi = sbase + OFF_X + s * 2 * X_PLANE_B, x_lo = x_hi + X_PLANE_B;
-                        if (layer == 0) { mbar_wait(bar0 + 8 * (BAR_X0 + s), ph_x[s]); ph_x[s] ^= 1; }
-                        else { mbar_wait(bar0 + 8 * (BAR_A0 + s), ph_a[s]); ph_a[s] ^= 1; }
-                        tc_fence_after();
-                        if (layer == 0) issue_layer<128, 0, 2>(acc, 0, 0, x_hi, x_lo, w_hi + OFF_W0, w_lo + OFF_W0);
-                        else if (layer == 1) issue_layer<128, 8, 0>(acc, a_hi, a_lo, 0, 0, w_hi + OFF_W1, w_lo + OFF_W1);
-                        else if (layer == 2) issue_layer<96, 8, 0>(acc, a_hi, a_lo, 0, 0, w_hi + OFF_W2, w_lo + OFF_W2);
-                        else issue_layer<128, 6, 2>(acc, a_hi, a_lo, x_hi, x_lo, w_hi + OFF_W3, w_lo + OFF_W3);
+            for (int q = 0; q < 2; ++q) {
+                xd_hi[q] = smem_desc(sbase + OFF_X + q * 2 * X_PLANE_B, X_CHUNK_B, 128);
+                xd_lo[q] = smem_desc(sbase + OFF_X + q * 2 * X_PLANE_B + X_PLANE_B, X_CHUNK_B, 128);
+            }
+        }
+        uint32_t ph_x = 0, ph_a = 0, ph_e = 0;             // bit s = phase parity of slot s
+        for (int64_t it = 0;; ++it) {
+            const int64_t t0 = blockIdx.x + (int64_t)gridDim.x * (2 * it), t1 = t0 + gridDim.x;
+            const bool live[2] = {t0 < n_tiles, t1 < n_tiles};
+            if (!live[0]) break;
+#pragma unroll 1
+            for (int layer = 0; layer < 4; ++layer) {
+#pragma unroll 1
+                for (int s = 0; s < 2; ++s) {
+                    if (!live[s]) continue;
+                    const uint32_t acc = tmem + s * 256, a_hi = acc + 128, a_lo = acc + 192;
+                    if (layer == 0) {
+                        mbar_wait_tight(bar0 + 8 * (BAR_X0 + s), (ph_x >> s) & 1); ph_x ^= 1u << s;
+                        // the previous tile's head evaluation must have finished reading this slot's accumulator
+                        if (it > 0) { mbar_wait_tight(bar0 + 8 * (BAR_E0 + s), (ph_e >> s) & 1); ph_e ^= 1u << s; }
+                    }
+                    else { mbar_wait_tight(bar0 + 8 * (BAR_A0 + s), (ph_a >> s) & 1); ph_a ^= 1u << s; }
+                    TC_ACC(1, tcur);                       // [1] MMA warp waiting for operands
+                    tc_fence_after();
+                    if (elect_one()) {
+                        if (layer == 0) issue_layer(idesc_f16(128), 128 * 16, 0, 2, acc, 0, 0, s ? xd_hi[1] : xd_hi[0], s ? xd_lo[1] : xd_lo[0], wd_hi[0], wd_lo[0]);
+                        else if (layer == 1) issue_layer(idesc_f16(128), 128 * 16, 8, 0, acc, a_hi, a_lo, 0, 0, wd_hi[1], wd_lo[1]);
+                        else if (layer == 2) issue_layer(idesc_f16(96), 96 * 16, 8, 0, acc, a_hi, a_lo, 0, 0, wd_hi[2], wd_lo[2]);
+                        else issue_layer(idesc_f16(128), 128 * 16, 8, 0, acc, a_hi, a_lo, 0, 0, wd_hi[3], wd_lo[3]);     // [h2 | x] both in TMEM
                         mma_commit(bar0 + 8 * (BAR_ACC0 + s));
                     }
+                    __syncwarp();
+                    TC_ACC(2, tcur);                       // [2] MMA warp issuing
                 }
             }
         }
-        __syncwarp();
+    } else if (warp >= PRODUCER_WARP0) {
+        // ===================================================== gather producer of slot s: global -> (hi, lo) fp16 -> layer-0 A tile in smem
+        const int s = warp - PRODUCER_WARP0;
+        if (s < 2) {
+            unsigned char* x_hi_p = smem + OFF_X + s * 2 * X_PLANE_B;
+            const int n3 = a.lat_n * a.lat_n * a.lat_n;
+            const float inv_n = 1.0f / (float)(a.lat_n > 0 ? a.lat_n : 1);
+            float xa[32], xb[32];                       // two 32-sample passes in flight (one sample per lane)
+            bool va = false, vb = false;
+            uint32_t ph_xf = 0;
+            int64_t tile = blockIdx.x + (int64_t)gridDim.x * s;
+            if (tile < n_tiles) gather_load_row(a, tile * TILE + lane, n_total, n3, inv_n, xa, va);
+            for (int64_t it = 0; tile < n_tiles; ++it) {
+                TC_ACC(0, tcur);                             // producer [0]: prefetch of the first pass
+                if (it > 0) { mbar_wait(bar0 + 8 * (BAR_XF0 + s), ph_xf); ph_xf ^= 1; }      // previous tile's x is parked in TMEM (layer-2 epilogue)
+                TC_ACC(1, tcur);                             // producer [1]: waiting for the x tile to be free
+                gather_load_row(a, tile * TILE + 32 + lane, n_total, n3, inv_n, xb, vb);
+                gather_store_row(xa, va, lane, x_hi_p);
+                gather_load_row(a, tile * TILE + 64 + lane, n_total, n3, inv_n, xa, va);
+                gather_store_row(xb, vb, 32 + lane, x_hi_p);
+                gather_load_row(a, tile * TILE + 96 + lane, n_total, n3, inv_n, xb, vb);
+                gather_store_row(xa, va, 64 + lane, x_hi_p);
+                const int64_t next = tile + 2 * (int64_t)gridDim.x;
+                if (next < n_tiles) gather_load_row(a, next * TILE + lane, n_total, n3, inv_n, xa, va);   // run ahead while the tensor pipe works
+                gather_store_row(xb, vb, 96 + lane, x_hi_p);
+                TC_ACC(3, tcur);                             // producer [3]: streaming the tile
+                fence_async_smem();                          // generic-proxy stores -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar0 + 8 * (BAR_X0 + s));
+                TC_ACC(4, tcur);                             // producer [4]: proxy fence + arrive
+                tile = next;
+            }
+        }
     } else {
-        // ===================================================== gather + epilogue warpgroup of slot s (one sample per thread)
-        const int s = warp >> 2;
-        const int row = threadIdx.x & 127;
-        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        // ===================================================== epilogue warps of slot s
+        const int s = warp >> 3;
+        const int quad = warp & 3, half = (warp >> 2) & 1;
+        const int row = quad * 32 + lane;           // the sample this thread converts / outputs (TMEM lane)
+        const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
         const uint32_t acc = tmem + s * 256 + lane_base, a_hi = acc + 128, a_lo = acc + 192;
-        unsigned char* x_hi_p = smem + OFF_X + s * 2 * X_PLANE_B;
-        unsigned char* x_lo_p = x_hi_p + X_PLANE_B;
         const float* bias = reinterpret_cast<const float*>(smem + OFF_BIAS);
         const int n3 = a.lat_n * a.lat_n * a.lat_n;
         uint32_t ph_acc = 0;
-        bool weights_ready = false;
+        // the head this warp evaluates (half 0: sdf, half 1: std); weights come from the constant bank (c_head_w)
+        const int head_slot = *reinterpret_cast<const int*>(image + IMAGE_B);         // which constant-memory slot holds this decoder's heads
+        const float head_bias = __ldg(P + (half ? DecW::bu : DecW::b4));
+        mbar_wait(bar0 + 8 * BAR_W, 0);               // biases arrive with the weight image
         for (int64_t it = 0;; ++it) {
             const int64_t tile = blockIdx.x + (int64_t)gridDim.x * (2 * it + s);
             if (tile >= n_tiles) break;
-            const int64_t sidx = tile * TILE + row;
-            int64_t src_row, out; int li;
-            decode_sample_source(a, sidx, n_total, n3, src_row, out, li);
-            {   // ---- gather the 32 inputs of this sample, split, and write the layer-0 A tile (k-chunk-major, conflict free)
-                float x[32];
-                if (src_row >= 0) {
-                    const float* lp = a.latent + src_row * DIF_L;
-#pragma unroll
-                    for (int j = 0; j < DIF_L; ++j) x[j] = __ldg(lp + j);
-                    if (a.mode == 0) {
-                        x[29] = __ldg(a.xyz + sidx * 3); x[30] = __ldg(a.xyz + sidx * 3 + 1); x[31] = __ldg(a.xyz + sidx * 3 + 2);
-                    } else {
-                        const int nn = a.lat_n;
-                        x[29] = lattice_coord(a, li / (nn * nn)); x[30] = lattice_coord(a, (li / nn) % nn); x[31] = lattice_coord(a, li % nn);
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] = 0.f;
-                }
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint4 h, l;
-                    split_pair(x[8 * c + 0], x[8 * c + 1], h.x, l.x); split_pair(x[8 * c + 2], x[8 * c + 3], h.y, l.y);
-                    split_pair(x[8 * c + 4], x[8 * c + 5], h.z, l.z); split_pair(x[8 * c + 6], x[8 * c + 7], h.w, l.w);
-                    *reinterpret_cast<uint4*>(x_hi_p + c * (TILE * 16) + row * 16) = h;
-                    *reinterpret_cast<uint4*>(x_lo_p + c * (TILE * 16) + row * 16) = l;
-                }
-                fence_async_smem();                         // generic-proxy stores -> visible to the tensor core (async proxy)
-                mbar_arrive(bar0 + 8 * (BAR_X0 + s));
-            }
-            if (!weights_ready) { mbar_wait(bar0 + 8 * BAR_W, 0); weights_ready = true; }     // biases arrive with the weight image
-            // ---- hidden layers 0..2: accumulator -> +bias, ReLU, split -> fp16 A operand in TMEM
-#pragma unroll
+            TC_ACC(7, tcur);
+            // ---- hidden layers 0..2: this warp converts its column half: accumulator -> +bias, ReLU, split -> fp16 A operand in TMEM
+#pragma unroll 1
             for (int layer = 0; layer < 3; ++layer) {
-                const int ncol = layer == 2 ? 96 : 128;
-                const float* b = bias + (layer == 0 ? 0 : (layer == 1 ? 128 : 256));
+                const int hw = layer == 2 ? 48 : 64;          // columns per half (layer 2 has 96 outputs)
+                const int c_base = half * hw;
+                const float* b = bias + layer * 128 + c_base;  // b0 @0, b1 @128, b2 @256
                 mbar_wait(bar0 + 8 * (BAR_ACC0 + s), ph_acc); ph_acc ^= 1;
+                TC_ACC(4, tcur);                               // [4] epilogue warps waiting for the accumulator
                 tc_fence_after();
+                if (layer == 2) {
+                    // Layers 0-2 are done with the 64 A-operand columns.  Park this sample's 32 inputs (hi plane by half-0 warps, lo plane by
+                    // half-1 warps) in the 16 A-operand columns that layer 2's 96 outputs leave free, so that the skip
+                    // connection of layer 3 reads [h2 | x] entirely from TMEM and the producer may refill the x tile now
+                    // (it then overlaps with layer 3 and the head evaluation instead of sitting on the critical path).
+                    const unsigned char* xp = smem + OFF_X + s * 2 * X_PLANE_B + half * X_PLANE_B + row * 16;
+                    uint32_t xv[16];
 #pragma unroll
-                for (int c0 = 0; c0 < 128; c0 += 32) {
-                    if (c0 < ncol) {
-                        uint32_t v[32], hi[16], lo[16];
-                        tmem_ld32(acc + c0, v);
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float2 bb = *reinterpret_cast<const float2*>(b + c0 + 2 * j);
-                            const float f0 = fmaxf(__uint_as_float(v[2 * j]) + bb.x, 0.f), f1 = fmaxf(__uint_as_float(v[2 * j + 1]) + bb.y, 0.f);
-                            split_pair(f0, f1, hi[j], lo[j]);
-                        }
-                        tmem_st16(a_hi + c0 / 2, hi);
-                        tmem_st16(a_lo + c0 / 2, lo);
+                    for (int cc = 0; cc < 4; ++cc) {
+                        const uint4 q = *reinterpret_cast<const uint4*>(xp + cc * X_CHUNK_B);
+                        xv[4 * cc] = q.x; xv[4 * cc + 1] = q.y; xv[4 * cc + 2] = q.z; xv[4 * cc + 3] = q.w;
                     }
+                    tmem_st16((half ? a_lo : a_hi) + 48, xv);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar0 + 8 * (BAR_XF0 + s));    // (our own generic-proxy reads of x are complete)
+                }
+#pragma unroll 1
+                for (int c = 0; c < hw; c += 32) {             // 32 columns per iteration (the last one of layer 2 has 16)
+                    uint32_t v0[16], v1[16];
+                    const bool two = c + 16 < hw;
+                    tmem_ld16_nowait(acc + c_base + c, v0);
+                    if (two) tmem_ld16_nowait(acc + c_base + c + 16, v1);
+                    tmem_ld_wait();
+                    convert_chunk<16>(v0, b + c, a_hi + (c_base + c) / 2, a_lo + (c_base + c) / 2);
+                    if (two) convert_chunk<16>(v1, b + c + 16, a_hi + (c_base + c) / 2 + 8, a_lo + (c_base + c) / 2 + 8);
                 }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
-                mbar_arrive(bar0 + 8 * (BAR_A0 + s));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar0 + 8 * (BAR_A0 + s));
+                TC_ACC(5, tcur);                               // [5] hidden-layer conversion
             }
-            // ---- layer 3 + the two heads on CUDA cores (std from the last layer's input, di_decoder.py:65-70)
+            // ---- layer 3 + one head per column-half warp on CUDA cores (half 0 -> sdf, half 1 -> std; di_decoder.py:65-70,84)
             mbar_wait(bar0 + 8 * (BAR_ACC0 + s), ph_acc); ph_acc ^= 1;
+            TC_ACC(4, tcur);
             tc_fence_after();
-            float p_sdf = 0.f, p_std = 0.f;
-#pragma unroll
+            float p0 = 0.f, p1 = 0.f;
+            const float* hw_c = c_head_w[head_slot][half];     // constant bank: the weight is an FFMA operand, no load instruction
+#pragma unroll 1
             for (int c0 = 0; c0 < 128; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(acc + c0, v);
+                uint32_t v0[16], v1[16];
+                tmem_ld16_nowait(acc + c0, v0);
+                tmem_ld16_nowait(acc + c0 + 16, v1);
+                tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 bb = *reinterpret_cast<const float4*>(bias + 352 + c0 + j);
-                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(P + DecW::w4 + c0 + j));
-                    const float4 wu = __ldg(reinterpret_cast<const float4*>(P + DecW::wu + c0 + j));
-                    const float h0 = fmaxf(__uint_as_float(v[j]) + bb.x, 0.f), h1 = fmaxf(__uint_as_float(v[j + 1]) + bb.y, 0.f);
-                    const float h2 = fmaxf(__uint_as_float(v[j + 2]) + bb.z, 0.f), h3 = fmaxf(__uint_as_float(v[j + 3]) + bb.w, 0.f);
-                    p_sdf = fmaf(w4.x, h0, p_sdf); p_sdf = fmaf(w4.y, h1, p_sdf); p_sdf = fmaf(w4.z, h2, p_sdf); p_sdf = fmaf(w4.w, h3, p_sdf);
-                    p_std = fmaf(wu.x, h0, p_std); p_std = fmaf(wu.y, h1, p_std); p_std = fmaf(wu.z, h2, p_std); p_std = fmaf(wu.w, h3, p_std);
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 b0 = *reinterpret_cast<const float4*>(bias + 352 + c0 + j), b1 = *reinterpret_cast<const float4*>(bias + 352 + c0 + 16 + j);
+                    p0 = fmaf(hw_c[c0 + j], fmaxf(__uint_as_float(v0[j]) + b0.x, 0.f), p0);
+                    p0 = fmaf(hw_c[c0 + j + 1], fmaxf(__uint_as_float(v0[j + 1]) + b0.y, 0.f), p0);
+                    p0 = fmaf(hw_c[c0 + j + 2], fmaxf(__uint_as_float(v0[j + 2]) + b0.z, 0.f), p0);
+                    p0 = fmaf(hw_c[c0 + j + 3], fmaxf(__uint_as_float(v0[j + 3]) + b0.w, 0.f), p0);
+                    p1 = fmaf(hw_c[c0 + 16 + j], fmaxf(__uint_as_float(v1[j]) + b1.x, 0.f), p1);
+                    p1 = fmaf(hw_c[c0 + 16 + j + 1], fmaxf(__uint_as_float(v1[j + 1]) + b1.y, 0.f), p1);
+                    p1 = fmaf(hw_c[c0 + 16 + j + 2], fmaxf(__uint_as_float(v1[j + 2]) + b1.z, 0.f), p1);
+                    p1 = fmaf(hw_c[c0 + 16 + j + 3], fmaxf(__uint_as_float(v1[j + 3]) + b1.w, 0.f), p1);
                 }
             }
-            tc_fence_before();                               // accumulator reads are complete before the next tile's MMA may overwrite it
-            if (src_row >= 0) {
-                a.sdf[out] = a.sdf_sign * tanhf(p_sdf + __ldg(P + DecW::b4));
-                a.std[out] = 0.05f + 0.5f * softplus_ref(p_std + __ldg(P + DecW::bu));
-            } else if (sidx < n_total && a.mode == 0 && !a.out_index) {
-                a.sdf[out] = 0.f; a.std[out] = 0.f;
-            }
+            tc_fence_before();                               // accumulator reads complete: the next tile's layer 0 may overwrite it
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar0 + 8 * (BAR_E0 + s));
+            const int64_t sidx = tile * TILE + row;
+            int64_t src_row, out; int li_unused;
+            decode_sample_source(a, sidx, n_total, n3, src_row, out, li_unused);
+            const float pre = p0 + p1 + head_bias;
+            float* dst = half ? a.std : a.sdf;
+            if (src_row >= 0) dst[out] = half ? 0.05f + 0.5f * softplus_ref(pre) : a.sdf_sign * tanhf(pre);
+            else if (sidx < n_total && a.mode == 0 && !a.out_index) dst[out] = 0.f;
+            TC_ACC(6, tcur);                                   // [6] last layer + heads + output
         }
+    }
+    if (timing && lane == 0) {
+        for (int k = 0; k < 8; ++k) g_tc_timing[((size_t)blockIdx.x * 20 + warp) * 8 + k] = (unsigned long long)tacc[k];
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(512));
+    if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(512));
 }
 
 // ---- weight image: fp16 hi/lo planes in the no-swizzle K-major core-matrix layout, + biases -----------------------------
 // element (n, k) of a layer with N rows lives at  (k/8)*(N*16) + n*16 + (k%8)*2  bytes inside its slab.
-__global__ void prepare_tc_kernel(const float* __restrict__ P, unsigned char* __restrict__ image) {
+__global__ void prepare_tc_kernel(const float* __restrict__ P, unsigned char* __restrict__ image, int head_slot) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     const int offW[4] = {DecW::W0, DecW::W1, DecW::W2, DecW::W3};
     const int Ns[4] = {128, 128, 96, 128}, Ks[4] = {32, 128, 128, 128};
@@ -321,6 +480,7 @@ __global__ void prepare_tc_kernel(const float* __restrict__ P, unsigned char* __
             *reinterpret_cast<__half*>(image + PLANE_B + o) = lo;
         }
     }
+    if (tid == 0) *reinterpret_cast<int*>(image + IMAGE_B) = head_slot;
     float* b = reinterpret_cast<float*>(image + OFF_BIAS);
     for (int i = tid; i < 128; i += nth) {
         b[i] = P[DecW::b0 + i]; b[128 + i] = P[DecW::b1 + i]; b[352 + i] = P[DecW::b3 + i];
@@ -330,10 +490,19 @@ __global__ void prepare_tc_kernel(const float* __restrict__ P, unsigned char* __
 
 }  // namespace tc
 
-size_t decoder_tc_image_bytes() { return tc::IMAGE_B; }
+size_t decoder_tc_image_bytes() { return tc::IMAGE_B + 16; }
+
+int set_tc_timing_buffer(unsigned long long* dev_buf) {
+    return cudaMemcpyToSymbol(tc::g_tc_timing, &dev_buf, sizeof(dev_buf)) == cudaSuccess ? DIF_OK : DIF_E_LAUNCH;
+}
 
 int prepare_decoder_tc(const float* P, unsigned char* image, cudaStream_t st) {
-    tc::prepare_tc_kernel<<<64, 256, 0, st>>>(P, image);
+    static std::atomic<int> next_slot{0};
+    const int slot = next_slot.fetch_add(1) % tc::HEAD_SLOTS;
+    // w4[128] and wu[128] are adjacent in the prepared fp32 section: one device-to-device copy into the constant bank
+    if (cudaMemcpyToSymbolAsync(tc::c_head_w, P + DecW::w4, 2 * 128 * sizeof(float), (size_t)slot * 2 * 128 * sizeof(float),
+                                cudaMemcpyDeviceToDevice, st) != cudaSuccess) return check_launch("cudaMemcpyToSymbolAsync(c_head_w)");
+    tc::prepare_tc_kernel<<<64, 256, 0, st>>>(P, image, slot);
     DIF_COUNT_LAUNCH(1);
     return check_launch("prepare_tc_kernel");
 }

@@ -159,6 +159,9 @@ int dif_groupby_sum(const float* values /*[n][L]*/, const int64_t* indices /*[n]
 enum { DIF_PROF_ENCODE = 0, DIF_PROF_ICP = 1, DIF_PROF_DECODE = 2, DIF_PROF_MC = 3, DIF_PROF_COUNT = 4 };
 int dif_profile_hook(int which, void* start_event, void* stop_event);
 uint64_t dif_launch_count(int reset);
+/* dif_debug_tc_timing: dev_buf = uint64[148*20*8] or NULL; when set, the tensor-core decoder records per-warp phase cycles
+ * (development aid used by tools/tc_timing.py). */
+int dif_debug_tc_timing(void* dev_buf);
 
 int dif_abi_version(void);
 const char* dif_last_error(void);        /* thread-local text of the last DIF_E_LAUNCH */
