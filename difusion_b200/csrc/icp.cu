@@ -5,11 +5,11 @@
 // The reference runs ~15 torch launches + 2 boolean-mask syncs for the lookup, cuBLAS forward, an autograd backward that
 // also builds parameter gradients, and three host syncs (.cpu() x2, .item()) per Gauss-Newton iteration.
 #include "mlp_simt.cuh"
+#include "icp_args.cuh"
+#include <stdlib.h>
 
 namespace dif {
 
-struct MapRO { const int64_t* indexer; const float* latent; const float* obs; Grid g; float ignore_th; };
-struct Pose { float Rc[9], tc[3], Rd[9], td[3], Rl[9]; };      // composite (last*delta), delta, last rotation
 
 constexpr int ICP_VALS = 32;     // 21 upper-tri H + 6 g + E + M, padded
 
@@ -169,6 +169,15 @@ int dif_icp_linearize(const dif_map_view* map, const void* decoder_prepared, con
     unsigned int* counter = c.take<unsigned int>(1);
     cudaMemsetAsync(counter, 0, sizeof(unsigned int), st);
     cudaMemsetAsync(out_dev, 0, 44 * sizeof(double), st);
+    // tensor-core path (decoder forward + backward on tcgen05) for frames worth of points; DIF_ICP_PATH=simt forces fp32 SIMT
+    const char* path_env = getenv("DIF_ICP_PATH");                     // read per call so tests can compare both paths
+    const bool force_simt = path_env && path_env[0] == 's';
+    if (!force_simt && n >= 2048) {
+        double* accum = reinterpret_cast<double*>(partials);               // 32 fp64 accumulators at the head of the scratch
+        cudaMemsetAsync(accum, 0, 32 * sizeof(double), st);
+        IcpTcArgs a{m, obs_xyz, (int)n, p, huber_k, want_grad, accum, counter, out_dev};
+        return launch_icp_tc(decoder_prepared, a, st);
+    }
     const int64_t n_tiles = (n + MLP_T - 1) / MLP_T;
     int grid = (int)(n_tiles < DIF_NUM_SMS * 3 ? n_tiles : DIF_NUM_SMS * 3);
     if (grid < 1) grid = 1;

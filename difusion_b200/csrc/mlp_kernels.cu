@@ -146,10 +146,9 @@ size_t decoder_tc_image_bytes();
 int prepare_decoder_tc(const float* P, unsigned char* image, cudaStream_t st);
 
 // 0 = auto (tensor cores for forward-only launches of >= 1024 samples), 1 = force fp32 SIMT, 2 = force tensor cores
-static int decode_path_override() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("DIF_DECODE_PATH"); v = !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 't' ? 2 : 0)); }
-    return v;
+static int decode_path_override() {      // read per call so tests can compare both paths
+    const char* e = getenv("DIF_DECODE_PATH");
+    return !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 't' ? 2 : 0));
 }
 
 int launch_decode(DecodeArgs a, int64_t n_max, cudaStream_t st) {

@@ -333,3 +333,41 @@ def test_tensor_core_decoder_matches_fp32_path(golden, model, dev):
     pick = torch.cat([torch.arange(0, 4096), torch.arange(n - 4096, n), torch.randperm(n, generator=g)[:8192]])
     o_sdf, o_std = O.decoder_forward(W.dec, lat[pick], xyz[pick])
     assert close(sdf_tc.cpu()[pick, 0].numpy(), o_sdf.numpy(), TOL) and close(std_tc.cpu()[pick, 0].numpy(), o_std.numpy(), TOL)
+
+
+def test_tensor_core_icp_matches_fp32_path(golden, model, dev, monkeypatch):
+    """compute_sdf_Hg through the tcgen05 forward+backward kernel vs the exact-fp32 SIMT kernel (DIF_ICP_PATH=simt) on the
+    same map and points, with and without gradients, including a pose that leaves many points outside observed PLIVoxes."""
+    import argparse
+    from difusion_b200.system.map import DenseIndexedMap
+    from difusion_b200.system.tracker import SDFTracker
+    from difusion_b200.utils.motion_util import Isometry, Rotation
+    fx = golden["s1_map"]
+    m = DenseIndexedMap(model, fixture_args(fx), 29, dev)
+    for f in range(int(fx["n_frames"])):
+        m.integrate_keyframe(_t(fx[f"f{f}.xyz"], dev), _t(fx[f"f{f}.normal"], dev))
+    trk = SDFTracker(m, argparse.Namespace(sdf=dict(robust_kernel="huber", robust_k=5.0, subsample=0.5), rgb=None,
+                                           iter_config=[{"n": 2, "type": [["sdf"]]}]))
+    last = Isometry(q=Rotation(matrix=fx["hg.R_last"]), t=fx["hg.t_last"])
+    obs = _t(fx["hg.obs"], dev)
+    for xi in ([0, 0, 0, 0, 0, 0], [0.004, -0.003, 0.002, 0.003, -0.002, 0.001], [0.3, 0.1, -0.2, 0.05, 0.02, -0.04]):
+        delta = Isometry.from_twist(np.asarray(xi, float))
+        monkeypatch.delenv("DIF_ICP_PATH", raising=False)
+        H, g, E = trk.compute_sdf_Hg(0, last, delta, obs, no_grad=False)
+        _, _, E_ng = trk.compute_sdf_Hg(-1, last, delta, obs, no_grad=True)
+        n_tc = float(m.icp_linearize(obs, last.q.rotation_matrix, last.t, delta.q.rotation_matrix, delta.t)[43])
+        monkeypatch.setenv("DIF_ICP_PATH", "simt")
+        H2, g2, E2 = trk.compute_sdf_Hg(0, last, delta, obs, no_grad=False)
+        n_simt = float(m.icp_linearize(obs, last.q.rotation_matrix, last.t, delta.q.rotation_matrix, delta.t)[43])
+        monkeypatch.delenv("DIF_ICP_PATH", raising=False)
+        assert n_tc == n_simt > 1000                              # identical valid sets (integer lookup path)
+        assert np.abs(H - H2).max() <= 2e-4 * np.abs(H2).max() and np.abs(g - g2).max() <= 2e-4 * np.abs(g2).max()
+        assert close(E, E2, 1e-5) and close(E_ng, E2, 1e-5)
+    # ragged sizes / single tile / one slot only
+    for n in (2048, 2049, 4000):
+        delta = Isometry.from_twist(np.zeros(6))
+        o = m.icp_linearize(obs[:n], last.q.rotation_matrix, last.t, delta.q.rotation_matrix, delta.t).cpu().numpy()
+        monkeypatch.setenv("DIF_ICP_PATH", "simt")
+        o2 = m.icp_linearize(obs[:n], last.q.rotation_matrix, last.t, delta.q.rotation_matrix, delta.t).cpu().numpy()
+        monkeypatch.delenv("DIF_ICP_PATH", raising=False)
+        assert o[43] == o2[43] and np.abs(o[:36] - o2[:36]).max() <= 2e-4 * np.abs(o2[:36]).max() and close(o[42], o2[42], 1e-5)
