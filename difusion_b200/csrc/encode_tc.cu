@@ -1,0 +1,354 @@
+// Tensor-core (tcgen05 / TMEM) evaluation of the DI-Fusion point encoder with the 8-offset sample gather fused in front and
+// the per-PLIVox scatter-accumulate fused behind it.
+//   replaces reference network/di_encoder.py:26-30 (Conv1d(k=1)+BN+ReLU x3, Conv1d) evaluated on the materialised
+//   (S, 6) sample tensor of system/map.py:419-446, and ext/indexing/indexing.cu:59-109 (groupby_sum).  SURVEY rows a-4..a-6.
+//
+// Persistent, one CTA per SM, 128-sample tiles (= TMEM lanes).  20 warps: 16 epilogue warps (TMEM lane quadrant x column
+// quarter), one MMA issuer, two gather producers (64 samples of a tile each; the x tile is double buffered so they run one
+// tile ahead).  Layers as tcgen05.mma M128 x N{32,64,256,32} x K16 with fp32 accumulation in TMEM and the same 3-pass fp16
+// hi/lo split as the decoder (hi*hi + lo*hi + hi*lo); BN is folded into the weights at load.
+//   L0  x[128x16 (6 real)]  (smem)  * W0^T -> acc[:, 0:32]    -> +b, ReLU, split -> h0 (A operand in TMEM)
+//   L1  h0[128x32]          (TMEM)  * W1^T -> acc[:, 0:64]    -> h1
+//   L2  h1[128x64]          (TMEM)  * W2^T -> acc[:, 0:256]   -> h2 (K = 256: the whole 256-column A region)
+//   L3  h2[128x256]         (TMEM)  * W3^T -> acc[:, 0:32]    -> +b3 -> atomicAdd into slot_sum[slot][0:29]  (or plain store)
+// TMEM map (512 columns): accumulator [0, 256), A operand [256, 512).
+#include "tc_common.cuh"
+
+namespace dif {
+namespace enc {
+
+using namespace tc;
+
+// ---- weight image (bytes): hi plane, lo plane, biases -------------------------------------------------------------------
+constexpr uint32_t EW0_B = 32 * 16 * 2, EW1_B = 64 * 32 * 2, EW2_B = 256 * 64 * 2, EW3_B = 32 * 256 * 2;
+constexpr uint32_t EOFF_W0 = 0, EOFF_W1 = EOFF_W0 + EW0_B, EOFF_W2 = EOFF_W1 + EW1_B, EOFF_W3 = EOFF_W2 + EW2_B;
+constexpr uint32_t EPLANE_B = EOFF_W3 + EW3_B;                    // 54272
+constexpr uint32_t EOFF_BIAS = 2 * EPLANE_B;                      // b0[32] b1[64] b2[256] b3[32]
+constexpr uint32_t EBIAS_B = 384 * 4;
+constexpr uint32_t EIMAGE_B = EOFF_BIAS + EBIAS_B;                // 110080
+constexpr uint32_t EX_CHUNK_B = TILE * 16 + 16;                   // one 8-wide K chunk of the x tile (+16 B bank skew)
+constexpr uint32_t EX_PLANE_B = 2 * EX_CHUNK_B;                   // K = 16: chunk 0 = (rel xyz, normal, 0, 0), chunk 1 = zeros
+constexpr uint32_t EOFF_X = EIMAGE_B;                             // [2 buffers][hi, lo]
+constexpr uint32_t EOFF_SLOT = EOFF_X + 4 * EX_PLANE_B;           // [4 buffers][128] int32: target PLIVox slot of every sample
+constexpr uint32_t EOFF_BAR = EOFF_SLOT + 4 * TILE * 4;             //   (4 deep: a tile's slots are read by its epilogue long after layer 0 freed the x buffer)
+constexpr uint32_t ESMEM_B = EOFF_BAR + 96 + 16;
+static_assert(EIMAGE_B % 16 == 0 && ESMEM_B <= 232448, "shared memory layout");
+
+enum { EB_W = 0, EB_X0 = 1, EB_X1 = 2, EB_XF0 = 3, EB_XF1 = 4, EB_ACC = 5, EB_A = 6, EB_E = 7 };
+
+struct EncodeArgs {
+    // mode 0: samples come from the integrate sample list (point index, offset index, target slot); results are accumulated
+    //         into slot_sum.  mode 1: explicit (n, 6) inputs, results stored to out (n, 29)  (dif_encode).
+    int mode;
+    Grid g; const float* p_hat; const float* normal; const int32_t* s_pt; const int32_t* s_slot; const uint8_t* s_off;
+    const int32_t* n_dev; float* slot_sum;
+    const float* xyzn; int64_t n; float* out;
+};
+
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t addr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(addr));
+}
+__device__ __forceinline__ void tmem_st4(uint32_t addr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+}
+
+// +bias, ReLU, hi/lo split of 16 accumulator columns -> 8 + 8 packed A-operand columns
+__device__ __forceinline__ void convert16(const uint32_t* v, const float* b, uint32_t a_hi, uint32_t a_lo) {
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float2 bb = *reinterpret_cast<const float2*>(b + 2 * j);
+        split_pair(fmaxf(__uint_as_float(v[2 * j]) + bb.x, 0.f), fmaxf(__uint_as_float(v[2 * j + 1]) + bb.y, 0.f), hi[j], lo[j]);
+    }
+    tmem_st8(a_hi, hi); tmem_st8(a_lo, lo);
+}
+
+// TS stage: D (+)= A_tmem * B (three passes); w_step16 = descriptor increment per K=16 step
+__device__ __forceinline__ void issue_ts(uint32_t idesc, uint32_t w_step16, int ksteps, uint32_t acc, uint32_t a_hi_t, uint32_t a_lo_t,
+                                         uint64_t w_hi_d, uint64_t w_lo_d) {
+    uint32_t accumulate = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t a_t = pass == 1 ? a_lo_t : a_hi_t;
+        uint64_t w = pass == 2 ? w_lo_d : w_hi_d;
+#pragma unroll 4
+        for (int ks = 0; ks < ksteps; ++ks) { mma_ts(acc, a_t + ks * 8, w, idesc, accumulate); accumulate = 1; w += w_step16; }
+    }
+}
+
+__global__ void __launch_bounds__(THREADS, 1) encode_tc_kernel(const unsigned char* __restrict__ image, EncodeArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bar0 = sbase + EOFF_BAR;
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + EOFF_BAR + 96);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n_total = a.mode == 0 ? (int64_t)*a.n_dev : a.n;
+    const int64_t n_tiles = (n_total + TILE - 1) / TILE;
+    if ((int64_t)blockIdx.x >= n_tiles) return;                   // nothing to do: skip the weight load altogether
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar0 + 8 * EB_W, 1);
+        mbar_init(bar0 + 8 * EB_X0, 2); mbar_init(bar0 + 8 * EB_X1, 2);        // two producer warps fill one x buffer
+        mbar_init(bar0 + 8 * EB_XF0, 1); mbar_init(bar0 + 8 * EB_XF1, 1);      // tcgen05.commit after layer 0: buffer free
+        mbar_init(bar0 + 8 * EB_ACC, 1);
+        mbar_init(bar0 + 8 * EB_A, 16);
+        mbar_init(bar0 + 8 * EB_E, 16);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // K chunk 1 of every x plane is identically zero (the encoder has 6 inputs, padded to K = 16): written once
+    for (int i = threadIdx.x; i < 4 * (int)(EX_CHUNK_B / 16); i += THREADS)
+        *reinterpret_cast<uint4*>(smem + EOFF_X + (i / (EX_CHUNK_B / 16)) * EX_PLANE_B + EX_CHUNK_B + (i % (EX_CHUNK_B / 16)) * 16) = make_uint4(0, 0, 0, 0);
+    fence_async_smem();
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_ptr_s)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_ptr_s, 0);
+    const uint32_t acc_c = tmem, a_c = tmem + 256;                // accumulator / A-operand column bases
+
+    if (warp == MMA_WARP) {
+        // ===================================================== weight load + MMA issuer (warp-uniform, instructions elected)
+        if (lane == 0) {
+            mbar_expect_tx(bar0 + 8 * EB_W, EIMAGE_B);
+            constexpr uint32_t CH = 32768;
+            for (uint32_t off = 0; off < EIMAGE_B; off += CH) bulk_g2s(sbase + off, image + off, (EIMAGE_B - off) < CH ? (EIMAGE_B - off) : CH, bar0 + 8 * EB_W);
+        }
+        __syncwarp();
+        mbar_wait(bar0 + 8 * EB_W, 0);
+        const uint64_t w0h = smem_desc(sbase + EOFF_W0, 32 * 16, 128), w0l = smem_desc(sbase + EPLANE_B + EOFF_W0, 32 * 16, 128);
+        const uint64_t w1h = smem_desc(sbase + EOFF_W1, 64 * 16, 128), w1l = smem_desc(sbase + EPLANE_B + EOFF_W1, 64 * 16, 128);
+        const uint64_t w2h = smem_desc(sbase + EOFF_W2, 256 * 16, 128), w2l = smem_desc(sbase + EPLANE_B + EOFF_W2, 256 * 16, 128);
+        const uint64_t w3h = smem_desc(sbase + EOFF_W3, 32 * 16, 128), w3l = smem_desc(sbase + EPLANE_B + EOFF_W3, 32 * 16, 128);
+        uint32_t ph_x = 0, ph_a = 0, ph_e = 0;
+        int64_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int buf = (int)(it & 1);
+            // ---- L0: A = x tile (smem), one K=16 step, N = 32
+            mbar_wait_tight(bar0 + 8 * (EB_X0 + buf), (ph_x >> buf) & 1); ph_x ^= 1u << buf;
+            if (it > 0) { mbar_wait_tight(bar0 + 8 * EB_E, ph_e); ph_e ^= 1; }       // previous tile's outputs were read
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t xh = smem_desc(sbase + EOFF_X + buf * 2 * EX_PLANE_B, EX_CHUNK_B, 128);
+                const uint64_t xl = smem_desc(sbase + EOFF_X + buf * 2 * EX_PLANE_B + EX_PLANE_B, EX_CHUNK_B, 128);
+                const uint32_t id = idesc_f16(32);
+                mma_ss(acc_c, xh, w0h, id, 0); mma_ss(acc_c, xl, w0h, id, 1); mma_ss(acc_c, xh, w0l, id, 1);
+                mma_commit(bar0 + 8 * EB_ACC);
+                mma_commit(bar0 + 8 * (EB_XF0 + buf));
+            }
+            __syncwarp();
+            // ---- L1 (K = 32, N = 64), L2 (K = 64, N = 256), L3 (K = 256, N = 32): A from TMEM
+#pragma unroll 1
+            for (int layer = 1; layer < 4; ++layer) {
+                mbar_wait_tight(bar0 + 8 * EB_A, ph_a); ph_a ^= 1;
+                tc_fence_after();
+                if (elect_one()) {
+                    if (layer == 1) issue_ts(idesc_f16(64), (2 * 64 * 16) >> 4, 2, acc_c, a_c, a_c + 16, w1h, w1l);
+                    else if (layer == 2) issue_ts(idesc_f16(256), (2 * 256 * 16) >> 4, 4, acc_c, a_c + 32, a_c + 64, w2h, w2l);
+                    else issue_ts(idesc_f16(32), (2 * 32 * 16) >> 4, 16, acc_c, a_c, a_c + 128, w3h, w3l);
+                    mma_commit(bar0 + 8 * EB_ACC);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= PRODUCER_WARP0) {
+        // ===================================================== gather producers: warp 17 rows 0..63, warp 18 rows 64..127
+        const int pw = warp - PRODUCER_WARP0;
+        if (pw < 2) {
+            uint32_t ph_xf = 0;
+            int64_t it = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const int buf = (int)(it & 1);
+                if (it >= 2) { mbar_wait(bar0 + 8 * (EB_XF0 + buf), (ph_xf >> buf) & 1); ph_xf ^= 1u << buf; }   // layer 0 of tile it-2 has read this buffer
+                unsigned char* x_hi_p = smem + EOFF_X + buf * 2 * EX_PLANE_B;
+                int32_t* slot_p = reinterpret_cast<int32_t*>(smem + EOFF_SLOT) + (int)(it & 3) * TILE;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int row = pw * 64 + h * 32 + lane;
+                    const int64_t si = tile * TILE + row;
+                    float in[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    int slot = -1;
+                    if (si < n_total) {
+                        if (a.mode == 0) {
+                            const int i = a.s_pt[si], k = a.s_off[si];
+                            slot = a.s_slot[si];
+                            const float px = a.p_hat[3 * i], py = a.p_hat[3 * i + 1], pz = a.p_hat[3 * i + 2];
+                            const float ox = (k & 4) ? 0.5f : -0.5f, oy = (k & 2) ? 0.5f : -0.5f, oz = (k & 1) ? 0.5f : -0.5f;
+                            const float cx = (float)clampi((int)ceilf(__fadd_rn(px, ox)) - 1, 0, a.g.nx - 1);
+                            const float cy = (float)clampi((int)ceilf(__fadd_rn(py, oy)) - 1, 0, a.g.ny - 1);
+                            const float cz = (float)clampi((int)ceilf(__fadd_rn(pz, oz)) - 1, 0, a.g.nz - 1);
+                            // rel = p - cell - 0.5, two separately rounded subtractions as in map.py:425
+                            in[0] = __fsub_rn(__fsub_rn(px, cx), 0.5f); in[1] = __fsub_rn(__fsub_rn(py, cy), 0.5f); in[2] = __fsub_rn(__fsub_rn(pz, cz), 0.5f);
+                            in[3] = a.normal[3 * i]; in[4] = a.normal[3 * i + 1]; in[5] = a.normal[3 * i + 2];
+                        } else {
+                            slot = 0;
+#pragma unroll
+                            for (int j = 0; j < 6; ++j) in[j] = __ldg(a.xyzn + si * 6 + j);
+                        }
+                    }
+                    uint4 hq, lq;
+                    split_pair(in[0], in[1], hq.x, lq.x); split_pair(in[2], in[3], hq.y, lq.y);
+                    split_pair(in[4], in[5], hq.z, lq.z); hq.w = 0u; lq.w = 0u;
+                    *reinterpret_cast<uint4*>(x_hi_p + row * 16) = hq;
+                    *reinterpret_cast<uint4*>(x_hi_p + EX_PLANE_B + row * 16) = lq;
+                    slot_p[row] = slot;
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar0 + 8 * (EB_X0 + buf));
+            }
+        }
+    } else {
+        // ===================================================== epilogue warps: lanes 32*quad.., column quarter cq
+        const int quad = warp & 3, cq = warp >> 2;
+        const int row = quad * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+        const uint32_t acc = acc_c + lane_base, ar = a_c + lane_base;
+        const float* bias = reinterpret_cast<const float*>(smem + EOFF_BIAS);
+        uint32_t ph_acc = 0;
+        mbar_wait(bar0 + 8 * EB_W, 0);
+        int64_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            // ---- E0: 32 columns, 8 per warp -> h0 (K = 32): hi @ A+0..15, lo @ A+16..31
+            mbar_wait(bar0 + 8 * EB_ACC, ph_acc); ph_acc ^= 1;
+            tc_fence_after();
+            const int slot = reinterpret_cast<const int32_t*>(smem + EOFF_SLOT)[(int)(it & 3) * TILE + row];     // (written before the x tile was published)
+            {
+                uint32_t v[8], hi[4], lo[4];
+                tmem_ld8_nowait(acc + 8 * cq, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    split_pair(fmaxf(__uint_as_float(v[2 * j]) + bias[8 * cq + 2 * j], 0.f), fmaxf(__uint_as_float(v[2 * j + 1]) + bias[8 * cq + 2 * j + 1], 0.f), hi[j], lo[j]);
+                tmem_st4(ar + 4 * cq, hi); tmem_st4(ar + 16 + 4 * cq, lo);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar0 + 8 * EB_A);
+            // ---- E1: 64 columns, 16 per warp -> h1 (K = 64): hi @ A+32..63, lo @ A+64..95
+            mbar_wait(bar0 + 8 * EB_ACC, ph_acc); ph_acc ^= 1;
+            tc_fence_after();
+            {
+                uint32_t v[16];
+                tmem_ld16_nowait(acc + 16 * cq, v);
+                tmem_ld_wait();
+                convert16(v, bias + 32 + 16 * cq, ar + 32 + 8 * cq, ar + 64 + 8 * cq);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar0 + 8 * EB_A);
+            // ---- E2: 256 columns, 64 per warp -> h2 (K = 256): hi @ A+0..127, lo @ A+128..255
+            mbar_wait(bar0 + 8 * EB_ACC, ph_acc); ph_acc ^= 1;
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < 64; c += 32) {
+                uint32_t v0[16], v1[16];
+                const int col = 64 * cq + c;
+                tmem_ld16_nowait(acc + col, v0);
+                tmem_ld16_nowait(acc + col + 16, v1);
+                tmem_ld_wait();
+                convert16(v0, bias + 96 + col, ar + col / 2, ar + 128 + col / 2);
+                convert16(v1, bias + 96 + col + 16, ar + col / 2 + 8, ar + 128 + col / 2 + 8);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar0 + 8 * EB_A);
+            // ---- E3: 32 columns (29 real), 8 per warp: + b3, then accumulate into the target PLIVox (or store)
+            mbar_wait(bar0 + 8 * EB_ACC, ph_acc); ph_acc ^= 1;
+            tc_fence_after();
+            uint32_t v[8];
+            tmem_ld8_nowait(acc + 8 * cq, v);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar0 + 8 * EB_E);               // accumulator consumed: the next tile's layer 0 may start
+            const int64_t si = tile * TILE + row;
+            if (slot >= 0 && si < n_total) {
+                float* dst = a.mode == 0 ? a.slot_sum + (int64_t)slot * DIF_L : a.out + si * DIF_L;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int col = 8 * cq + j;
+                    if (col < DIF_L) {
+                        const float o = __uint_as_float(v[j]) + bias[352 + col];
+                        if (a.mode == 0) atomicAdd(dst + col, o); else dst[col] = o;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(512));
+}
+
+// ---- weight image: fp16 hi/lo planes, no-swizzle K-major core-matrix slabs (element (n,k) at (k/8)*(N*16) + n*16 + (k%8)*2) ----
+__global__ void prepare_encoder_tc_kernel(const float* __restrict__ P, unsigned char* __restrict__ image) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    // source: k-major fp32 copies of mlp_simt.cuh (EncW::W?t[k][n]); K of layer 0 padded 6 -> 16, N of layer 3 padded 29 -> 32
+    const int srcs[4] = {EncW::W0t, EncW::W1t, EncW::W2t, EncW::W3t};
+    const int Ns[4] = {32, 64, 256, 32}, Ks[4] = {16, 32, 64, 256}, Kreal[4] = {6, 32, 64, 256};
+    const uint32_t offs[4] = {EOFF_W0, EOFF_W1, EOFF_W2, EOFF_W3};
+    for (int l = 0; l < 4; ++l) {
+        const int N = Ns[l], K = Ks[l];
+        for (int i = tid; i < N * K; i += nth) {
+            const int n = i / K, k = i % K;
+            const float w = k < Kreal[l] ? P[srcs[l] + k * N + n] : 0.f;          // (W3t already has zero columns 29..31)
+            const __half h = __float2half_rn(w);
+            const __half lo = __float2half_rn(w - __half2float(h));
+            const uint32_t o = offs[l] + (uint32_t)(k / 8) * (N * 16) + n * 16 + (k % 8) * 2;
+            *reinterpret_cast<__half*>(image + o) = h;
+            *reinterpret_cast<__half*>(image + EPLANE_B + o) = lo;
+        }
+    }
+    float* b = reinterpret_cast<float*>(image + EOFF_BIAS);
+    for (int i = tid; i < 256; i += nth) {
+        b[96 + i] = P[EncW::b2 + i];
+        if (i < 32) { b[i] = P[EncW::b0 + i]; b[352 + i] = P[EncW::b3 + i]; }
+        if (i < 64) b[32 + i] = P[EncW::b1 + i];
+    }
+}
+
+}  // namespace enc
+
+size_t encoder_tc_image_bytes() { return enc::EIMAGE_B; }
+
+int prepare_encoder_tc(const float* P, unsigned char* image, cudaStream_t st) {
+    enc::prepare_encoder_tc_kernel<<<64, 256, 0, st>>>(P, image);
+    DIF_COUNT_LAUNCH(1);
+    return check_launch("prepare_encoder_tc_kernel");
+}
+
+static int launch(const unsigned char* image, const enc::EncodeArgs& a, int64_t max_samples, cudaStream_t st) {
+    const int64_t max_tiles = (max_samples + tc::TILE - 1) / tc::TILE;
+    const int grid = (int)(max_tiles < DIF_NUM_SMS ? (max_tiles > 0 ? max_tiles : 1) : DIF_NUM_SMS);
+    cudaFuncSetAttribute(enc::encode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc::ESMEM_B);
+    prof_begin(DIF_PROF_ENCODE, st);
+    enc::encode_tc_kernel<<<grid, tc::THREADS, enc::ESMEM_B, st>>>(image, a);
+    prof_end(DIF_PROF_ENCODE, st);
+    DIF_COUNT_LAUNCH(1);
+    return check_launch("encode_tc_kernel");
+}
+
+// integrate path: samples from the gather list (device-side count), accumulate into slot_sum
+int launch_encode_accumulate_tc(const void* encoder_prepared, Grid g, const float* p_hat, const float* normal, const int32_t* s_pt,
+                                const int32_t* s_slot, const uint8_t* s_off, const int32_t* n_dev, int64_t max_samples, float* slot_sum,
+                                cudaStream_t st) {
+    const unsigned char* image = (const unsigned char*)encoder_prepared + (size_t)EncW::FP32_END * sizeof(float);
+    enc::EncodeArgs a{0, g, p_hat, normal, s_pt, s_slot, s_off, n_dev, slot_sum, nullptr, 0, nullptr};
+    return launch(image, a, max_samples, st);
+}
+
+// dif_encode path: explicit (n, 6) inputs -> (n, 29) outputs
+int launch_encode_tc(const void* encoder_prepared, const float* xyzn, int64_t n, float* out, cudaStream_t st) {
+    const unsigned char* image = (const unsigned char*)encoder_prepared + (size_t)EncW::FP32_END * sizeof(float);
+    enc::EncodeArgs a{1, Grid{}, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, xyzn, n, out};
+    return launch(image, a, n, st);
+}
+
+}  // namespace dif

@@ -144,6 +144,9 @@ static int grid_for_tiles(int64_t n_tiles, int ctas_per_sm) {
 
 size_t decoder_tc_image_bytes();
 int prepare_decoder_tc(const float* P, unsigned char* image, cudaStream_t st);
+size_t encoder_tc_image_bytes();
+int prepare_encoder_tc(const float* P, unsigned char* image, cudaStream_t st);
+int launch_encode_tc(const void* encoder_prepared, const float* xyzn, int64_t n, float* out, cudaStream_t st);
 
 // 0 = auto (tensor cores for forward-only launches of >= 1024 samples), 1 = force fp32 SIMT, 2 = force tensor cores
 static int decode_path_override() {      // read per call so tests can compare both paths
@@ -202,7 +205,7 @@ uint64_t dif_launch_count(int reset) { const uint64_t v = dif::g_launches; if (r
 const char* dif_last_error(void) { return dif::g_last_error; }
 
 size_t dif_decoder_prepared_bytes(void) { return (size_t)DecW::FP32_END * sizeof(float) + decoder_tc_image_bytes(); }
-size_t dif_encoder_prepared_bytes(void) { return (size_t)EncW::FP32_END * sizeof(float); }
+size_t dif_encoder_prepared_bytes(void) { return (size_t)EncW::FP32_END * sizeof(float) + encoder_tc_image_bytes(); }
 
 int dif_prepare_decoder(const float* blob_dev, void* prepared_dev, void* stream) {
     if (!blob_dev || !prepared_dev) return DIF_E_INVALID;
@@ -217,7 +220,9 @@ int dif_prepare_encoder(const float* blob_dev, void* prepared_dev, void* stream)
     if (!blob_dev || !prepared_dev) return DIF_E_INVALID;
     prepare_encoder_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(blob_dev, (float*)prepared_dev);
     DIF_COUNT_LAUNCH(1);
-    return check_launch("prepare_encoder_kernel");
+    int rc = check_launch("prepare_encoder_kernel");
+    if (rc) return rc;
+    return prepare_encoder_tc((const float*)prepared_dev, (unsigned char*)prepared_dev + (size_t)EncW::FP32_END * sizeof(float), (cudaStream_t)stream);
 }
 
 int dif_decode(const void* decoder_prepared, const float* latent, const int32_t* rows, const float* xyz, int64_t n,
@@ -233,6 +238,10 @@ int dif_decode(const void* decoder_prepared, const float* latent, const int32_t*
 int dif_encode(const void* encoder_prepared, const float* xyzn, int64_t n, float* latent_out, void* stream) {
     if (n < 0 || !encoder_prepared || (n > 0 && (!xyzn || !latent_out))) return DIF_E_INVALID;
     if (n == 0) return DIF_OK;
+    {   // tensor cores for anything beyond a few tiles; DIF_ENCODE_PATH=simt forces the exact-fp32 kernel
+        const char* e = getenv("DIF_ENCODE_PATH");
+        if (!(e && e[0] == 's') && n >= 1024) return launch_encode_tc(encoder_prepared, xyzn, n, latent_out, (cudaStream_t)stream);
+    }
     const size_t smem = sizeof(EncoderSmem);
     cudaFuncSetAttribute(encode_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int64_t n_tiles = (n + MLP_T - 1) / MLP_T;

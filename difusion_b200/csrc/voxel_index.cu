@@ -9,8 +9,13 @@
 // self-cleaning, so no O(grid) memset is paid per frame.  HBM-bound integer work: coalesced point streams, 4/8-byte
 // random lookups into indexer/obs_count, warp-aggregated atomics for compaction.
 #include "mlp_simt.cuh"
+#include <stdlib.h>
 
 namespace dif {
+
+int launch_encode_accumulate_tc(const void* encoder_prepared, Grid g, const float* p_hat, const float* normal, const int32_t* s_pt,
+                                const int32_t* s_slot, const uint8_t* s_off, const int32_t* n_dev, int64_t max_samples, float* slot_sum,
+                                cudaStream_t st);
 
 constexpr int CHUNK_WORDS = 1024;            // bitmap words per block in the ordered scan (256 threads x 4 words)
 constexpr int SCAN_THREADS = 256;
@@ -450,15 +455,23 @@ int dif_integrate(const dif_map_view* map, const void* encoder_prepared, const f
     if (n > 0) {
         gather_kernel<<<nb, 256, 0, st>>>(m, (int)n, S.p_hat, S.cell, S.kept, P.cell_count, P.slot_cnt, S.s_pt, S.s_slot, S.s_off,
                                           S.touched, S.ctr, stats_dev);
-        const size_t smem = sizeof(EncoderSmem);
-        cudaFuncSetAttribute(encode_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        const int64_t max_tiles = (8 * n + MLP_T - 1) / MLP_T;
-        const int grid = (int)(max_tiles < DIF_NUM_SMS * 4 ? max_tiles : DIF_NUM_SMS * 4);
-        prof_begin(DIF_PROF_ENCODE, st);
-        encode_accumulate_kernel<<<grid, MLP_THREADS, smem, st>>>(m, (const float*)encoder_prepared, S.p_hat, normal, S.s_pt, S.s_slot,
-                                                                  S.s_off, S.ctr, P.slot_sum);
-        prof_end(DIF_PROF_ENCODE, st);
-        DIF_COUNT_LAUNCH(3);
+        const char* enc_env = getenv("DIF_ENCODE_PATH");                 // "simt" forces the exact-fp32 kernel (tests compare both)
+        if (!(enc_env && enc_env[0] == 's') && n >= 256) {
+            const int rc = launch_encode_accumulate_tc(encoder_prepared, m.g, S.p_hat, normal, S.s_pt, S.s_slot, S.s_off, S.ctr + CTR_N_SAMPLES,
+                                                       8 * n, P.slot_sum, st);
+            if (rc) return rc;
+            DIF_COUNT_LAUNCH(2);
+        } else {
+            const size_t smem = sizeof(EncoderSmem);
+            cudaFuncSetAttribute(encode_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            const int64_t max_tiles = (8 * n + MLP_T - 1) / MLP_T;
+            const int grid = (int)(max_tiles < DIF_NUM_SMS * 4 ? max_tiles : DIF_NUM_SMS * 4);
+            prof_begin(DIF_PROF_ENCODE, st);
+            encode_accumulate_kernel<<<grid, MLP_THREADS, smem, st>>>(m, (const float*)encoder_prepared, S.p_hat, normal, S.s_pt, S.s_slot,
+                                                                      S.s_off, S.ctr, P.slot_sum);
+            prof_end(DIF_PROF_ENCODE, st);
+            DIF_COUNT_LAUNCH(3);
+        }
         fuse_kernel<<<DIF_NUM_SMS * 2, 256, 0, st>>>(m, S.touched, S.ctr, P.slot_cnt, P.slot_sum, stats_dev);
     }
     return check_launch("dif_integrate");
