@@ -11,7 +11,7 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libdifusion_b200.so"
 
 DIF_STAT_COUNT = 8
-STAT_N_KEPT, STAT_N_NEW, STAT_N_SAMPLES, STAT_N_UPDATED, STAT_N_OCCUPIED, STAT_FLAGS, STAT_N_FOCUSED = range(7)
+STAT_N_KEPT, STAT_N_NEW, STAT_N_SAMPLES, STAT_N_UPDATED, STAT_N_OCCUPIED, STAT_FLAGS, STAT_N_FOCUSED, STAT_N_XCHG = range(8)
 
 
 class MapView(C.Structure):
@@ -20,7 +20,8 @@ class MapView(C.Structure):
                 ("voxel_obs_count", C.c_void_p), ("slot_dirty", C.c_void_p), ("n_occupied", C.c_void_p),
                 ("capacity", C.c_int64), ("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32),
                 ("bound_min", C.c_float * 3), ("voxel_size", C.c_float), ("prune_min_vox_obs", C.c_int32),
-                ("ignore_count_th", C.c_float), ("encoder_count_th", C.c_float)]
+                ("ignore_count_th", C.c_float), ("encoder_count_th", C.c_float),
+                ("shard_rank", C.c_int32), ("shard_world", C.c_int32), ("xchg_slots", C.c_void_p)]
 
 
 _P, _I64, _I32, _F, _SZ = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_size_t
@@ -29,6 +30,7 @@ _MV = C.POINTER(MapView)
 # name -> (restype, argtypes); this table is also what tests/test_abi.py checks against include/difusion_b200.h
 SIGNATURES = {
     "dif_abi_version": (C.c_int, []),
+    "dif_shard_owner": (C.c_int, [_I64, C.c_int]),
     "dif_profile_hook": (C.c_int, [C.c_int, _P, _P]),
     "dif_launch_count": (C.c_uint64, [C.c_int]),
     "dif_debug_tc_timing": (C.c_int, [_P]),

@@ -67,6 +67,15 @@ __device__ __forceinline__ bool in_grid(const Grid& g, int ix, int iy, int iz) {
     return (unsigned)ix < (unsigned)g.nx && (unsigned)iy < (unsigned)g.ny && (unsigned)iz < (unsigned)g.nz;
 }
 
+// owner rank of a PLIVox: 64-bit finaliser (splitmix64) of its linear id, modulo the number of ranks
+__host__ __device__ __forceinline__ int shard_owner(int64_t lin, int world) {
+    uint64_t z = (uint64_t)lin + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (int)(z % (uint64_t)world);
+}
+
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 __device__ __forceinline__ float warp_sum(float v) {

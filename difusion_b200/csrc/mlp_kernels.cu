@@ -195,6 +195,7 @@ using namespace dif;
 extern "C" {
 
 int dif_debug_tc_timing(void* dev_buf) { return dif::set_tc_timing_buffer((unsigned long long*)dev_buf); }
+int dif_shard_owner(int64_t linear_id, int world) { return world > 1 ? dif::shard_owner(linear_id, world) : 0; }
 int dif_abi_version(void) { return DIF_ABI_VERSION; }
 int dif_profile_hook(int which, void* start_event, void* stop_event) {
     if (which < 0 || which >= DIF_PROF_COUNT) return DIF_E_INVALID;

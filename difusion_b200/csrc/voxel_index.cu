@@ -25,11 +25,13 @@ enum { CTR_N_SAMPLES = 0, CTR_N_TOUCHED = 1, CTR_BASE_SLOT = 2, CTR_OVERFLOW = 3
 struct MapDev {          // by-value copy of dif_map_view for kernels
     int64_t* indexer; float* latent; int64_t* pos; float* obs; uint8_t* dirty; int32_t* n_occ; int64_t capacity;
     Grid g; int prune; float ignore_th, enc_th;
+    int shard_rank, shard_world; int32_t* xchg;
 };
 static MapDev to_dev(const dif_map_view* m) {
     MapDev d; d.indexer = m->indexer; d.latent = m->latent_vecs; d.pos = m->latent_vecs_pos; d.obs = m->voxel_obs_count;
     d.dirty = m->slot_dirty; d.n_occ = m->n_occupied; d.capacity = m->capacity; d.g = make_grid(m);
     d.prune = m->prune_min_vox_obs; d.ignore_th = m->ignore_count_th; d.enc_th = m->encoder_count_th;
+    d.shard_rank = m->shard_rank; d.shard_world = m->shard_world > 1 ? m->shard_world : 1; d.xchg = m->xchg_slots;
     return d;
 }
 
@@ -227,9 +229,9 @@ __global__ void gather_kernel(MapDev m, int n, const float* __restrict__ p_hat, 
                               int32_t* __restrict__ touched, int32_t* __restrict__ ctr, int32_t* __restrict__ stats) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    int slots[8]; int cnt = 0; bool focused = false;
+    int slots[8]; bool mine[8]; int cnt = 0; bool focused = false;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) slots[k] = -1;
+    for (int k = 0; k < 8; ++k) { slots[k] = -1; mine[k] = false; }
     if (i < n) {
         const int c = cell[i];
         if (c >= 0) cell_count[c] = 0u;                       // self-clean the histogram (every reader ran in K2)
@@ -250,9 +252,12 @@ __global__ void gather_kernel(MapDev m, int n, const float* __restrict__ p_hat, 
                     const int cx = clampi((int)ceilf(__fadd_rn(px, ox)) - 1, 0, g.nx - 1);
                     const int cy = clampi((int)ceilf(__fadd_rn(py, oy)) - 1, 0, g.ny - 1);
                     const int cz = clampi((int)ceilf(__fadd_rn(pz, oz)) - 1, 0, g.nz - 1);
-                    const int s = target_slot(m, lin_id(g, cx, cy, cz));
+                    const int tl = lin_id(g, cx, cy, cz);
+                    const int s = target_slot(m, tl);
                     slots[k] = s;
-                    cnt += s >= 0;
+                    // sharded map: every rank counts the observation, only the owner of the PLIVox encodes it
+                    mine[k] = s >= 0 && (m.shard_world == 1 || shard_owner(tl, m.shard_world) == m.shard_rank);
+                    cnt += mine[k];
                 }
             }
         }
@@ -271,7 +276,7 @@ __global__ void gather_kernel(MapDev m, int n, const float* __restrict__ p_hat, 
     for (int k = 0; k < 8; ++k) {
         const int s = slots[k];
         if (s >= 0) {
-            s_pt[base] = i; s_slot[base] = s; s_off[base] = (uint8_t)k; ++base;
+            if (mine[k]) { s_pt[base] = i; s_slot[base] = s; s_off[base] = (uint8_t)k; ++base; }
             if (atomicAdd(slot_cnt + s, 1u) == 0u) touched[atomicAdd(ctr + CTR_N_TOUCHED, 1)] = s;
         }
     }
@@ -335,14 +340,18 @@ __global__ void fuse_kernel(MapDev m, const int32_t* __restrict__ touched, const
         const float n_old = m.obs[slot];
         const float n_new = __fadd_rn(n_old, cnt);
         __syncwarp();
-        if (lane < DIF_L) {
+        const bool owned = m.shard_world == 1 || shard_owner(m.pos[slot], m.shard_world) == m.shard_rank;
+        if (owned && lane < DIF_L) {
             const int64_t o = (int64_t)slot * DIF_L + lane;
             const float sum = __fadd_rn(slot_sum[o], __fmul_rn(m.latent[o], n_old));
             m.latent[o] = __fdiv_rn(sum, n_new);
             slot_sum[o] = 0.f;
         }
         __syncwarp();
-        if (lane == 0) { m.obs[slot] = n_new; slot_cnt[slot] = 0u; if (m.dirty) m.dirty[slot] = 1; }
+        if (lane == 0) {
+            m.obs[slot] = n_new; slot_cnt[slot] = 0u; if (m.dirty) m.dirty[slot] = 1;
+            if (owned && m.shard_world > 1 && m.xchg) m.xchg[atomicAdd(stats + DIF_STAT_N_XCHG, 1)] = slot;    // row to publish to the other ranks
+        }
     }
 }
 
@@ -442,10 +451,11 @@ int dif_integrate(const dif_map_view* map, const void* encoder_prepared, const f
     const int n_chunks = (int)((n_words + CHUNK_WORDS - 1) / CHUNK_WORDS);
     cudaMemsetAsync(S.ctr, 0, CTR_COUNT * sizeof(int32_t), st);
     cudaMemsetAsync(stats_dev, 0, DIF_STAT_COUNT * sizeof(int32_t), st);
-    const int nb = (int)((n + 255) / 256);
+    const int PT = 64;                                             // small blocks: a 30k-point frame must still fill 148 SMs
+    const int nb = (int)((n + PT - 1) / PT);
     if (n > 0) {
-        voxelize_kernel<<<nb, 256, 0, st>>>(m, xyz, (int)n, S.p_hat, S.cell, P.cell_count, stats_dev);
-        prune_mark_kernel<<<nb, 256, 0, st>>>(m, (int)n, S.cell, P.cell_count, S.kept, unq_mask, P.bitmap, stats_dev);
+        voxelize_kernel<<<nb, PT, 0, st>>>(m, xyz, (int)n, S.p_hat, S.cell, P.cell_count, stats_dev);
+        prune_mark_kernel<<<nb, PT, 0, st>>>(m, (int)n, S.cell, P.cell_count, S.kept, unq_mask, P.bitmap, stats_dev);
         DIF_COUNT_LAUNCH(2);
     }
     DIF_COUNT_LAUNCH(3);
@@ -453,7 +463,7 @@ int dif_integrate(const dif_map_view* map, const void* encoder_prepared, const f
     bitmap_scan_kernel<<<1, 1024, 0, st>>>(S.chunk_sum, n_chunks, m.n_occ, m.capacity, S.ctr, stats_dev, 1);
     alloc_assign_kernel<<<n_chunks, SCAN_THREADS, 0, st>>>(m, P.bitmap, n_words, S.chunk_sum, S.ctr);
     if (n > 0) {
-        gather_kernel<<<nb, 256, 0, st>>>(m, (int)n, S.p_hat, S.cell, S.kept, P.cell_count, P.slot_cnt, S.s_pt, S.s_slot, S.s_off,
+        gather_kernel<<<nb, PT, 0, st>>>(m, (int)n, S.p_hat, S.cell, S.kept, P.cell_count, P.slot_cnt, S.s_pt, S.s_slot, S.s_off,
                                           S.touched, S.ctr, stats_dev);
         const char* enc_env = getenv("DIF_ENCODE_PATH");                 // "simt" forces the exact-fp32 kernel (tests compare both)
         if (!(enc_env && enc_env[0] == 's') && n >= 256) {
@@ -472,7 +482,7 @@ int dif_integrate(const dif_map_view* map, const void* encoder_prepared, const f
             prof_end(DIF_PROF_ENCODE, st);
             DIF_COUNT_LAUNCH(3);
         }
-        fuse_kernel<<<DIF_NUM_SMS * 2, 256, 0, st>>>(m, S.touched, S.ctr, P.slot_cnt, P.slot_sum, stats_dev);
+        fuse_kernel<<<DIF_NUM_SMS * 8, 256, 0, st>>>(m, S.touched, S.ctr, P.slot_cnt, P.slot_sum, stats_dev);
     }
     return check_launch("dif_integrate");
 }

@@ -113,7 +113,9 @@ class DenseIndexedMap:
         self._stats_ring = [(torch.zeros(_lib.DIF_STAT_COUNT, dtype=torch.int32).pin_memory(), torch.cuda.Event()) for _ in range(8)]
         self._stats_inflight = []            # [(ring index, max new slots of that call)]
         self._stats_next = 0
+        self._stats_last = [0] * _lib.DIF_STAT_COUNT
         self._n_occ_host = 0
+        self._shard_rank, self._shard_world, self._xchg = 0, 1, None       # see difusion_b200/shard.py
         self._cap_phys = 0
         self._latent = self._pos = self._obs = self._optimized = self._dirty = None
         self._persist = None
@@ -158,6 +160,7 @@ class DenseIndexedMap:
                 break
             self._stats_inflight.pop(0)
             st = buf.tolist()
+            self._stats_last = st
             self._n_occ_host = st[_lib.STAT_N_OCCUPIED]
             self.last_integrate_stats = dict(n_kept=st[0], n_new=st[1], n_samples=st[2], n_updated=st[3], n_occupied=st[4],
                                              flags=st[5], n_focused=st[6])
@@ -229,6 +232,8 @@ class DenseIndexedMap:
         v.prune_min_vox_obs = int(a.prune_min_vox_obs)
         v.ignore_count_th = float(a.ignore_count_th)
         v.encoder_count_th = float(a.encoder_count_th)
+        v.shard_rank, v.shard_world = self._shard_rank, self._shard_world
+        v.xchg_slots = self._xchg.data_ptr() if self._xchg is not None else None
         return v
 
     # ------------------------------------------------------------------ addressing helpers (map.py:287-319)
@@ -381,6 +386,10 @@ class DenseIndexedMap:
                     return self._make_mesh_from_cache() if not extract_async else None
                 self.mesh_cache.clear_updated_vec()
             self._sync_stats()
+            if self._shard_world > 1:                       # hash-sharded map: every rank meshes the PLIVoxes it owns
+                if updated is None:
+                    updated = torch.arange(self.n_occupied, device=self.device)
+                updated = self.owned_slots(updated)
 
         def do_meshing(res):
             torch.cuda.synchronize(self.device)

@@ -73,6 +73,12 @@ typedef struct dif_map_view {
     int32_t  prune_min_vox_obs;  /* fusion-lr-kt.yaml:32 */
     float    ignore_count_th;    /* :33 */
     float    encoder_count_th;   /* :34 */
+    /* -- hash-sharded map (new: the reference is single-GPU).  shard_world <= 1: unsharded.  Integer state is
+     * replicated (every rank runs the same index kernels on the same frame); the encoder MLP + latent fusion of a PLIVox run
+     * only on owner(cell) = mix64(linear id) % shard_world.  After dif_integrate, xchg_slots[0 .. stats[DIF_STAT_N_XCHG]) lists
+     * the slots whose latent rows this rank owns and changed: the caller all-gathers (slot, row) pairs and writes them back. */
+    int32_t  shard_rank, shard_world;
+    int32_t* xchg_slots;         /* [>= min(8*n_points, capacity)] or NULL */
 } dif_map_view;
 
 /* ---- integrate_keyframe  (system/map.py:340-452; SURVEY rows a-2 .. a-6) -----------------------------
@@ -89,6 +95,7 @@ enum {
     DIF_STAT_N_OCCUPIED = 4,     /* n_occupied after the call                                     */
     DIF_STAT_FLAGS = 5,          /* bit0: a point fell outside the grid (dropped); bit1: capacity exhausted */
     DIF_STAT_N_FOCUSED = 6,      /* points passing the focus mask (map.py:389-397)                */
+    DIF_STAT_N_XCHG = 7,         /* sharded map: owned PLIVoxes fused by this call (length of xchg_slots) */
     DIF_STAT_COUNT = 8
 };
 size_t dif_integrate_persist_bytes(int64_t n_cells, int64_t capacity);
@@ -162,6 +169,9 @@ uint64_t dif_launch_count(int reset);
 /* dif_debug_tc_timing: dev_buf = uint64[148*20*8] or NULL; when set, the tensor-core decoder records per-warp phase cycles
  * (development aid used by tools/tc_timing.py). */
 int dif_debug_tc_timing(void* dev_buf);
+
+/* owner rank of a PLIVox in a hash-sharded map: splitmix64(linear id) % world (host mirror of the device function). */
+int dif_shard_owner(int64_t linear_id, int world);
 
 int dif_abi_version(void);
 const char* dif_last_error(void);        /* thread-local text of the last DIF_E_LAUNCH */

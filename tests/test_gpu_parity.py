@@ -399,3 +399,47 @@ def test_tensor_core_encoder_matches_fp32_path(golden, model, dev, monkeypatch):
     a, b = maps["tc"], maps["simt"]
     assert a[0] == b[0] and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
     assert float((a[3] - b[3]).abs().max()) < 2e-5
+
+
+def test_mesh_scene_against_oracle(model, dev):
+    """BASELINE config 4 at reduced size (sphere R=0.9 m, 5 cm PLIVoxes, voxel_resolution 5 = 1 cm): select + lattice decode +
+    trilinear/select + marching cubes vs the oracle restatement of map.py:624-702 on the same map."""
+    from difusion_b200 import synthetic as S
+    from difusion_b200.system.map import DenseIndexedMap
+    from oracle import dif_oracle as O
+    R, n_pts = 0.9, 200_000
+    sc = S.Scene("S2s", [-1.1] * 3, [1.1] * 3, 0.05, 2, 4.0)
+    i = np.arange(n_pts) + 0.5
+    phi = np.arccos(1 - 2 * i / n_pts); th = np.pi * (1 + 5 ** 0.5) * i
+    d = np.stack([np.cos(th) * np.sin(phi), np.sin(th) * np.sin(phi), np.cos(phi)], 1)
+    pts, nrm = (R * d).astype(np.float32), (-d).astype(np.float32)
+    W = O.load_weights_npz(GOLDEN / "weights.npz")
+    m = DenseIndexedMap(model, sc.map_args(), 29, dev)
+    o = O.OracleMap(W, sc.map_args())
+    for c in range(2):
+        sl = slice(c * n_pts // 2, (c + 1) * n_pts // 2)
+        m.integrate_keyframe(_t(pts[sl], dev), _t(nrm[sl], dev))
+        o.integrate_keyframe(pts[sl], nrm[sl])
+    assert m.n_occupied == o.n_occupied and np.array_equal(m.indexer.cpu().numpy(), o.indexer)
+    assert np.array_equal(m.voxel_obs_count.cpu().numpy(), o.voxel_obs_count)
+    assert close(m.latent_vecs.cpu().numpy(), o.latent_vecs, TOL)
+    for fast in (True, False):
+        focused, mapping, cs, cd, slots, cnt = m.mesh_cubes(5, fast=fast, updated_vec_id=None)
+        o_foc, o_map, o_hs, o_hd, o_occ = o.mesh_cubes(5, fast=fast, no_cache=True)
+        assert np.array_equal(focused.cpu().numpy(), o_foc) and np.array_equal(slots.cpu().numpy(), o_occ)
+        assert np.array_equal(mapping.cpu().numpy()[:o_map.shape[0]], o_map)
+        # threshold flips of the |sdf|<0.05 re-evaluation set are allowed on a tiny fraction of samples
+        assert frac_off(cs.cpu().numpy(), o_hs) < 2e-4 and frac_off(cd.cpu().numpy(), o_hd) < 2e-4
+        if fast:
+            assert abs(int(cnt[1]) - o.last_stats["n_high"]) <= max(20, o.last_stats["n_high"] // 2000)
+        n_tri = _assert_mc_equal(m.indexer.view(m.n_xyz), focused, mapping, cs, cd, m.n_xyz, 0.15, max_tri=int(6e6))
+        assert n_tri > 10000
+    # incremental extraction: only PLIVoxes touched since the last extraction are re-meshed (map.py:610-622, 703-714)
+    mesh_all = m.extract_mesh(5, int(6e6), max_std=0.15, no_cache=True)
+    extra = (pts[:2000] * np.float32(1.0)).astype(np.float32)
+    m.integrate_keyframe(_t(extra, dev), _t(nrm[:2000], dev))
+    upd = m.mesh_cache.updated_vec_id
+    assert 0 < upd.numel() < m.n_occupied
+    mesh_inc = m.extract_mesh(5, int(6e6), max_std=0.15)
+    assert mesh_inc.triangles.shape[0] > 0 and m.mesh_cache.updated_vec_id.numel() == 0
+    assert abs(mesh_inc.triangles.shape[0] - mesh_all.triangles.shape[0]) < 0.2 * mesh_all.triangles.shape[0]

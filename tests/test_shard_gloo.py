@@ -1,0 +1,67 @@
+"""CPU, world_size 2, gloo: the multi-GPU host logic of difusion_b200/shard.py (ownership hash, variable-length row exchange,
+ICP normal-equation combine) - the same code drives NCCL on GPUs."""
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    from difusion_b200 import shard
+    g = shard.ShardGroup()
+    ok = True
+    # --- variable-length exchange, including an empty contribution
+    rng = np.random.default_rng(100 + rank)
+    for counts in ([5, 9], [0, 4], [0, 0], [300, 1]):
+        n = counts[rank]
+        slots = torch.from_numpy(rng.integers(0, 1000, n).astype(np.int32))
+        rows = torch.from_numpy(rng.normal(size=(n, 29)).astype(np.float32))
+        s_all, r_all = g.all_gather_rows(slots, rows)
+        ok &= s_all.numel() == sum(counts) and r_all.shape == (sum(counts), 29)
+        off = sum(counts[:rank])
+        ok &= torch.equal(s_all[off:off + n], slots) and torch.equal(r_all[off:off + n], rows)
+    # --- a sharded "map": every rank fuses the rows it owns, the exchange makes all replicas identical
+    world_rows = 4096
+    lin = torch.arange(world_rows, dtype=torch.int64) * 7 + 3
+    own = shard.owner_of(lin, world)
+    ok &= bool(torch.equal(own, torch.from_numpy(shard.owner_of_np(lin.numpy(), world))))
+    ok &= all(int((own == r).sum()) > world_rows // (2 * world) for r in range(world))       # balanced
+    table = torch.zeros(world_rows, 29)
+    mine = torch.nonzero(own == rank).flatten()
+    table[mine] = torch.arange(world_rows, dtype=torch.float32)[mine, None] + torch.arange(29, dtype=torch.float32)[None, :] / 100
+    s_all, r_all = g.all_gather_rows(mine.int(), table[mine])
+    table.index_copy_(0, s_all.long(), r_all)
+    ref = torch.arange(world_rows, dtype=torch.float32)[:, None] + torch.arange(29, dtype=torch.float32)[None, :] / 100
+    ok &= bool(torch.equal(table, ref))
+    # --- ICP combine: per-rank (already normalised) partial systems -> the global one
+    rng = np.random.default_rng(7)
+    J = rng.normal(size=(1000, 6)); r = rng.normal(size=1000)
+    lo, hi = 1000 * rank // world, 1000 * (rank + 1) // world
+    Jr, rr = J[lo:hi], r[lo:hi]
+    out = np.zeros(44); M = hi - lo
+    out[:36] = (Jr.T @ Jr / M).ravel(); out[36:42] = Jr.T @ rr / M; out[42] = rr @ rr / M; out[43] = M
+    tot = shard.combine_icp(torch.from_numpy(out), g).numpy()
+    ok &= np.allclose(tot[:36], (J.T @ J / 1000).ravel()) and np.allclose(tot[36:42], J.T @ r / 1000) and np.isclose(tot[42], r @ r / 1000) and tot[43] == 1000
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_shard_host_logic_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]

@@ -1,0 +1,50 @@
+"""Run under torchrun with N GPUs: a hash-sharded map must end up bit-identical in its integer state, and (because every latent
+row is computed by exactly one owner with the same kernel) bit-identical in its latents, to a single-GPU map; the sharded ICP
+system must match the single-GPU one.   torchrun --nproc-per-node 2 --master-addr 127.0.0.1 tools/shard_check.py"""
+import os, sys, time
+from pathlib import Path
+import numpy as np, torch, torch.distributed as dist
+ROOT = Path(__file__).resolve().parents[1]; sys.path.insert(0, str(ROOT))
+from difusion_b200 import shard, synthetic as S
+from difusion_b200.network import utility as net_util
+from difusion_b200.system.map import DenseIndexedMap
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+g = shard.ShardGroup()
+model, _ = net_util.load_model(str(ROOT / "tests" / "golden" / "weights.npz"))
+sc = S.scene_S1(0.05)
+ref = DenseIndexedMap(model, sc.map_args(), 29, dev)                  # every rank also builds the unsharded map to compare
+sm = shard.make_sharded_map(model, sc.map_args(), 29, dev, g)
+ok = True
+n_frames = 6
+for f in range(n_frames):
+    R, t = S.orbit_pose(f * 10); pc, nc = S.frame_points(sc, R, t); xw, nw = S.to_world(pc, nc, R, t)
+    xw_d, nw_d, pc_d = torch.from_numpy(xw).to(dev), torch.from_numpy(nw).to(dev), torch.from_numpy(pc).to(dev)
+    if f >= 1:
+        a = ref.icp_linearize(pc_d, R, t, np.eye(3), np.zeros(3)).cpu().numpy()
+        b = sm.icp_linearize(pc_d, R, t, np.eye(3), np.zeros(3)).cpu().numpy()
+        icp_ok = a[43] == b[43] and np.abs(a[:36] - b[:36]).max() <= 2e-4 * np.abs(a[:36]).max() and abs(a[42] - b[42]) <= 1e-5 * abs(a[42])   # (ReLU-kink flips on 1e-7 latent noise)
+        if not icp_ok and rank == 0:
+            print("ICP mismatch", a[43], b[43], np.abs(a[:36] - b[:36]).max() / np.abs(a[:36]).max(), abs(a[42] - b[42]) / abs(a[42]))
+        ok &= bool(icp_ok)
+    m1 = ref.integrate_keyframe(xw_d, nw_d); m2 = sm.integrate_keyframe(xw_d, nw_d)
+    ok &= torch.equal(m1, m2) and ref.n_occupied == sm.n_occupied
+    ok &= torch.equal(ref.indexer, sm.indexer) and torch.equal(ref.voxel_obs_count, sm.voxel_obs_count) and torch.equal(ref.latent_vecs_pos, sm.latent_vecs_pos)
+    d = (ref.latent_vecs - sm.latent_vecs).abs().max().item()
+    ok &= d <= 2e-6            # same kernel, same samples per PLIVox; only the atomic accumulation order differs
+    if rank == 0:
+        print(f"frame {f}: n_occ {sm.n_occupied}  encoder samples on rank0 {sm.last_integrate_stats['n_samples']} of {ref.last_integrate_stats['n_samples']}"
+              f"  rows sent {sm.last_exchange['rows_sent']} / exchanged {sm.last_exchange['rows_total']}  max|dlatent| {d:.2e}")
+mesh_ref = ref.extract_mesh(4, int(4e6), max_std=0.15, no_cache=True)
+mesh_s = sm.extract_mesh(4, int(4e6), max_std=0.15, no_cache=True)
+cnt = torch.tensor([mesh_s.triangles.shape[0]], device=dev); dist.all_reduce(cnt)
+ok &= abs(int(cnt.item()) - mesh_ref.triangles.shape[0]) <= 0.002 * mesh_ref.triangles.shape[0]      # sign/threshold flips on 1e-7 latent noise
+flag = torch.tensor([int(ok)], device=dev); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print(f"mesh: single-GPU {mesh_ref.triangles.shape[0]} triangles, sharded total {int(cnt.item())} (rank0 part {mesh_s.triangles.shape[0]})")
+    print("SHARD CHECK", "OK" if flag.item() else "FAILED", f"world={world}")
+dist.destroy_process_group()
+sys.exit(0 if flag.item() else 1)
