@@ -319,16 +319,30 @@ def main():
     enc_flop = ENC_FLOP * float(sum(enc_samples))
     icp_flop = (DEC_FWD_FLOP + DEC_BWD_FLOP) * float(sum(icp_samples))
     enc_t, icp_t = sum(enc_ms) * 1e-3, sum(icp_ms) * 1e-3
-    dom = "encode_accumulate_kernel" if enc_t >= icp_t else "icp_linearize_kernel"
+    dom = "enc::encode_tc_kernel" if enc_t >= icp_t else "tc::icp_tc_kernel"
     dflop, dt, dn = (enc_flop, enc_t, len(enc_ms)) if enc_t >= icp_t else (icp_flop, icp_t, len(icp_ms))
     achieved = dflop / dt / 1e12 if dt > 0 else 0.0
+
+    def ncu_traffic(tag):                                   # dram read+write bytes per launch from the committed ncu --set full capture
+        f = ROOT / "profiles" / f"r1_ncu_{tag}_metrics.csv"
+        if not f.exists():
+            return None
+        tot = 0.0
+        for line in f.read_text().splitlines():
+            k, u, v = line.split(",")[:3]
+            if k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+        return tot
     roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tf_sustained"], "traffic": None, "peak_source": pk["src"] + ", bf16 sustained (kernel timed inside a long step)",
+                "frac": achieved / pk["tf_sustained"], "traffic": ncu_traffic("encode_tc" if enc_t >= icp_t else "icp_tc"),
+                "peak_source": pk["src"] + ", bf16 sustained (kernel timed inside a long step)",
                 "avg_launch_ms": 1e3 * dt / max(dn, 1), "algorithmic_flop_per_launch": dflop / max(dn, 1),
                 "share_of_step": dt / (total_ms * 1e-3),
-                "note": "fp32 SIMT path this round (exact-fp32 parity path); algorithmic FLOPs per SURVEY 8(d)",
-                "other": {"encode_accumulate_kernel": {"ms_total": sum(enc_ms), "tflops": enc_flop / enc_t / 1e12 if enc_t else 0, "samples": int(sum(enc_samples))},
-                          "icp_linearize_kernel": {"ms_total": sum(icp_ms), "tflops": icp_flop / icp_t / 1e12 if icp_t else 0, "samples": int(sum(icp_samples))}}}
+                "note": "tcgen05 kernels, ALGORITHMIC FLOPs per SURVEY 8(d) (decoder fwd 98816 + bwd 91904, encoder 52096 per sample); the tensor pipe issues "
+                        "3x that (fp16 hi/lo split passes).  A frame is only ~250 tiles of 128 samples, so these launches are latency-bound; the large-batch "
+                        "figure for the same MMA pipeline is in decoder_sweep / profiles/",
+                "other": {"enc::encode_tc_kernel": {"ms_total": sum(enc_ms), "tflops": enc_flop / enc_t / 1e12 if enc_t else 0, "samples": int(sum(enc_samples))},
+                          "tc::icp_tc_kernel": {"ms_total": sum(icp_ms), "tflops": icp_flop / icp_t / 1e12 if icp_t else 0, "samples": int(sum(icp_samples))}}}
 
     # ------------------------------------------------------------------ config 3 extras: decoder batch sweep (samples/s)
     sweep = {}

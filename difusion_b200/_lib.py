@@ -46,7 +46,7 @@ SIGNATURES = {
     "dif_encode": (C.c_int, [_P, _P, _I64, _P, _P]),
     "dif_map_query": (C.c_int, [_MV, _P, _I64, _P, _P, _P, _P]),
     "dif_icp_scratch_bytes": (_SZ, [_I64]),
-    "dif_icp_linearize": (C.c_int, [_MV, _P, _P, _I64, C.POINTER(C.c_float), _F, C.c_int, _P, _SZ, _P, _P]),
+    "dif_icp_linearize": (C.c_int, [_MV, _P, _P, _I64, _P, _F, C.c_int, _P, _SZ, _P, _P]),
     "dif_mesh_select_scratch_bytes": (_SZ, [_I64, _I64]),
     "dif_mesh_select": (C.c_int, [_MV, _P, _I64, _P, _P, _P, _P, _P, _SZ, _P]),
     "dif_mesh_decode_scratch_bytes": (_SZ, [_I64, C.c_int]),

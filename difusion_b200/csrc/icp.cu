@@ -167,15 +167,14 @@ int dif_icp_linearize(const dif_map_view* map, const void* decoder_prepared, con
     Carver c(scratch);
     float* partials = c.take<float>((size_t)DIF_NUM_SMS * 3 * ICP_VALS);
     unsigned int* counter = c.take<unsigned int>(1);
-    cudaMemsetAsync(counter, 0, sizeof(unsigned int), st);
-    cudaMemsetAsync(out_dev, 0, 44 * sizeof(double), st);
+    // `scratch` is zero-filled once by the caller; both kernels leave the counter zeroed again when they finish and write
+    // every partial row they later read, so no memset is needed per call.
     // tensor-core path (decoder forward + backward on tcgen05) for frames worth of points; DIF_ICP_PATH=simt forces fp32 SIMT
     const char* path_env = getenv("DIF_ICP_PATH");                     // read per call so tests can compare both paths
     const bool force_simt = path_env && path_env[0] == 's';
     if (!force_simt && n >= 2048) {
-        double* accum = reinterpret_cast<double*>(partials);               // 32 fp64 accumulators at the head of the scratch
-        cudaMemsetAsync(accum, 0, 32 * sizeof(double), st);
-        IcpTcArgs a{m, obs_xyz, (int)n, p, huber_k, want_grad, accum, counter, out_dev};
+        static_assert((size_t)DIF_NUM_SMS * 32 * sizeof(double) <= (size_t)DIF_NUM_SMS * 3 * ICP_VALS * sizeof(float), "partials region");
+        IcpTcArgs a{m, obs_xyz, (int)n, p, huber_k, want_grad, reinterpret_cast<double*>(partials), counter, out_dev};
         return launch_icp_tc(decoder_prepared, a, st);
     }
     const int64_t n_tiles = (n + MLP_T - 1) / MLP_T;

@@ -9,8 +9,8 @@ struct Pose { float Rc[9], tc[3], Rd[9], td[3], Rl[9]; };      // composite (las
 
 struct IcpTcArgs {
     MapRO m; const float* obs; int n; Pose pose; float huber_k; int want_grad;
-    double* accum;                // [32] fp64 sums: 21 upper-triangular H, 6 g, energy, M  (zeroed before the launch)
-    unsigned int* done_counter;   // zeroed before the launch
+    double* partials;             // [grid][32] per-CTA fp64 sums: 21 upper-triangular H, 6 g, energy, M (every row fully written)
+    unsigned int* done_counter;   // zero on entry, left zero on exit
     double* out;                  // [44]
 };
 

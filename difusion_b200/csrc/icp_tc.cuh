@@ -211,6 +211,7 @@ __global__ void __launch_bounds__(THREADS, 1) icp_tc_kernel(const unsigned char*
         const float* wuc = c_head_w[head_slot][1];
         const float b4 = __ldg(P + DecW::b4), bu = __ldg(P + DecW::bu);
         uint32_t ph_acc = 0;
+        double lane_sum = 0.0;                          // lane j of a half-1 warp: running sum of value j over this warp's tiles
         mbar_wait(bar0 + 8 * BAR_W, 0);
         for (int64_t it = 0;; ++it) {
             const int64_t tile = blockIdx.x + (int64_t)gridDim.x * (2 * it + s);
@@ -381,24 +382,42 @@ __global__ void __launch_bounds__(THREADS, 1) icp_tc_kernel(const unsigned char*
 #pragma unroll
                 for (int j = 0; j < 29; ++j) {
                     const float t = warp_sum(v[j]);
-                    if (lane == j) atomicAdd(a.accum + j, (double)t);      // one fp64 atomic per value per warp-tile
+                    if (lane == j) lane_sum += (double)t;
                 }
             }
         }
+        // no tile of this slot is left: its x tile is dead and becomes the CTA's reduction buffer [slot][quad][32] (fp64)
+        if (half == 1) reinterpret_cast<double*>(smem + OFF_X + s * 2 * X_PLANE_B)[quad * 32 + lane] = lane_sum;
     }
     tc_fence_before();
     __syncthreads();
     if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(512));
-    // ---- last CTA: scale by 1/M and expand the symmetric H
+    // ---- deterministic reduction (no atomics on the sums): fixed-order sum of the CTA's 8 warps -> partials[cta][32];
+    //      the last CTA to finish adds the CTAs' partials in a fixed order, scales by 1/M and expands the symmetric H
     __shared__ bool is_last;
-    if (threadIdx.x == 0) {
+    if (warp == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += reinterpret_cast<const double*>(smem + OFF_X + (w >> 2) * 2 * X_PLANE_B)[(w & 3) * 32 + lane];
+        a.partials[(size_t)blockIdx.x * 32 + lane] = t;
         __threadfence();
-        is_last = atomicAdd(a.done_counter, 1u) == gridDim.x - 1;
+        __syncwarp();
+        if (lane == 0) is_last = atomicAdd(a.done_counter, 1u) == gridDim.x - 1;
     }
     __syncthreads();
-    if (is_last && threadIdx.x < 32) {
-        __threadfence();
-        const double tot = threadIdx.x < 29 ? __ldcg(a.accum + threadIdx.x) : 0.0;
+    if (!is_last) return;
+    __threadfence();
+    double* red = reinterpret_cast<double*>(smem + OFF_X);                 // [16 slices][32]
+    if (threadIdx.x < 512) {
+        double t = 0.0;
+        for (unsigned c = threadIdx.x >> 5; c < gridDim.x; c += 16) t += __ldcg(a.partials + (size_t)c * 32 + lane);
+        red[threadIdx.x] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double tot = 0.0;
+#pragma unroll
+        for (int w = 0; w < 16; ++w) tot += red[w * 32 + threadIdx.x];
         const double M = __shfl_sync(0xffffffffu, tot, 28);
         const double scale = M > 0.0 ? 1.0 / M : 0.0;
         if (threadIdx.x < 21) {
@@ -409,6 +428,7 @@ __global__ void __launch_bounds__(THREADS, 1) icp_tc_kernel(const unsigned char*
         } else if (threadIdx.x < 27) a.out[36 + threadIdx.x - 21] = tot * scale;
         else if (threadIdx.x == 27) a.out[42] = tot * scale;
         else if (threadIdx.x == 28) a.out[43] = M;
+        if (threadIdx.x == 0) *a.done_counter = 0u;       // leave the counter clean for the next call (zero-filled once by the caller)
     }
 }
 

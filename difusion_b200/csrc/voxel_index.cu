@@ -64,8 +64,10 @@ constexpr int64_t MAX_CHUNKS = (int64_t(1) << 31) / 32 / CHUNK_WORDS;
 
 // ------------------------------------------------------------------------------------------------ K1 voxelise + histogram
 __global__ void voxelize_kernel(MapDev m, const float* __restrict__ xyz, int n, float* __restrict__ p_hat,
-                                int32_t* __restrict__ cell, uint32_t* __restrict__ cell_count, int32_t* __restrict__ stats) {
+                                int32_t* __restrict__ cell, uint32_t* __restrict__ cell_count, int32_t* __restrict__ stats,
+                                int32_t* __restrict__ ctr) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < CTR_COUNT) ctr[i] = 0;                  // per-call counters (first read by a later kernel of the same call)
     if (i >= n) return;
     const float3 p = normalize_point(m.g, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
     p_hat[3 * i] = p.x; p_hat[3 * i + 1] = p.y; p_hat[3 * i + 2] = p.z;
@@ -449,12 +451,12 @@ int dif_integrate(const dif_map_view* map, const void* encoder_prepared, const f
     const Scratch S = carve_scratch(scratch, n > 0 ? n : 1, MAX_CHUNKS);
     const int64_t n_words = (n_cells + 31) / 32;
     const int n_chunks = (int)((n_words + CHUNK_WORDS - 1) / CHUNK_WORDS);
-    cudaMemsetAsync(S.ctr, 0, CTR_COUNT * sizeof(int32_t), st);
     cudaMemsetAsync(stats_dev, 0, DIF_STAT_COUNT * sizeof(int32_t), st);
+    if (n == 0) cudaMemsetAsync(S.ctr, 0, CTR_COUNT * sizeof(int32_t), st);      // (otherwise zeroed by voxelize_kernel)
     const int PT = 64;                                             // small blocks: a 30k-point frame must still fill 148 SMs
     const int nb = (int)((n + PT - 1) / PT);
     if (n > 0) {
-        voxelize_kernel<<<nb, PT, 0, st>>>(m, xyz, (int)n, S.p_hat, S.cell, P.cell_count, stats_dev);
+        voxelize_kernel<<<nb, PT, 0, st>>>(m, xyz, (int)n, S.p_hat, S.cell, P.cell_count, stats_dev, S.ctr);
         prune_mark_kernel<<<nb, PT, 0, st>>>(m, (int)n, S.cell, P.cell_count, S.kept, unq_mask, P.bitmap, stats_dev);
         DIF_COUNT_LAUNCH(2);
     }

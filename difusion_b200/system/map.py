@@ -123,6 +123,7 @@ class DenseIndexedMap:
         self._scratch_points = 0
         self._mesh_persist = None
         self._icp_scratch = None
+        self._view_key, self._view_obj = None, None
         self._icp_out = None
         self._grow(max(1, _next_pow2(int(initial_capacity))))
 
@@ -220,6 +221,10 @@ class DenseIndexedMap:
         self.n_occupied = n
 
     def _view(self) -> _lib.MapView:
+        key = (self._indexer.data_ptr(), self._latent.data_ptr(), self._cap_phys, self._shard_rank, self._shard_world,
+               self._xchg.data_ptr() if self._xchg is not None else 0)
+        if self._view_key == key:
+            return self._view_obj
         a = self.args
         v = _lib.MapView()
         v.indexer, v.latent_vecs, v.latent_vecs_pos = self._indexer.data_ptr(), self._latent.data_ptr(), self._pos.data_ptr()
@@ -234,6 +239,7 @@ class DenseIndexedMap:
         v.encoder_count_th = float(a.encoder_count_th)
         v.shard_rank, v.shard_world = self._shard_rank, self._shard_world
         v.xchg_slots = self._xchg.data_ptr() if self._xchg is not None else None
+        self._view_key, self._view_obj = key, v
         return v
 
     # ------------------------------------------------------------------ addressing helpers (map.py:287-319)
@@ -315,12 +321,12 @@ class DenseIndexedMap:
         x = obs_xyz.detach().contiguous().float()
         n = x.size(0)
         if self._icp_scratch is None:
-            self._icp_scratch = torch.empty(self._L.dif_icp_scratch_bytes(n), dtype=torch.uint8, device=self.device)
+            self._icp_scratch = torch.zeros(self._L.dif_icp_scratch_bytes(n), dtype=torch.uint8, device=self.device)   # zero-filled once (ABI)
         out = torch.empty(44, dtype=torch.float64, device=self.device)
-        pose = (ctypes.c_float * 24)(*np.concatenate([np.asarray(R_last, np.float64).ravel(), np.asarray(t_last, np.float64).ravel(),
-                                                      np.asarray(R_delta, np.float64).ravel(), np.asarray(t_delta, np.float64).ravel()]).astype(np.float32).tolist())
+        pose = np.empty(24, np.float32)
+        pose[0:9], pose[9:12], pose[12:21], pose[21:24] = np.ravel(R_last), np.ravel(t_last), np.ravel(R_delta), np.ravel(t_delta)
         view = self._view()
-        _lib.check(self._L.dif_icp_linearize(ctypes.byref(view), self._prep.decoder.data_ptr(), x.data_ptr(), n, pose,
+        _lib.check(self._L.dif_icp_linearize(ctypes.byref(view), self._prep.decoder.data_ptr(), x.data_ptr(), n, pose.ctypes.data,
                                              float(huber_k) if huber_k else 0.0, int(want_grad), self._icp_scratch.data_ptr(),
                                              self._icp_scratch.numel(), out.data_ptr(), _lib.stream_ptr(self.device)), "dif_icp_linearize")
         return out

@@ -124,7 +124,8 @@ int dif_map_query(const dif_map_view* map, const float* xyz, int64_t n, int32_t*
  * Fused: transform obs by last*delta, lookup, decoder fwd (+bwd wrt xyz), r = sdf/std, J = [G R_last^T, q x .],
  * Huber(k) (huber_k <= 0: no robust kernel), normal equations.  pose = {R_last[9], t_last[3], R_delta[9], t_delta[3]}
  * row-major fp32 (host memory, copied at call time).  out_dev[44] (fp64): H[36] row-major, g[6], energy, M (valid count);
- * already divided by M as the reference does.  want_grad = 0 reproduces no_grad=True (only energy and M are written). */
+ * already divided by M as the reference does.  want_grad = 0 reproduces no_grad=True (only energy and M are written).
+ * `scratch` must be zero-filled ONCE by the caller; every call leaves it zero-filled again. */
 size_t dif_icp_scratch_bytes(int64_t n);
 int dif_icp_linearize(const dif_map_view* map, const void* decoder_prepared, const float* obs_xyz /*[n][3] camera frame*/,
                       int64_t n, const float* pose_host /*[24]*/, float huber_k, int want_grad,

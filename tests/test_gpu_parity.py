@@ -309,6 +309,64 @@ def test_large_batch_properties(model, dev):
         assert float((fd - ga[:, c]).abs().median()) < 2e-3
 
 
+def test_large_map_properties(model, dev):
+    """BASELINE config-5 scale: a 1000 x 1000 x 40 = 40 M-cell dense index (320 MB), S1-sized views into a height field.
+    The oracle cannot hold this in reasonable time, so the integer state is checked against an independent torch
+    formulation of the allocation rule (map.py:366-387) and the floating-point state through invariants."""
+    import argparse
+    from difusion_b200.system.map import DenseIndexedMap
+    vs = 0.05
+    args = argparse.Namespace(bound_min=[0.0, 0.0, 0.0], bound_max=[50.0, 50.0, 2.0], voxel_size=vs, prune_min_vox_obs=2,
+                              ignore_count_th=4.0, encoder_count_th=600.0)
+    m = DenseIndexedMap(model, args, 29, dev, initial_capacity=1 << 20)
+    assert m.n_xyz == [1000, 1000, 40] and m.indexer.numel() == 40_000_000
+    g = torch.Generator().manual_seed(21)
+    occupied = torch.zeros(40_000_000, dtype=torch.bool, device=dev)
+    total = 0
+    for f in range(6):
+        # a 6 m x 6 m patch of the height field z = 1 + 0.4 sin(x) cos(0.7 y), ~30k points, patches overlap between frames
+        x0, y0 = 5.0 + 4.0 * f, 45.0 - 6.0 * f
+        xy = torch.rand(30_000, 2, generator=g) * 6.0 + torch.tensor([x0, y0])
+        z = 1.0 + 0.4 * torch.sin(xy[:, 0]) * torch.cos(0.7 * xy[:, 1])
+        pts = torch.cat([xy, z[:, None]], 1).float().to(dev)
+        nrm = torch.tensor([[0.0, 0.0, 1.0]]).repeat(pts.size(0), 1).to(dev)
+        n_before = m.n_occupied
+        mask = m.integrate_keyframe(pts, nrm)
+        # independent restatement of voxelise + prune + allocate with sort-based torch ops
+        # (a 0-dim CUDA divisor forces a true fp32 division like torch-CPU, the oracle's arithmetic; with a Python-float
+        #  divisor torch-CUDA multiplies by the fp32 reciprocal instead, which moves points that sit on a cell face)
+        ijk = (torch.ceil((pts - torch.tensor(args.bound_min, device=dev)) / torch.tensor(vs, device=dev)) - 1).long()
+        lin = ijk[:, 2] + 40 * ijk[:, 1] + 40_000 * ijk[:, 0]
+        uq, inv, cnt = torch.unique(lin, return_inverse=True, return_counts=True)
+        keep = cnt[inv] > 2
+        assert torch.equal(mask, keep)
+        kept = ijk[keep]
+        nb = torch.tensor([[0, 0, 0], [1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], device=dev)
+        cand = (kept[:, None, :] + nb[None]).reshape(-1, 3)
+        hi = torch.tensor([999, 999, 39], device=dev)
+        cand = torch.minimum(torch.maximum(cand, torch.zeros_like(hi)), hi)
+        cl = torch.unique(cand[:, 2] + 40 * cand[:, 1] + 40_000 * cand[:, 0])
+        new = cl[~occupied[cl]]                                           # ascending linear id == slot order
+        occupied[new] = True
+        assert m.n_occupied == n_before + new.numel()
+        assert torch.equal(m.latent_vecs_pos[n_before:m.n_occupied], new)
+        assert torch.equal(m.indexer[new], torch.arange(n_before, m.n_occupied, device=dev))
+        total += int(keep.sum())
+    n = m.n_occupied
+    assert int((m.indexer >= 0).sum()) == n == int(occupied.sum())
+    assert torch.equal(m.indexer[m.latent_vecs_pos[:n]], torch.arange(n, device=dev))          # indexer and pos are inverse maps
+    obs = m.voxel_obs_count[:n]
+    lat = m.latent_vecs[:n]
+    assert bool(torch.isfinite(lat).all()) and float(obs.min()) >= 0 and bool((obs == obs.round()).all())
+    assert bool((lat[obs == 0] == 0).all()) and bool((lat[obs > 0].abs().sum(1) > 0).all())
+    # every kept point contributes to at most 8 cells, at least its own
+    assert total <= float(obs.sum()) <= 8 * total
+    # decode through the big index: samples in observed cells are valid, far-away ones are not
+    q = torch.cat([pts[:4096], pts[:16] + torch.tensor([0.0, 0.0, 0.9], device=dev)])
+    sdf, std, valid = m.get_sdf(q)
+    assert int(valid[:4096].sum()) > 2000 and not bool(valid[4096:].any()) and float(sdf.abs().max()) <= 1.0 and float(std.min()) > 0.05
+
+
 def test_tensor_core_decoder_matches_fp32_path(golden, model, dev):
     """tcgen05 forward (3-pass fp16 split, fp32 TMEM accumulation) vs the exact-fp32 SIMT kernel and vs the reference fixture.
     Forward-only launches of >= 1024 samples take the tensor-core kernel; a launch that also asks for d/dxyz takes the SIMT kernel."""
@@ -371,6 +429,11 @@ def test_tensor_core_icp_matches_fp32_path(golden, model, dev, monkeypatch):
         o2 = m.icp_linearize(obs[:n], last.q.rotation_matrix, last.t, delta.q.rotation_matrix, delta.t).cpu().numpy()
         monkeypatch.delenv("DIF_ICP_PATH", raising=False)
         assert o[43] == o2[43] and np.abs(o[:36] - o2[:36]).max() <= 2e-4 * np.abs(o2[:36]).max() and close(o[42], o2[42], 1e-5)
+    # the tensor-core kernel reduces through per-CTA partials in a fixed order: results are bit-reproducible run to run
+    delta = Isometry.from_twist(np.asarray([0.004, -0.003, 0.002, 0.003, -0.002, 0.001]))
+    runs = [m.icp_linearize(obs, last.q.rotation_matrix, last.t, delta.q.rotation_matrix, delta.t).cpu().numpy() for _ in range(4)]
+    assert all(np.array_equal(runs[0], r) for r in runs[1:])
+    assert np.array_equal(runs[0][:36].reshape(6, 6), runs[0][:36].reshape(6, 6).T)
 
 
 def test_tensor_core_encoder_matches_fp32_path(golden, model, dev, monkeypatch):
