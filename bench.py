@@ -371,7 +371,7 @@ def main():
                                 "frac_of_bf16_burst_peak": sps * DEC_FWD_FLOP / 1e12 / pk["tf_burst"]}
 
     # ------------------------------------------------------------------ cpu baseline: the oracle port on the host cores (bounded sample)
-    ns = min(a.cpu_sample, K)
+    ns = max(1, min(a.cpu_sample, K))
     cpu_sec = run_cpu_port(frames, sc, ns, 1, cores)
     cpu = {"value": ns / cpu_sec, "unit": "frames/s", "cores": cores, "kind": "port",
            "sample": f"frames 0..{ns - 1} of the same stream (the most expensive prefix: most PLIVoxes still below encoder_count_th), "

@@ -7,6 +7,7 @@
 #include "../../include/difusion_b200.h"
 
 #define DIF_L 29                 // latent dim
+#define DIF_SUM_STRIDE 32         // row stride of the per-slot encoder sums (16-byte aligned rows: float4 reductions)
 #define DIF_NUM_SMS 148          // B200
 
 namespace dif {
@@ -33,6 +34,27 @@ inline int check_launch(const char* what) {
 }
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------------------
+// The per-frame path is a chain of short kernels; with the programmatic-stream-serialization attribute a kernel may be
+// scheduled while its predecessor is still running and blocks at pdl_wait() until the predecessor has completed and its
+// writes are visible, which hides the launch latency (and, for the tensor-core kernels, the weight-image load) behind the
+// predecessor.  Rules kept by every kernel launched through launch_pdl: pdl_wait() is executed unconditionally by every
+// thread before the first access to memory another kernel of the stream may have written, and nothing is read before it
+// except kernel parameters and the prepared (constant) network images.  DIF_PDL=0 turns the attribute off (A/B timing).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 // Carves a caller-provided workspace into aligned sub-buffers.
 struct Carver {

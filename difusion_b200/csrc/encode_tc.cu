@@ -10,7 +10,7 @@
 //   L0  x[128x16 (6 real)]  (smem)  * W0^T -> acc[:, 0:32]    -> +b, ReLU, split -> h0 (A operand in TMEM)
 //   L1  h0[128x32]          (TMEM)  * W1^T -> acc[:, 0:64]    -> h1
 //   L2  h1[128x64]          (TMEM)  * W2^T -> acc[:, 0:256]   -> h2 (K = 256: the whole 256-column A region)
-//   L3  h2[128x256]         (TMEM)  * W3^T -> acc[:, 0:32]    -> +b3 -> atomicAdd into slot_sum[slot][0:29]  (or plain store)
+//   L3  h2[128x256]         (TMEM)  * W3^T -> acc[:, 0:32]    -> +b3 -> float4 atomicAdd into slot_sum[slot][0:32]  (or plain store)
 // TMEM map (512 columns): accumulator [0, 256), A operand [256, 512).
 #include "tc_common.cuh"
 
@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(THREADS, 1) encode_tc_kernel(const unsigned ch
     const uint32_t bar0 = sbase + EOFF_BAR;
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + EOFF_BAR + 96);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_wait(); pdl_launch_dependents();                          // the sample count below is written by the previous kernel
     const int64_t n_total = a.mode == 0 ? (int64_t)*a.n_dev : a.n;
     const int64_t n_tiles = (n_total + TILE - 1) / TILE;
     if ((int64_t)blockIdx.x >= n_tiles) return;                   // nothing to do: skip the weight load altogether
@@ -270,14 +271,19 @@ __global__ void __launch_bounds__(THREADS, 1) encode_tc_kernel(const unsigned ch
             if (lane == 0) mbar_arrive(bar0 + 8 * EB_E);               // accumulator consumed: the next tile's layer 0 may start
             const int64_t si = tile * TILE + row;
             if (slot >= 0 && si < n_total) {
-                float* dst = a.mode == 0 ? a.slot_sum + (int64_t)slot * DIF_L : a.out + si * DIF_L;
+                float o[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int col = 8 * cq + j;
-                    if (col < DIF_L) {
-                        const float o = __uint_as_float(v[j]) + bias[352 + col];
-                        if (a.mode == 0) atomicAdd(dst + col, o); else dst[col] = o;
-                    }
+                for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(v[j]) + bias[352 + 8 * cq + j];      // (padding columns 29..31 are exactly 0)
+                if (a.mode == 0) {
+                    // two 16-byte vector reductions per thread into the 128-byte-strided sum row (4x fewer L2 atomic operations)
+                    float4* dst = reinterpret_cast<float4*>(a.slot_sum + (int64_t)slot * DIF_SUM_STRIDE + 8 * cq);
+                    atomicAdd(dst, make_float4(o[0], o[1], o[2], o[3]));
+                    atomicAdd(dst + 1, make_float4(o[4], o[5], o[6], o[7]));
+                } else {
+                    float* dst = a.out + si * DIF_L;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (8 * cq + j < DIF_L) dst[8 * cq + j] = o[j];
                 }
             }
         }
@@ -309,7 +315,7 @@ __global__ void prepare_encoder_tc_kernel(const float* __restrict__ P, unsigned 
     float* b = reinterpret_cast<float*>(image + EOFF_BIAS);
     for (int i = tid; i < 256; i += nth) {
         b[96 + i] = P[EncW::b2 + i];
-        if (i < 32) { b[i] = P[EncW::b0 + i]; b[352 + i] = P[EncW::b3 + i]; }
+        if (i < 32) { b[i] = P[EncW::b0 + i]; b[352 + i] = i < DIF_L ? P[EncW::b3 + i] : 0.f; }
         if (i < 64) b[32 + i] = P[EncW::b1 + i];
     }
 }
@@ -329,7 +335,7 @@ static int launch(const unsigned char* image, const enc::EncodeArgs& a, int64_t 
     const int grid = (int)(max_tiles < DIF_NUM_SMS ? (max_tiles > 0 ? max_tiles : 1) : DIF_NUM_SMS);
     cudaFuncSetAttribute(enc::encode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc::ESMEM_B);
     prof_begin(DIF_PROF_ENCODE, st);
-    enc::encode_tc_kernel<<<grid, tc::THREADS, enc::ESMEM_B, st>>>(image, a);
+    launch_pdl(enc::encode_tc_kernel, grid, tc::THREADS, enc::ESMEM_B, st, image, a);
     prof_end(DIF_PROF_ENCODE, st);
     DIF_COUNT_LAUNCH(1);
     return check_launch("encode_tc_kernel");

@@ -114,13 +114,17 @@ __global__ void __launch_bounds__(THREADS, 1) icp_tc_kernel(const unsigned char*
     tc_fence_after();
     const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_ptr_s, 0);
 
+    // The weight image is constant data: its load is issued BEFORE the programmatic-dependent-launch wait, so it (and the
+    // barrier / TMEM set-up above) overlaps with the tail of the previous kernel of the stream.
+    if (warp == MMA_WARP && lane == 0) {
+        mbar_expect_tx(bar0 + 8 * BAR_W, IMAGE_B);
+        constexpr uint32_t CH = 32768;
+        for (uint32_t off = 0; off < IMAGE_B; off += CH) bulk_g2s(sbase + off, image + off, (IMAGE_B - off) < CH ? (IMAGE_B - off) : CH, bar0 + 8 * BAR_W);
+    }
+    pdl_wait(); pdl_launch_dependents();
+
     if (warp == MMA_WARP) {
-        // ===================================================== weight load + MMA issuer (warp-uniform, instructions elected)
-        if (lane == 0) {
-            mbar_expect_tx(bar0 + 8 * BAR_W, IMAGE_B);
-            constexpr uint32_t CH = 32768;
-            for (uint32_t off = 0; off < IMAGE_B; off += CH) bulk_g2s(sbase + off, image + off, (IMAGE_B - off) < CH ? (IMAGE_B - off) : CH, bar0 + 8 * BAR_W);
-        }
+        // ===================================================== MMA issuer (warp-uniform, instructions elected)
         __syncwarp();
         mbar_wait(bar0 + 8 * BAR_W, 0);
         // forward (K-major) and backward (MN-major, LBO = 128 B between 8-row groups, SBO = slab chunk stride) descriptors
@@ -441,7 +445,7 @@ int launch_icp_tc(const void* decoder_prepared, const IcpTcArgs& a, cudaStream_t
     const int grid = (int)(n_tiles < DIF_NUM_SMS ? (n_tiles > 0 ? n_tiles : 1) : DIF_NUM_SMS);
     cudaFuncSetAttribute(tc::icp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::ICP_SMEM_B);
     prof_begin(DIF_PROF_ICP, st);
-    tc::icp_tc_kernel<<<grid, tc::THREADS, tc::ICP_SMEM_B, st>>>(image, P, a);
+    launch_pdl(tc::icp_tc_kernel, grid, tc::THREADS, tc::ICP_SMEM_B, st, image, P, a);
     prof_end(DIF_PROF_ICP, st);
     DIF_COUNT_LAUNCH(1);
     return check_launch("icp_tc_kernel");

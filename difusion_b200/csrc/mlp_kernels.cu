@@ -7,6 +7,10 @@
 namespace dif {
 
 thread_local char g_last_error[256] = "";
+bool pdl_enabled() {
+    const char* e = getenv("DIF_PDL");                                  // read per call so one process can time both settings
+    return !(e && e[0] == '0');
+}
 thread_local ProfHook g_prof[DIF_PROF_COUNT] = {};
 thread_local uint64_t g_launches = 0;
 

@@ -35,14 +35,17 @@ static MapDev to_dev(const dif_map_view* m) {
     return d;
 }
 
-struct Persist { uint32_t* cell_count; uint32_t* bitmap; uint32_t* slot_cnt; float* slot_sum; };
+constexpr int ALLOC_GRID_MAX = DIF_NUM_SMS * 4;      // blocks of alloc_kernel: all co-resident (they wait for each other)
+struct Persist { uint32_t* cell_count; uint32_t* bitmap; uint32_t* slot_cnt; float* slot_sum; int32_t* alloc_sync; };
 static size_t persist_bytes(int64_t n_cells, int64_t capacity) {
-    return align_up(n_cells * 4) + align_up(((n_cells + 31) / 32) * 4) + align_up(capacity * 4) + align_up(capacity * DIF_L * 4);
+    return align_up(n_cells * 4) + align_up(((n_cells + 31) / 32) * 4) + align_up(capacity * 4) + align_up(capacity * DIF_SUM_STRIDE * 4) +
+           align_up((ALLOC_GRID_MAX + 8) * 4);
 }
 static Persist carve_persist(void* p, int64_t n_cells, int64_t capacity) {
     Carver c(p); Persist r;
     r.cell_count = c.take<uint32_t>(n_cells); r.bitmap = c.take<uint32_t>((n_cells + 31) / 32);
-    r.slot_cnt = c.take<uint32_t>(capacity); r.slot_sum = c.take<float>(capacity * DIF_L);
+    r.slot_cnt = c.take<uint32_t>(capacity); r.slot_sum = c.take<float>(capacity * DIF_SUM_STRIDE);
+    r.alloc_sync = c.take<int32_t>(ALLOC_GRID_MAX + 8);
     return r;
 }
 
@@ -66,6 +69,7 @@ constexpr int64_t MAX_CHUNKS = (int64_t(1) << 31) / 32 / CHUNK_WORDS;
 __global__ void voxelize_kernel(MapDev m, const float* __restrict__ xyz, int n, float* __restrict__ p_hat,
                                 int32_t* __restrict__ cell, uint32_t* __restrict__ cell_count, int32_t* __restrict__ stats,
                                 int32_t* __restrict__ ctr) {
+    pdl_wait(); pdl_launch_dependents();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < CTR_COUNT) ctr[i] = 0;                  // per-call counters (first read by a later kernel of the same call)
     if (i >= n) return;
@@ -92,6 +96,7 @@ __device__ __forceinline__ void mark_if_empty(const MapDev& m, uint32_t* bitmap,
 __global__ void prune_mark_kernel(MapDev m, int n, const int32_t* __restrict__ cell, const uint32_t* __restrict__ cell_count,
                                   uint8_t* __restrict__ kept, uint8_t* __restrict__ unq_mask, uint32_t* __restrict__ bitmap,
                                   int32_t* __restrict__ stats) {
+    pdl_wait(); pdl_launch_dependents();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     bool k = false;
     if (i < n) {
@@ -134,9 +139,8 @@ __global__ void bitmap_count_kernel(const uint32_t* __restrict__ bitmap, int64_t
     }
 }
 
-// single block: exclusive scan of chunk sums in place; publishes base slot / total / overflow; bumps n_occupied.
-__global__ void bitmap_scan_kernel(int32_t* __restrict__ chunk_sum, int n_chunks, int32_t* __restrict__ n_occ, int64_t capacity,
-                                   int32_t* __restrict__ ctr, int32_t* __restrict__ stats, int is_alloc) {
+// single block: exclusive scan of chunk sums in place; publishes the total (mesh selection path).
+__global__ void bitmap_scan_kernel(int32_t* __restrict__ chunk_sum, int n_chunks, int32_t* __restrict__ ctr) {
     __shared__ int warp_tot[32];
     __shared__ int carry_s;
     if (threadIdx.x == 0) carry_s = 0;
@@ -162,19 +166,7 @@ __global__ void bitmap_scan_kernel(int32_t* __restrict__ chunk_sum, int n_chunks
         if (threadIdx.x == 1023) carry_s = carry + warp_tot[31] + incl;
         __syncthreads();
     }
-    if (threadIdx.x == 0) {
-        const int total = carry_s;
-        if (is_alloc) {
-            const int base_slot = *n_occ;
-            const int overflow = (int64_t)base_slot + total > capacity;
-            ctr[CTR_BASE_SLOT] = base_slot; ctr[CTR_OVERFLOW] = overflow; ctr[CTR_N_NEW] = overflow ? 0 : total;
-            if (!overflow) *n_occ = base_slot + total; else atomicOr(stats + DIF_STAT_FLAGS, 2);
-            stats[DIF_STAT_N_NEW] = overflow ? 0 : total;
-            stats[DIF_STAT_N_OCCUPIED] = overflow ? base_slot : base_slot + total;
-        } else {
-            ctr[CTR_N_NEW] = total;
-        }
-    }
+    if (threadIdx.x == 0) ctr[CTR_N_NEW] = carry_s;
 }
 
 // rank of this thread's first set bit inside the chunk (threads own 4 consecutive words => ascending linear id order)
@@ -189,32 +181,112 @@ __device__ __forceinline__ int block_exclusive_scan(int c, int* warp_tot) {
     return off + incl - c;
 }
 
-// K3c: hand out slots in ascending linear id (map.py:283,318-319), initialise the new rows (map.py:269-277), clear the bitmap.
-__global__ void alloc_assign_kernel(MapDev m, uint32_t* __restrict__ bitmap, int64_t n_words, const int32_t* __restrict__ chunk_off,
-                                    const int32_t* __restrict__ ctr) {
+// K3 fused (integrate path): count + ordered scan + slot assignment in ONE launch.  Block b owns a contiguous range of bitmap
+// chunks; it publishes the population of its range, waits for every other block's figure (the grid is at most ALLOC_GRID_MAX
+// blocks, all co-resident), derives its base slot and the call's total, then walks its chunks in ascending linear-id order
+// (the order the reference's sorted unique gives, map.py:283).  sync[0..grid) = population + 1 (0 = not yet published), sync[ALLOC_GRID_MAX] = finished
+// blocks; the last block to finish zeroes them again, so `persist` stays in its zero-filled-once state between calls.
+__global__ void __launch_bounds__(SCAN_THREADS) alloc_kernel(MapDev m, uint32_t* __restrict__ bitmap, int64_t n_words, int n_chunks,
+                                                             int chunks_per_block, int32_t* sync, int32_t* __restrict__ ctr,
+                                                             int32_t* __restrict__ stats) {
+    pdl_wait(); pdl_launch_dependents();
     __shared__ int warp_tot[SCAN_THREADS / 32];
-    const int64_t w0 = (int64_t)blockIdx.x * CHUNK_WORDS + threadIdx.x * 4;
-    uint32_t w[4]; int c = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { w[j] = (w0 + j < n_words) ? bitmap[w0 + j] : 0u; c += __popc(w[j]); }
-    int rank = block_exclusive_scan(c, warp_tot);
-    if (c == 0) return;
-    const bool overflow = ctr[CTR_OVERFLOW] != 0;
-    int slot = ctr[CTR_BASE_SLOT] + chunk_off[blockIdx.x] + rank;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        uint32_t bits = w[j];
-        if (!bits) continue;
-        bitmap[w0 + j] = 0u;
-        while (bits && !overflow) {
-            const int b = __ffs(bits) - 1; bits &= bits - 1;
-            const int64_t lin = (w0 + j) * 32 + b;
-            m.indexer[lin] = slot; m.pos[slot] = lin; m.obs[slot] = 0.f;
-            float* row = m.latent + (int64_t)slot * DIF_L;
-#pragma unroll
-            for (int q = 0; q < DIF_L; ++q) row[q] = 0.f;
-            ++slot;
+    __shared__ int bcast[4];
+    const int c_begin = blockIdx.x * chunks_per_block;
+    const int c_end = min(n_chunks, c_begin + chunks_per_block);
+    // thread 0 reads n_occupied before it publishes this block's figure; block 0 updates it only after every block published
+    const int base_slot0 = threadIdx.x == 0 ? *reinterpret_cast<volatile int32_t*>(m.n_occ) : 0;
+    // ---- phase 1: population of the range
+    int c = 0;
+    for (int ch = c_begin; ch < c_end; ++ch) {
+        const int64_t w0 = (int64_t)ch * CHUNK_WORDS + threadIdx.x * 4;
+        if (w0 + 3 < n_words) {
+            const uint4 v = *reinterpret_cast<const uint4*>(bitmap + w0);
+            c += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+        } else {
+            for (int j = 0; j < 4; ++j) if (w0 + j < n_words) c += __popc(bitmap[w0 + j]);
         }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) warp_tot[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int j = 0; j < SCAN_THREADS / 32; ++j) t += warp_tot[j];
+        __threadfence();
+        atomicExch(sync + blockIdx.x, t + 1);
+    }
+    // ---- phase 2: every block's figure -> this block's exclusive prefix and the total
+    int before = 0, total = 0;
+    for (int j = threadIdx.x; j < (int)gridDim.x; j += SCAN_THREADS) {
+        int v;
+        while ((v = *reinterpret_cast<volatile int32_t*>(sync + j)) == 0) __nanosleep(64);
+        total += v - 1;
+        if (j < (int)blockIdx.x) before += v - 1;
+    }
+    __syncthreads();                                                   // warp_tot is reused
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { before += __shfl_xor_sync(0xffffffffu, before, o); total += __shfl_xor_sync(0xffffffffu, total, o); }
+    __shared__ int red[2][SCAN_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = before; red[1][threadIdx.x >> 5] = total; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int bsum = 0, tsum = 0;
+        for (int j = 0; j < SCAN_THREADS / 32; ++j) { bsum += red[0][j]; tsum += red[1][j]; }
+        const int base_slot = base_slot0;
+        const int overflow = (int64_t)base_slot + tsum > m.capacity;
+        bcast[0] = bsum; bcast[1] = tsum; bcast[2] = overflow; bcast[3] = base_slot;
+        if (blockIdx.x == 0) {
+            ctr[CTR_BASE_SLOT] = base_slot; ctr[CTR_OVERFLOW] = overflow; ctr[CTR_N_NEW] = overflow ? 0 : tsum;
+            if (!overflow) *m.n_occ = base_slot + tsum; else atomicOr(stats + DIF_STAT_FLAGS, 2);
+            stats[DIF_STAT_N_NEW] = overflow ? 0 : tsum;
+            stats[DIF_STAT_N_OCCUPIED] = overflow ? base_slot : base_slot + tsum;
+        }
+    }
+    __syncthreads();
+    const bool overflow = bcast[2] != 0;
+    int running = bcast[3] + bcast[0];
+    // ---- phase 3: hand out slots in ascending linear id (map.py:283,318-319), initialise rows (map.py:269-277), clear the bitmap
+    if (bcast[1] > 0) {
+        for (int ch = c_begin; ch < c_end; ++ch) {
+            const int64_t w0 = (int64_t)ch * CHUNK_WORDS + threadIdx.x * 4;
+            uint32_t w[4]; int cc = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { w[j] = (w0 + j < n_words) ? bitmap[w0 + j] : 0u; cc += __popc(w[j]); }
+            __syncthreads();                                           // warp_tot of the previous chunk has been read
+            const int rank = block_exclusive_scan(cc, warp_tot);
+            int chunk_total = 0;
+            for (int j = 0; j < SCAN_THREADS / 32; ++j) chunk_total += warp_tot[j];
+            int slot = running + rank;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint32_t bits = w[j];
+                if (!bits) continue;
+                bitmap[w0 + j] = 0u;
+                while (bits && !overflow) {
+                    const int b = __ffs(bits) - 1; bits &= bits - 1;
+                    const int64_t lin = (w0 + j) * 32 + b;
+                    m.indexer[lin] = slot; m.pos[slot] = lin; m.obs[slot] = 0.f;
+                    float* row = m.latent + (int64_t)slot * DIF_L;
+#pragma unroll
+                    for (int q = 0; q < DIF_L; ++q) row[q] = 0.f;
+                    ++slot;
+                }
+            }
+            running += chunk_total;
+        }
+    }
+    // ---- last block out cleans the synchronisation words
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        bcast[0] = atomicAdd(sync + ALLOC_GRID_MAX, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (bcast[0]) {
+        for (int j = threadIdx.x; j < (int)gridDim.x; j += SCAN_THREADS) sync[j] = 0;
+        if (threadIdx.x == 0) sync[ALLOC_GRID_MAX] = 0;
     }
 }
 
@@ -229,6 +301,7 @@ __global__ void gather_kernel(MapDev m, int n, const float* __restrict__ p_hat, 
                               const uint8_t* __restrict__ kept, uint32_t* __restrict__ cell_count, uint32_t* __restrict__ slot_cnt,
                               int32_t* __restrict__ s_pt, int32_t* __restrict__ s_slot, uint8_t* __restrict__ s_off,
                               int32_t* __restrict__ touched, int32_t* __restrict__ ctr, int32_t* __restrict__ stats) {
+    pdl_wait(); pdl_launch_dependents();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     int slots[8]; bool mine[8]; int cnt = 0; bool focused = false;
@@ -241,24 +314,39 @@ __global__ void gather_kernel(MapDev m, int n, const float* __restrict__ p_hat, 
             const Grid& g = m.g;
             const int iz = c % g.nz, iy = (c / g.nz) % g.ny, ix = c / (g.nz * g.ny);
             // focus mask: primary cell in T U N6(T) (map.py:389-397).  A clamped neighbour of t collapses onto t itself, so
-            // membership is: P in T, or an in-bounds face neighbour of P is in T.
-            focused = target_slot(m, c) >= 0
-                || (ix > 0 && target_slot(m, c - g.nz * g.ny) >= 0) || (ix < g.nx - 1 && target_slot(m, c + g.nz * g.ny) >= 0)
-                || (iy > 0 && target_slot(m, c - g.nz) >= 0) || (iy < g.ny - 1 && target_slot(m, c + g.nz) >= 0)
-                || (iz > 0 && target_slot(m, c - 1) >= 0) || (iz < g.nz - 1 && target_slot(m, c + 1) >= 0);
+            // membership is: P in T, or an in-bounds face neighbour of P is in T.  All 7 (then all 8) two-level lookups are
+            // issued together: after an L2 flush every one of them is a DRAM round trip, a short-circuit chain serialises them.
+            const int sy = g.nz, sx = g.nz * g.ny;
+            const int nb[7] = {c, ix > 0 ? c - sx : -1, ix < g.nx - 1 ? c + sx : -1, iy > 0 ? c - sy : -1, iy < g.ny - 1 ? c + sy : -1,
+                               iz > 0 ? c - 1 : -1, iz < g.nz - 1 ? c + 1 : -1};
+            int64_t ns[7];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) ns[k] = nb[k] >= 0 ? m.indexer[nb[k]] : -1;
+            float no[7];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) no[k] = ns[k] >= 0 ? m.obs[ns[k]] : m.enc_th;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) focused |= no[k] < m.enc_th;
             if (focused) {
                 const float px = p_hat[3 * i], py = p_hat[3 * i + 1], pz = p_hat[3 * i + 2];
+                int tl[8]; int64_t ts[8]; float to[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {                 // offsets in the order of map.py:186-189
                     const float ox = (k & 4) ? 0.5f : -0.5f, oy = (k & 2) ? 0.5f : -0.5f, oz = (k & 1) ? 0.5f : -0.5f;
                     const int cx = clampi((int)ceilf(__fadd_rn(px, ox)) - 1, 0, g.nx - 1);
                     const int cy = clampi((int)ceilf(__fadd_rn(py, oy)) - 1, 0, g.ny - 1);
                     const int cz = clampi((int)ceilf(__fadd_rn(pz, oz)) - 1, 0, g.nz - 1);
-                    const int tl = lin_id(g, cx, cy, cz);
-                    const int s = target_slot(m, tl);
+                    tl[k] = lin_id(g, cx, cy, cz);
+                    ts[k] = m.indexer[tl[k]];
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) to[k] = ts[k] >= 0 ? m.obs[ts[k]] : m.enc_th;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int s = to[k] < m.enc_th ? (int)ts[k] : -1;        // T membership (target_slot)
                     slots[k] = s;
                     // sharded map: every rank counts the observation, only the owner of the PLIVox encodes it
-                    mine[k] = s >= 0 && (m.shard_world == 1 || shard_owner(tl, m.shard_world) == m.shard_rank);
+                    mine[k] = s >= 0 && (m.shard_world == 1 || shard_owner(tl[k], m.shard_world) == m.shard_rank);
                     cnt += mine[k];
                 }
             }
@@ -274,13 +362,14 @@ __global__ void gather_kernel(MapDev m, int n, const float* __restrict__ p_hat, 
     base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
     const unsigned fb = __ballot_sync(0xffffffffu, focused);
     if (lane == 0 && fb) atomicAdd(stats + DIF_STAT_N_FOCUSED, __popc(fb));
+    unsigned before[8];                                       // the 8 counter bumps are issued back to back (independent round trips)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) before[k] = slots[k] >= 0 ? atomicAdd(slot_cnt + slots[k], 1u) : 1u;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int s = slots[k];
-        if (s >= 0) {
-            if (mine[k]) { s_pt[base] = i; s_slot[base] = s; s_off[base] = (uint8_t)k; ++base; }
-            if (atomicAdd(slot_cnt + s, 1u) == 0u) touched[atomicAdd(ctr + CTR_N_TOUCHED, 1)] = s;
-        }
+        if (s >= 0 && mine[k]) { s_pt[base] = i; s_slot[base] = s; s_off[base] = (uint8_t)k; ++base; }
+        if (before[k] == 0u) touched[atomicAdd(ctr + CTR_N_TOUCHED, 1)] = s;
     }
 }
 
@@ -322,7 +411,7 @@ __global__ void __launch_bounds__(MLP_THREADS) encode_accumulate_kernel(
         for (int idx = threadIdx.x; idx < MLP_T * 32; idx += MLP_THREADS) {
             const int t = idx / 32, j = idx % 32;
             const int slot = tile_slot[t];
-            if (j < DIF_L && slot >= 0) atomicAdd(slot_sum + (int64_t)slot * DIF_L + j, s.out[j * MLP_TP + t]);
+            if (j < DIF_L && slot >= 0) atomicAdd(slot_sum + (int64_t)slot * DIF_SUM_STRIDE + j, s.out[j * MLP_TP + t]);
         }
         __syncthreads();
     }
@@ -332,6 +421,7 @@ __global__ void __launch_bounds__(MLP_THREADS) encode_accumulate_kernel(
 // latent <- (sum + latent*n)/(n+cnt);  n <- n+cnt  (map.py:449-451), one warp per touched PLIVox; cleans slot_sum/slot_cnt.
 __global__ void fuse_kernel(MapDev m, const int32_t* __restrict__ touched, const int32_t* __restrict__ ctr,
                             uint32_t* __restrict__ slot_cnt, float* __restrict__ slot_sum, int32_t* __restrict__ stats) {
+    pdl_wait(); pdl_launch_dependents();
     const int n_touched = ctr[CTR_N_TOUCHED];
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -343,12 +433,13 @@ __global__ void fuse_kernel(MapDev m, const int32_t* __restrict__ touched, const
         const float n_new = __fadd_rn(n_old, cnt);
         __syncwarp();
         const bool owned = m.shard_world == 1 || shard_owner(m.pos[slot], m.shard_world) == m.shard_rank;
+        const int64_t so = (int64_t)slot * DIF_SUM_STRIDE + lane;
         if (owned && lane < DIF_L) {
             const int64_t o = (int64_t)slot * DIF_L + lane;
-            const float sum = __fadd_rn(slot_sum[o], __fmul_rn(m.latent[o], n_old));
+            const float sum = __fadd_rn(slot_sum[so], __fmul_rn(m.latent[o], n_old));
             m.latent[o] = __fdiv_rn(sum, n_new);
-            slot_sum[o] = 0.f;
         }
+        if (owned) slot_sum[so] = 0.f;                                 // all 32 lanes: the padding columns are cleaned too
         __syncwarp();
         if (lane == 0) {
             m.obs[slot] = n_new; slot_cnt[slot] = 0u; if (m.dirty) m.dirty[slot] = 1;
@@ -456,17 +547,19 @@ int dif_integrate(const dif_map_view* map, const void* encoder_prepared, const f
     const int PT = 64;                                             // small blocks: a 30k-point frame must still fill 148 SMs
     const int nb = (int)((n + PT - 1) / PT);
     if (n > 0) {
-        voxelize_kernel<<<nb, PT, 0, st>>>(m, xyz, (int)n, S.p_hat, S.cell, P.cell_count, stats_dev, S.ctr);
-        prune_mark_kernel<<<nb, PT, 0, st>>>(m, (int)n, S.cell, P.cell_count, S.kept, unq_mask, P.bitmap, stats_dev);
+        launch_pdl(voxelize_kernel, nb, PT, 0, st, m, xyz, (int)n, S.p_hat, S.cell, P.cell_count, stats_dev, S.ctr);
+        launch_pdl(prune_mark_kernel, nb, PT, 0, st, m, (int)n, S.cell, P.cell_count, S.kept, unq_mask, P.bitmap, stats_dev);
         DIF_COUNT_LAUNCH(2);
     }
-    DIF_COUNT_LAUNCH(3);
-    bitmap_count_kernel<<<n_chunks, SCAN_THREADS, 0, st>>>(P.bitmap, n_words, S.chunk_sum);
-    bitmap_scan_kernel<<<1, 1024, 0, st>>>(S.chunk_sum, n_chunks, m.n_occ, m.capacity, S.ctr, stats_dev, 1);
-    alloc_assign_kernel<<<n_chunks, SCAN_THREADS, 0, st>>>(m, P.bitmap, n_words, S.chunk_sum, S.ctr);
+    DIF_COUNT_LAUNCH(1);
+    {
+        const int grid = n_chunks < ALLOC_GRID_MAX ? n_chunks : ALLOC_GRID_MAX;
+        const int per = (n_chunks + grid - 1) / grid;
+        launch_pdl(alloc_kernel, (n_chunks + per - 1) / per, SCAN_THREADS, 0, st, m, P.bitmap, n_words, n_chunks, per, P.alloc_sync, S.ctr, stats_dev);
+    }
     if (n > 0) {
-        gather_kernel<<<nb, PT, 0, st>>>(m, (int)n, S.p_hat, S.cell, S.kept, P.cell_count, P.slot_cnt, S.s_pt, S.s_slot, S.s_off,
-                                          S.touched, S.ctr, stats_dev);
+        launch_pdl(gather_kernel, nb, PT, 0, st, m, (int)n, S.p_hat, S.cell, S.kept, P.cell_count, P.slot_cnt, S.s_pt, S.s_slot, S.s_off,
+                   S.touched, S.ctr, stats_dev);
         const char* enc_env = getenv("DIF_ENCODE_PATH");                 // "simt" forces the exact-fp32 kernel (tests compare both)
         if (!(enc_env && enc_env[0] == 's') && n >= 256) {
             const int rc = launch_encode_accumulate_tc(encoder_prepared, m.g, S.p_hat, normal, S.s_pt, S.s_slot, S.s_off, S.ctr + CTR_N_SAMPLES,
@@ -484,7 +577,7 @@ int dif_integrate(const dif_map_view* map, const void* encoder_prepared, const f
             prof_end(DIF_PROF_ENCODE, st);
             DIF_COUNT_LAUNCH(3);
         }
-        fuse_kernel<<<DIF_NUM_SMS * 8, 256, 0, st>>>(m, S.touched, S.ctr, P.slot_cnt, P.slot_sum, stats_dev);
+        launch_pdl(fuse_kernel, DIF_NUM_SMS * 8, 256, 0, st, m, S.touched, S.ctr, P.slot_cnt, P.slot_sum, stats_dev);
     }
     return check_launch("dif_integrate");
 }
@@ -520,7 +613,7 @@ int dif_mesh_select(const dif_map_view* map, const int32_t* updated_slots, int64
     const int64_t k_max = updated_slots ? n_updated : m.capacity;
     if (k_max > 0) mesh_mark_kernel<<<(int)((k_max + 255) / 256), 256, 0, st>>>(m, updated_slots, n_updated, focused_ids_out, bitmap, counts_dev);
     bitmap_count_kernel<<<n_chunks, SCAN_THREADS, 0, st>>>(bitmap, n_words, chunk_sum);
-    bitmap_scan_kernel<<<1, 1024, 0, st>>>(chunk_sum, n_chunks, m.n_occ, m.capacity, ctr, counts_dev, 0);
+    bitmap_scan_kernel<<<1, 1024, 0, st>>>(chunk_sum, n_chunks, ctr);
     mesh_assign_kernel<<<n_chunks, SCAN_THREADS, 0, st>>>(m, bitmap, n_words, chunk_sum, ctr, block_slots_out, mapping_out, counts_dev);
     DIF_COUNT_LAUNCH(k_max > 0 ? 4 : 3);
     return check_launch("dif_mesh_select");

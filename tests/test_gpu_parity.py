@@ -325,7 +325,7 @@ def test_large_map_properties(model, dev):
     total = 0
     for f in range(6):
         # a 6 m x 6 m patch of the height field z = 1 + 0.4 sin(x) cos(0.7 y), ~30k points, patches overlap between frames
-        x0, y0 = 5.0 + 4.0 * f, 45.0 - 6.0 * f
+        x0, y0 = 5.0 + 4.0 * f, 43.0 - 6.0 * f
         xy = torch.rand(30_000, 2, generator=g) * 6.0 + torch.tensor([x0, y0])
         z = 1.0 + 0.4 * torch.sin(xy[:, 0]) * torch.cos(0.7 * xy[:, 1])
         pts = torch.cat([xy, z[:, None]], 1).float().to(dev)
@@ -341,6 +341,7 @@ def test_large_map_properties(model, dev):
         keep = cnt[inv] > 2
         assert torch.equal(mask, keep)
         kept = ijk[keep]
+        kept = kept[~occupied[lin[keep]]]                                 # E0: EMPTY cells hit by a kept point (map.py:380-383)
         nb = torch.tensor([[0, 0, 0], [1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], device=dev)
         cand = (kept[:, None, :] + nb[None]).reshape(-1, 3)
         hi = torch.tensor([999, 999, 39], device=dev)
