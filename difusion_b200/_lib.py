@@ -5,10 +5,11 @@ The product path has NO CPU fallback: if the CUDA library is missing or fails to
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libdifusion_b200.so"
+LIB_PATH = Path(os.environ["DIF_LIB_PATH"]) if os.environ.get("DIF_LIB_PATH") else _HERE / "libdifusion_b200.so"   # override: kernel A/B builds (tools/)
 
 DIF_STAT_COUNT = 8
 STAT_N_KEPT, STAT_N_NEW, STAT_N_SAMPLES, STAT_N_UPDATED, STAT_N_OCCUPIED, STAT_FLAGS, STAT_N_FOCUSED, STAT_N_XCHG = range(8)

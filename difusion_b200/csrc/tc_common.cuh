@@ -58,8 +58,30 @@ __device__ __forceinline__ void mbar_wait_ns(uint32_t bar, uint32_t parity) {
                  "@!p bra RETRY;\n\t"
                  "DONE:\n\t}\n" :: "r"(bar), "r"(parity), "n"(SLEEP_NS) : "memory");
 }
+// Alternative: let the hardware suspend the thread on the barrier (try_wait with a suspend-time hint): no polling at all and
+// the wake-up comes with the phase flip.
+__device__ __forceinline__ void mbar_wait_suspend(uint32_t bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "WAIT:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+                 "@!p bra WAIT;\n\t}\n" :: "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+}
+#ifndef DIF_WAIT_MODE
+#define DIF_WAIT_MODE 0
+#endif
+#if DIF_WAIT_MODE == 0
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { mbar_wait_ns<96>(bar, parity); }
 __device__ __forceinline__ void mbar_wait_tight(uint32_t bar, uint32_t parity) { mbar_wait_ns<20>(bar, parity); }   // MMA issuer
+#elif DIF_WAIT_MODE == 1
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { mbar_wait_ns<32>(bar, parity); }
+__device__ __forceinline__ void mbar_wait_tight(uint32_t bar, uint32_t parity) { mbar_wait_ns<20>(bar, parity); }
+#elif DIF_WAIT_MODE == 2
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { mbar_wait_suspend(bar, parity); }
+__device__ __forceinline__ void mbar_wait_tight(uint32_t bar, uint32_t parity) { mbar_wait_suspend(bar, parity); }
+#else
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { mbar_wait_suspend(bar, parity); }
+__device__ __forceinline__ void mbar_wait_tight(uint32_t bar, uint32_t parity) { mbar_wait_ns<20>(bar, parity); }
+#endif
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");

@@ -88,11 +88,6 @@ __global__ void voxelize_kernel(MapDev m, const float* __restrict__ xyz, int n, 
 }
 
 // ------------------------------------------------------------------------------------------------ K2 prune + mark new cells
-__device__ __forceinline__ void mark_if_empty(const MapDev& m, uint32_t* bitmap, int ix, int iy, int iz) {
-    const int c = lin_id(m.g, clampi(ix, 0, m.g.nx - 1), clampi(iy, 0, m.g.ny - 1), clampi(iz, 0, m.g.nz - 1));
-    if (m.indexer[c] == -1) atomicOr(bitmap + (c >> 5), 1u << (c & 31));
-}
-
 __global__ void prune_mark_kernel(MapDev m, int n, const int32_t* __restrict__ cell, const uint32_t* __restrict__ cell_count,
                                   uint8_t* __restrict__ kept, uint8_t* __restrict__ unq_mask, uint32_t* __restrict__ bitmap,
                                   int32_t* __restrict__ stats) {
@@ -101,17 +96,29 @@ __global__ void prune_mark_kernel(MapDev m, int n, const int32_t* __restrict__ c
     bool k = false;
     if (i < n) {
         const int c = cell[i];
-        k = c >= 0 && (m.prune <= 0 || cell_count[c] > (uint32_t)m.prune);      // strict '>' (map.py:375)
+        if (c >= 0) {
+            // E = (E0 U N6(E0)) restricted to empty cells, neighbours clamped to the grid (map.py:385-386, :545-557).
+            // The histogram read and the 7 index lookups are issued together: after an L2 flush each is a DRAM round trip.
+            const Grid& g = m.g;
+            const int iz = c % g.nz, iy = (c / g.nz) % g.ny, ix = c / (g.nz * g.ny);
+            int nb[7];
+            nb[0] = c;
+            nb[1] = lin_id(g, clampi(ix - 1, 0, g.nx - 1), iy, iz); nb[2] = lin_id(g, clampi(ix + 1, 0, g.nx - 1), iy, iz);
+            nb[3] = lin_id(g, ix, clampi(iy - 1, 0, g.ny - 1), iz); nb[4] = lin_id(g, ix, clampi(iy + 1, 0, g.ny - 1), iz);
+            nb[5] = lin_id(g, ix, iy, clampi(iz - 1, 0, g.nz - 1)); nb[6] = lin_id(g, ix, iy, clampi(iz + 1, 0, g.nz - 1));
+            const uint32_t cnt = m.prune > 0 ? cell_count[c] : 0u;
+            int64_t s7[7];
+#pragma unroll
+            for (int q = 0; q < 7; ++q) s7[q] = m.indexer[nb[q]];
+            k = m.prune <= 0 || cnt > (uint32_t)m.prune;                         // strict '>' (map.py:375)
+            if (k && s7[0] == -1) {
+#pragma unroll
+                for (int q = 0; q < 7; ++q)
+                    if (s7[q] == -1) atomicOr(bitmap + (nb[q] >> 5), 1u << (nb[q] & 31));
+            }
+        }
         kept[i] = k;
         if (unq_mask) unq_mask[i] = k;
-        if (k && m.indexer[c] == -1) {
-            // E = (E0 U N6(E0)) restricted to empty cells, neighbours clamped to the grid (map.py:385-386, :545-557)
-            const int iz = c % m.g.nz, iy = (c / m.g.nz) % m.g.ny, ix = c / (m.g.nz * m.g.ny);
-            atomicOr(bitmap + (c >> 5), 1u << (c & 31));
-            mark_if_empty(m, bitmap, ix - 1, iy, iz); mark_if_empty(m, bitmap, ix + 1, iy, iz);
-            mark_if_empty(m, bitmap, ix, iy - 1, iz); mark_if_empty(m, bitmap, ix, iy + 1, iz);
-            mark_if_empty(m, bitmap, ix, iy, iz - 1); mark_if_empty(m, bitmap, ix, iy, iz + 1);
-        }
     }
     const unsigned b = __ballot_sync(0xffffffffu, k);
     if ((threadIdx.x & 31) == 0 && b) atomicAdd(stats + DIF_STAT_N_KEPT, __popc(b));
@@ -314,33 +321,34 @@ __global__ void gather_kernel(MapDev m, int n, const float* __restrict__ p_hat, 
             const Grid& g = m.g;
             const int iz = c % g.nz, iy = (c / g.nz) % g.ny, ix = c / (g.nz * g.ny);
             // focus mask: primary cell in T U N6(T) (map.py:389-397).  A clamped neighbour of t collapses onto t itself, so
-            // membership is: P in T, or an in-bounds face neighbour of P is in T.  All 7 (then all 8) two-level lookups are
+            // membership is: P in T, or an in-bounds face neighbour of P is in T.  All 7 + 8 two-level lookups are
             // issued together: after an L2 flush every one of them is a DRAM round trip, a short-circuit chain serialises them.
             const int sy = g.nz, sx = g.nz * g.ny;
             const int nb[7] = {c, ix > 0 ? c - sx : -1, ix < g.nx - 1 ? c + sx : -1, iy > 0 ? c - sy : -1, iy < g.ny - 1 ? c + sy : -1,
                                iz > 0 ? c - 1 : -1, iz < g.nz - 1 ? c + 1 : -1};
-            int64_t ns[7];
+            const float px = p_hat[3 * i], py = p_hat[3 * i + 1], pz = p_hat[3 * i + 2];
+            int tl[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {                     // offsets in the order of map.py:186-189
+                const float ox = (k & 4) ? 0.5f : -0.5f, oy = (k & 2) ? 0.5f : -0.5f, oz = (k & 1) ? 0.5f : -0.5f;
+                const int cx = clampi((int)ceilf(__fadd_rn(px, ox)) - 1, 0, g.nx - 1);
+                const int cy = clampi((int)ceilf(__fadd_rn(py, oy)) - 1, 0, g.ny - 1);
+                const int cz = clampi((int)ceilf(__fadd_rn(pz, oz)) - 1, 0, g.nz - 1);
+                tl[k] = lin_id(g, cx, cy, cz);
+            }
+            int64_t ns[7], ts[8];
 #pragma unroll
             for (int k = 0; k < 7; ++k) ns[k] = nb[k] >= 0 ? m.indexer[nb[k]] : -1;
-            float no[7];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) ts[k] = m.indexer[tl[k]];
+            float no[7], to[8];
 #pragma unroll
             for (int k = 0; k < 7; ++k) no[k] = ns[k] >= 0 ? m.obs[ns[k]] : m.enc_th;
 #pragma unroll
+            for (int k = 0; k < 8; ++k) to[k] = ts[k] >= 0 ? m.obs[ts[k]] : m.enc_th;
+#pragma unroll
             for (int k = 0; k < 7; ++k) focused |= no[k] < m.enc_th;
             if (focused) {
-                const float px = p_hat[3 * i], py = p_hat[3 * i + 1], pz = p_hat[3 * i + 2];
-                int tl[8]; int64_t ts[8]; float to[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {                 // offsets in the order of map.py:186-189
-                    const float ox = (k & 4) ? 0.5f : -0.5f, oy = (k & 2) ? 0.5f : -0.5f, oz = (k & 1) ? 0.5f : -0.5f;
-                    const int cx = clampi((int)ceilf(__fadd_rn(px, ox)) - 1, 0, g.nx - 1);
-                    const int cy = clampi((int)ceilf(__fadd_rn(py, oy)) - 1, 0, g.ny - 1);
-                    const int cz = clampi((int)ceilf(__fadd_rn(pz, oz)) - 1, 0, g.nz - 1);
-                    tl[k] = lin_id(g, cx, cy, cz);
-                    ts[k] = m.indexer[tl[k]];
-                }
-#pragma unroll
-                for (int k = 0; k < 8; ++k) to[k] = ts[k] >= 0 ? m.obs[ts[k]] : m.enc_th;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const int s = to[k] < m.enc_th ? (int)ts[k] : -1;        // T membership (target_slot)
@@ -352,7 +360,11 @@ __global__ void gather_kernel(MapDev m, int n, const float* __restrict__ p_hat, 
             }
         }
     }
-    // warp-aggregated reservation in the sample list
+    // per-PLIVox observation counters first (they do not need the list position), then the warp-aggregated reservation in
+    // the sample list: both atomic round trips are in flight together
+    unsigned before[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) before[k] = slots[k] >= 0 ? atomicAdd(slot_cnt + slots[k], 1u) : 1u;
     int incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
@@ -362,9 +374,6 @@ __global__ void gather_kernel(MapDev m, int n, const float* __restrict__ p_hat, 
     base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
     const unsigned fb = __ballot_sync(0xffffffffu, focused);
     if (lane == 0 && fb) atomicAdd(stats + DIF_STAT_N_FOCUSED, __popc(fb));
-    unsigned before[8];                                       // the 8 counter bumps are issued back to back (independent round trips)
-#pragma unroll
-    for (int k = 0; k < 8; ++k) before[k] = slots[k] >= 0 ? atomicAdd(slot_cnt + slots[k], 1u) : 1u;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int s = slots[k];
