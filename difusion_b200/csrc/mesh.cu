@@ -73,8 +73,9 @@ __global__ void write_counts_kernel(int32_t* counts, int32_t n_low, const int32_
 // One CTA per focused PLIVox.  Stage 1: the 27 neighbour batch indices.  Stage 2: the (r+1)^3 blended corner values
 // (each computed once instead of up to 8x as in the reference's per-sub-cube threads).  Stage 3: one thread per
 // sub-cube: case lookup, edge vertices, block-scan of triangle counts, ONE atomicAdd per CTA to reserve output, emit.
-// All sign-deciding float arithmetic uses explicit round-to-nearest ops in the reference's order (no FMA contraction),
-// so the case index is bit-identical to the scalar restatement in oracle/mc_oracle.c.
+// Float arithmetic is written with explicit round-to-nearest intrinsics and explicit fmaf in exactly the places where nvcc
+// (-fmad=true) contracts the reference source (read off the reference's PTX; see oracle/mc_oracle.c header), so case indices
+// and vertices are bit-identical to the reference extension and to the scalar restatement in oracle/mc_oracle.c.
 constexpr int MC_THREADS = 128;
 constexpr int MC_MAX_R = 8;
 
@@ -102,7 +103,7 @@ __device__ __forceinline__ float2 blended_corner(const McArgs& a, const int* nb 
         w_m[k] = __fdiv_rn(w_m[k], rf); w_p[k] = __fdiv_rn(w_p[k], rf);
     }
     const int own = own_is_p[0] * 4 + own_is_p[1] * 2 + own_is_p[2];
-    float s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
+    float s1 = 0.f, s2 = 0.f, s4 = 0.f;
     const float qnan = __int_as_float(0x7fc00000);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -116,15 +117,14 @@ __device__ __forceinline__ float2 blended_corner(const McArgs& a, const int* nb 
         }
         const float w = __fmul_rn(__fmul_rn(xp ? w_p[0] : w_m[0], yp ? w_p[1] : w_m[1]), zp ? w_p[2] : w_m[2]);
         if (sdf == sdf) {
-            s1 = __fadd_rn(s1, __fmul_rn(__fmul_rn(sdf, w), sd));
-            const float ws = __fmul_rn(w, sd);
-            s2 = __fadd_rn(s2, ws); s3 = __fadd_rn(s3, ws);
+            s1 = __fmaf_rn(__fmul_rn(sdf, w), sd, s1);
+            s2 = __fmaf_rn(w, sd, s2);
             s4 = __fadd_rn(s4, w);
         } else if (own == k) {
             return make_float2(qnan, qnan);
         }
     }
-    return make_float2(__fdiv_rn(s1, s2), __fdiv_rn(s3, s4));
+    return make_float2(__fdiv_rn(s1, s2), __fdiv_rn(s2, s4));
 }
 
 __device__ __forceinline__ float4 edge_vertex(float3 p1, float3 p2, float std1, float std2, float v1, float v2) {
@@ -133,8 +133,8 @@ __device__ __forceinline__ float4 edge_vertex(float3 p1, float3 p2, float std1, 
     if (fabsf(__fsub_rn(v1, v2)) < 1.0e-5f) return make_float4(p1.x, p1.y, p1.z, std1);
     const float w2 = __fdiv_rn(__fsub_rn(0.0f, v1), __fsub_rn(v2, v1));
     const float w1 = __fsub_rn(1.f, w2);
-    return make_float4(__fadd_rn(__fmul_rn(p1.x, w1), __fmul_rn(p2.x, w2)), __fadd_rn(__fmul_rn(p1.y, w1), __fmul_rn(p2.y, w2)),
-                       __fadd_rn(__fmul_rn(p1.z, w1), __fmul_rn(p2.z, w2)), __fadd_rn(__fmul_rn(std1, w1), __fmul_rn(std2, w2)));
+    return make_float4(__fmaf_rn(p2.x, w2, __fmul_rn(p1.x, w1)), __fmaf_rn(p2.y, w2, __fmul_rn(p1.y, w1)),
+                       __fmaf_rn(p2.z, w2, __fmul_rn(p1.z, w1)), __fmaf_rn(std2, w2, __fmul_rn(std1, w1)));
 }
 
 __global__ void __launch_bounds__(MC_THREADS) marching_cubes_kernel(McArgs a) {
@@ -188,12 +188,12 @@ __global__ void __launch_bounds__(MC_THREADS) marching_cubes_kernel(McArgs a) {
                     for (int e = 0; e < 12; ++e) {
                         if (emask & (1 << e)) {
                             const int p = e_a[e], q = e_b[e];
-                            const float3 p1 = make_float3(__fadd_rn((float)bx, __fmul_rn((float)(rx + dx8[p]), sbs)),
-                                                          __fadd_rn((float)by, __fmul_rn((float)(ry + dy8[p]), sbs)),
-                                                          __fadd_rn((float)bz, __fmul_rn((float)(rz + dz8[p]), sbs)));
-                            const float3 p2 = make_float3(__fadd_rn((float)bx, __fmul_rn((float)(rx + dx8[q]), sbs)),
-                                                          __fadd_rn((float)by, __fmul_rn((float)(ry + dy8[q]), sbs)),
-                                                          __fadd_rn((float)bz, __fmul_rn((float)(rz + dz8[q]), sbs)));
+                            const float3 p1 = make_float3(__fmaf_rn((float)(rx + dx8[p]), sbs, (float)bx),
+                                                          __fmaf_rn((float)(ry + dy8[p]), sbs, (float)by),
+                                                          __fmaf_rn((float)(rz + dz8[p]), sbs, (float)bz));
+                            const float3 p2 = make_float3(__fmaf_rn((float)(rx + dx8[q]), sbs, (float)bx),
+                                                          __fmaf_rn((float)(ry + dy8[q]), sbs, (float)by),
+                                                          __fmaf_rn((float)(rz + dz8[q]), sbs, (float)bz));
                             vert[e] = edge_vertex(p1, p2, sd[p], sd[q], v[p], v[q]);
                         }
                     }

@@ -9,13 +9,20 @@
  *       host wrapper   :322-382  -> count semantics (triangles past max_tri are counted, not written)
  *   tables: include/dif_mc_tables.h (values == mc_data.cuh:40,54)
  *
- * Parity status: the reference kernel is CUDA-only and cannot execute in the build container, and the
- * reference ships no test vectors => this restatement is NOT pinned against an execution of the
- * reference ("parity unpinned" for the MC stage).  It is pinned only by construction
- * (line-by-line semantics above) and by analytic tests (tests/test_oracle_mc.py).
+ * Parity status: PINNED against executions of the unmodified reference kernel.  oracle/build_ref.py compiles
+ * the reference extension from /root/reference into oracle/_ref/marching_cubes/, tests/golden/make_golden_gpu.py
+ * runs it on a B200 and stores inputs + outputs in tests/golden/ref_ext_mc_r*.npz; tests/test_oracle_mc.py checks
+ * this restatement against those vectors BIT-EXACTLY, and tests/test_ref_ext_gpu.py compares the product kernel with
+ * the reference module live on the GPU.
  *
- * Built with -ffp-contract=off: every float op below is a separately rounded IEEE fp32 op, which is what
- * the CUDA product kernel reproduces with explicit __fmul_rn/__fadd_rn/__fdiv_rn.
+ * Rounding: built with -ffp-contract=off; every float op is a separately rounded IEEE fp32 op EXCEPT where nvcc
+ * (default -fmad=true) contracts the reference source into a fused multiply-add.  Those places were read off the
+ * PTX/SASS nvcc 12.9 emits for the reference file and are written as explicit fmaf() here (and as fmaf in the
+ * product kernel):   total_sdf.x += (sdf*w)*std  -> fma(sdf*w, std, acc)      (:109, :118, ... one per corner)
+ *                    total_weight.x / total_sdf.y += w*std -> fma(w, std, acc) (one register: the compiler merges both)
+ *                    total_weight.y += w        -> plain add
+ *                    points[i] = bpos + rpos*sbs -> fma(rpos, sbs, bpos)       (:224-252)
+ *                    p1*w1 + p2*w2              -> fma(p2, w2, p1*w1)          (:195-198)
  * Only tests/, bench.py's cpu_baseline leg and __graft_entry__.smoke() may load this.
  */
 #include <math.h>
@@ -71,7 +78,7 @@ static sv_t blended_corner(const mc_ctx* c, uint32_t bx, uint32_t by, uint32_t b
     }
     const int own = own_is_p[0] * 4 + own_is_p[1] * 2 + own_is_p[2];
 
-    float s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
+    float s1 = 0.f, s2 = 0.f, s4 = 0.f;
     for (int k = 0; k < 8; ++k) {                         /* order mmm, mmp, mpm, mpp, pmm, pmp, ppm, ppp */
         const int xp = (k >> 2) & 1, yp = (k >> 1) & 1, zp = k & 1;
         sv_t q = raw_lookup(c,
@@ -80,15 +87,16 @@ static sv_t blended_corner(const mc_ctx* c, uint32_t bx, uint32_t by, uint32_t b
         float w = (xp ? w_p[0] : w_m[0]) * (yp ? w_p[1] : w_m[1]);
         w = w * (zp ? w_p[2] : w_m[2]);
         if (!isnan(q.sdf)) {
-            float t = q.sdf * w; t = t * q.std;  s1 += t;
-            float ws = w * q.std;                s2 += ws;  s3 += ws;
-            s4 += w;
+            const float t = q.sdf * w;
+            s1 = fmaf(t, q.std, s1);                       /* total_sdf.x */
+            s2 = fmaf(w, q.std, s2);                       /* total_weight.x == total_sdf.y */
+            s4 += w;                                       /* total_weight.y */
         } else if (own == k) {
             sv_t miss = { NAN, NAN };
             return miss;
         }
     }
-    sv_t out = { s1 / s2, s3 / s4 };
+    sv_t out = { s1 / s2, s2 / s4 };
     return out;
 }
 
@@ -103,11 +111,10 @@ static v4 edge_vertex(const float* p1, const float* p2, float std1, float std2, 
     float w2 = (0.0f - v1) / (v2 - v1);
     float w1 = 1 - w2;
     v4 o;
-    float t;
-    t = p1[0] * w1; o.x = t + p2[0] * w2;
-    t = p1[1] * w1; o.y = t + p2[1] * w2;
-    t = p1[2] * w1; o.z = t + p2[2] * w2;
-    t = std1 * w1;  o.w = t + std2 * w2;
+    o.x = fmaf(p2[0], w2, p1[0] * w1);
+    o.y = fmaf(p2[1], w2, p1[1] * w1);
+    o.z = fmaf(p2[2], w2, p1[2] * w1);
+    o.w = fmaf(std2, w2, std1 * w1);
     return o;
 }
 
@@ -133,7 +140,7 @@ int64_t dif_oracle_marching_cubes(const int64_t* indexer, const int64_t* valid_b
                 const uint32_t cx = rx + CORNER[i][0], cy = ry + CORNER[i][1], cz = rz + CORNER[i][2];
                 val[i] = blended_corner(&c, bx, by, bz, cx, cy, cz);
                 if (isnan(val[i].sdf)) { bad = 1; break; }
-                pt[i][0] = (float)bx + (float)cx * sbs; pt[i][1] = (float)by + (float)cy * sbs; pt[i][2] = (float)bz + (float)cz * sbs;
+                pt[i][0] = fmaf((float)cx, sbs, (float)bx); pt[i][1] = fmaf((float)cy, sbs, (float)by); pt[i][2] = fmaf((float)cz, sbs, (float)bz);
             }
             if (bad) continue;
             int type = 0;

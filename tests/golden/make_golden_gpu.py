@@ -1,0 +1,76 @@
+"""Generates tests/golden/ref_ext_*.npz on a GPU box by EXECUTING THE UNMODIFIED REFERENCE CUDA EXTENSIONS
+(oracle/_ref/<name>/<name>.so, built from /root/reference by oracle/build_ref.py) on seeded inputs.
+
+    gpurun -- 'python tests/golden/make_golden_gpu.py gpurun_out/golden'      (then copy the .npz files to tests/golden/)
+
+Fixtures (inputs AND reference outputs are stored, so the CPU tests need neither a GPU nor the reference):
+  ref_ext_mc_r{2,4,5}.npz  marching_cubes_sparse_interp (ext/marching_cubes/mc_interp_kernel.cu) on analytic sphere cubes with a missing
+                           PLIVox, PLIVoxes left out of the batch, noisy std; outputs for max_std = 10 and 0.15, canonically sorted
+  ref_ext_groupby.npz      groupby_sum (ext/indexing/indexing.cu:59-109)
+The reference ships no vectors of its own, so these executions are the pin for the two CUDA-only ops.
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+
+def mc_case(r: int, seed: int = 0):
+    """Deterministic MC input: sphere SDF lattice cubes over a small grid (shared with tests/test_oracle_mc.py)."""
+    from test_oracle_mc import _sphere_cubes
+    n_xyz = [6, 5, 7] if r < 5 else [5, 4, 5]
+    c = (np.asarray(n_xyz) / 2.0).tolist()
+    indexer, mapping, sdf, std = _sphere_cubes(n_xyz, r, c, 1.9 if r < 5 else 1.6, drop=(2, 2, 3))
+    rng = np.random.default_rng(seed)
+    std = (std + rng.uniform(0, 0.1, std.shape)).astype(np.float32)
+    sdf = (sdf + rng.normal(0, 0.01, sdf.shape)).astype(np.float32)            # neighbouring cubes disagree, like decoder output
+    B = sdf.shape[0]
+    keep = rng.permutation(B)[: int(B * 0.9)]
+    mapping = np.full(B, -1, np.int32)
+    mapping[keep] = np.arange(len(keep), dtype=np.int32)
+    sdf, std = np.ascontiguousarray(sdf[keep]), np.ascontiguousarray(std[keep])
+    blocks = np.sort(rng.choice(B, int(B * 0.8), replace=False)).astype(np.int64)
+    blocks = blocks[indexer.reshape(-1)[blocks] != -1]
+    return dict(n_xyz=np.asarray(n_xyz), indexer=indexer, blocks=blocks, mapping=mapping, cube_sdf=sdf, cube_std=std)
+
+
+def canon(tri, fid, std):
+    """Canonical order: by PLIVox id, then by the 9 vertex coordinates (exact floats)."""
+    key = np.concatenate([fid[:, None].astype(np.float64), tri.reshape(len(tri), 9).astype(np.float64)], 1)
+    order = np.lexsort(key.T[::-1])
+    return tri[order], fid[order], std[order]
+
+
+def main():
+    out = Path(sys.argv[1] if len(sys.argv) > 1 else ROOT / "gpurun_out" / "golden")
+    out.mkdir(parents=True, exist_ok=True)
+    from oracle import build_ref
+    dev = torch.device("cuda:0")
+    mc = build_ref.load_module("marching_cubes")
+    ix = build_ref.load_module("indexing")
+    for r in (2, 4, 5):
+        c = mc_case(r)
+        t = {k: torch.from_numpy(v).to(dev) for k, v in c.items() if k != "n_xyz"}
+        res = {}
+        for tag, max_std in (("all", 10.0), ("flt", 0.15)):
+            tri, fid, std = mc.marching_cubes_sparse_interp(t["indexer"], t["blocks"], t["mapping"], t["cube_sdf"], t["cube_std"], 1 << 20,
+                                                            c["n_xyz"].tolist(), max_std)
+            tri, fid, std = canon(tri.cpu().numpy(), fid.cpu().numpy(), std.cpu().numpy())
+            res.update({f"{tag}.tri": tri, f"{tag}.fid": fid, f"{tag}.std": std, f"{tag}.max_std": np.float32(max_std)})
+            print(f"mc r={r} max_std={max_std}: {tri.shape[0]} triangles")
+        np.savez_compressed(out / f"ref_ext_mc_r{r}.npz", r=r, **c, **res)
+    g = torch.Generator().manual_seed(0)
+    v = torch.randn(5000, 29, generator=g)
+    idx = torch.randint(0, 37, (5000,), generator=g)
+    s, cnt = ix.groupby_sum(v.to(dev), idx.to(dev), 40)
+    np.savez_compressed(out / "ref_ext_groupby.npz", values=v.numpy(), indices=idx.numpy(), C=40, sum=s.cpu().numpy(), count=cnt.cpu().numpy())
+    print("groupby_sum:", s.shape, cnt.dtype, int(cnt.sum()))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,6 +1,10 @@
-"""CPU: analytic checks of the C marching-cubes restatement (oracle/mc_oracle.c).  The reference MC kernel is
-CUDA-only, so this stage of the oracle is pinned by construction and by these properties only."""
+"""CPU: the C marching-cubes restatement (oracle/mc_oracle.c) against (1) golden vectors produced by EXECUTING the unmodified
+reference CUDA kernel on a B200 (tests/golden/ref_ext_mc_r*.npz, generator tests/golden/make_golden_gpu.py) - bit-exact - and
+(2) analytic properties."""
 import numpy as np
+import pytest
+
+from conftest import GOLDEN
 
 from oracle import mc_oracle
 
@@ -74,3 +78,32 @@ def test_r5_grid():
     tri, _, _ = mc_oracle.marching_cubes_interp(indexer, np.arange(64, dtype=np.int64), mapping, sdf, std, 1 << 20, n_xyz, 10.0)
     rad = np.linalg.norm(tri.reshape(-1, 3) - 2.0, axis=1)
     assert tri.shape[0] > 500 and np.abs(rad - 1.3).max() < 0.02
+
+
+def _canon(tri, fid, std):
+    key = np.concatenate([fid[:, None].astype(np.float64), tri.reshape(len(tri), 9).astype(np.float64)], 1)
+    order = np.lexsort(key.T[::-1])
+    return tri[order], fid[order], std[order]
+
+
+@pytest.mark.parametrize("r", [2, 4, 5])
+def test_restatement_is_bit_exact_against_the_executed_reference_kernel(r):
+    fx = np.load(GOLDEN / f"ref_ext_mc_r{r}.npz")
+    for tag in ("all", "flt"):
+        tri, fid, std = mc_oracle.marching_cubes_interp(fx["indexer"], fx["blocks"], fx["mapping"], fx["cube_sdf"], fx["cube_std"], 1 << 20,
+                                                        fx["n_xyz"].tolist(), float(fx[f"{tag}.max_std"]))
+        tri, fid, std = _canon(tri, fid, std)
+        assert tri.shape == fx[f"{tag}.tri"].shape and tri.shape[0] > 50
+        assert np.array_equal(fid, fx[f"{tag}.fid"])
+        assert np.array_equal(tri.view(np.uint32), fx[f"{tag}.tri"].view(np.uint32))
+        assert np.array_equal(std.view(np.uint32), fx[f"{tag}.std"].view(np.uint32))
+
+
+def test_groupby_restatement_against_the_executed_reference_kernel():
+    """ext/indexing/indexing.cu:59-109 executed on a B200 vs the oracle's index_add_ restatement (count = L per member row)."""
+    import torch
+    fx = np.load(GOLDEN / "ref_ext_groupby.npz")
+    v, idx, C = torch.from_numpy(fx["values"]), torch.from_numpy(fx["indices"]), int(fx["C"])
+    s = torch.zeros(C, v.size(1)).index_add_(0, idx, v).numpy()
+    assert np.all(np.abs(s - fx["sum"]) <= 1e-4 + 1e-4 * np.abs(fx["sum"]))
+    assert np.array_equal(fx["count"], v.size(1) * np.bincount(fx["indices"], minlength=C))
