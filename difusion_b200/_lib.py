@@ -54,6 +54,8 @@ SIGNATURES = {
     "dif_mesh_decode": (C.c_int, [_MV, _P, _P, _I64, C.c_int, C.c_int, _P, _P, _P, _SZ, _P, _P]),
     "dif_marching_cubes": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _I64, _P, _I64, _P, _P, C.c_int, _F, _P, _P, _P, _I64, _P, _P]),
     "dif_groupby_sum": (C.c_int, [_P, _P, _I64, _I32, _I64, _P, _P, _P]),
+    "dif_mesh_cache_scratch_bytes": (_SZ, [_I64, _I64]),
+    "dif_mesh_cache_merge": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _I64, _F, C.POINTER(C.c_float), _I64, _P, _P, _P, _P, _P, _SZ, _P]),
 }
 
 _lib = None

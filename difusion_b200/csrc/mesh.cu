@@ -14,118 +14,109 @@ int launch_decode_lattice(const float* P, const float* latent, const int32_t* bl
 // ------------------------------------------------------------------------------------------------ trilinear x2 + select
 // torch.nn.functional.interpolate(mode='trilinear', align_corners=True), l^3 -> (2l)^3 per PLIVox (map.py:658-665), then the
 // |sdf| < 0.05 test (:667).  Writes the NEGATED sdf (:687) and std into the cubes and appends the global lattice index of
-// every selected sample to `list` (warp-aggregated).
-__global__ void upsample_select_kernel(const float* __restrict__ low_sdf, const float* __restrict__ low_std, int64_t n_blocks, int l,
-                                       float* __restrict__ cube_sdf, float* __restrict__ cube_std, uint32_t* __restrict__ list,
-                                       int32_t* __restrict__ n_sel) {
-    const int h = 2 * l, h3 = h * h * h, l3 = l * l * l;
-    const int64_t total = n_blocks * h3;
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool sel = false;
-    if (g < total) {
-        const int64_t b = g / h3; const int i = (int)(g % h3);
-        const int X = i / (h * h), Y = (i / h) % h, Z = i % h;
-        const float scale = (float)(l - 1) / (float)(h - 1);                  // area_pixel_compute_scale, align_corners
-        int i0[3], i1[3]; float w0[3], w1[3];
-        const int D[3] = {X, Y, Z};
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const float src = __fmul_rn(scale, (float)D[a]);
-            i0[a] = (int)src; i1[a] = i0[a] + (i0[a] < l - 1 ? 1 : 0);
-            w1[a] = __fsub_rn(src, (float)i0[a]); w0[a] = __fsub_rn(1.f, w1[a]);
-        }
-        const float* ps = low_sdf + b * l3; const float* pd = low_std + b * l3;
-        float out[2];
-#pragma unroll
-        for (int which = 0; which < 2; ++which) {
-            const float* p = which ? pd : ps;
-            float acc_d[2];
-#pragma unroll
-            for (int dx = 0; dx < 2; ++dx) {
-                const int xo = (dx ? i1[0] : i0[0]) * l * l;
-                float acc_h[2];
-#pragma unroll
-                for (int dy = 0; dy < 2; ++dy) {
-                    const int yo = xo + (dy ? i1[1] : i0[1]) * l;
-                    acc_h[dy] = __fadd_rn(__fmul_rn(w0[2], p[yo + i0[2]]), __fmul_rn(w1[2], p[yo + i1[2]]));
-                }
-                acc_d[dx] = __fadd_rn(__fmul_rn(w0[1], acc_h[0]), __fmul_rn(w1[1], acc_h[1]));
-            }
-            out[which] = __fadd_rn(__fmul_rn(w0[0], acc_d[0]), __fmul_rn(w1[0], acc_d[1]));
-        }
-        cube_sdf[g] = -out[0];
-        cube_std[g] = out[1];
-        sel = fabsf(out[0]) < 0.05f;
+// every selected sample to `list`.
+// One CTA per PLIVox (grid-stride): the low cube is staged in shared memory with coalesced loads, the per-axis source index /
+// weight tables (2l entries) are computed once per CTA, outputs are written as contiguous float streams, and the selected
+// indices are collected in shared memory so that the global cursor sees ONE atomicAdd per PLIVox.
+constexpr int UP_THREADS = 256;
+
+template <int L>
+__global__ void __launch_bounds__(UP_THREADS) upsample_select_kernel(const float* __restrict__ low_sdf, const float* __restrict__ low_std,
+                                                                     int64_t n_blocks, float* __restrict__ cube_sdf, float* __restrict__ cube_std,
+                                                                     uint32_t* __restrict__ list, int32_t* __restrict__ n_sel) {
+    constexpr int H = 2 * L, H3 = H * H * H, L3 = L * L * L;
+    __shared__ float s_sdf[L3], s_std[L3];
+    __shared__ int t_i0[H], t_i1[H];
+    __shared__ float t_w0[H], t_w1[H];
+    __shared__ float z_sdf[L * L * H], z_std[L * L * H], y_sdf[L * H * H], y_std[L * H * H];
+    __shared__ uint16_t s_list[H3];
+    __shared__ int s_n, s_base;
+    const int tid = threadIdx.x;
+    if (tid < H) {
+        const float scale = (float)(L - 1) / (float)(H - 1);                  // area_pixel_compute_scale, align_corners
+        const float src = __fmul_rn(scale, (float)tid);
+        const int i0 = (int)src;
+        t_i0[tid] = i0; t_i1[tid] = i0 + (i0 < L - 1 ? 1 : 0);
+        const float w1 = __fsub_rn(src, (float)i0);
+        t_w1[tid] = w1; t_w0[tid] = __fsub_rn(1.f, w1);
     }
-    const unsigned ballot = __ballot_sync(0xffffffffu, sel);
-    if (ballot) {
-        const int lane = threadIdx.x & 31;
-        int base = 0;
-        if (lane == 0) base = atomicAdd(n_sel, __popc(ballot));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (sel) list[base + __popc(ballot & ((1u << lane) - 1u))] = (uint32_t)g;
+    for (int64_t b = blockIdx.x; b < n_blocks; b += gridDim.x) {
+        if (tid == 0) s_n = 0;
+        for (int i = tid; i < L3; i += UP_THREADS) { s_sdf[i] = low_sdf[b * L3 + i]; s_std[i] = low_std[b * L3 + i]; }
+        __syncthreads();
+        // separable evaluation, same operations in the same order as the direct 8-tap form (z, then y, then x), each partial
+        // result computed once instead of once per output that shares it: 5.25 instead of 21 flops per output and field
+        for (int j = tid; j < L * L * H; j += UP_THREADS) {                    // along z: [x][y][Z]
+            const int xy = j / H, Z = j % H;
+            const int i0 = xy * L + t_i0[Z], i1 = xy * L + t_i1[Z];
+            const float w0 = t_w0[Z], w1 = t_w1[Z];
+            z_sdf[j] = __fadd_rn(__fmul_rn(w0, s_sdf[i0]), __fmul_rn(w1, s_sdf[i1]));
+            z_std[j] = __fadd_rn(__fmul_rn(w0, s_std[i0]), __fmul_rn(w1, s_std[i1]));
+        }
+        __syncthreads();
+        for (int j = tid; j < L * H * H; j += UP_THREADS) {                    // along y: [x][Y][Z]
+            const int x = j / (H * H), Y = (j / H) % H, Z = j % H;
+            const int i0 = (x * L + t_i0[Y]) * H + Z, i1 = (x * L + t_i1[Y]) * H + Z;
+            const float w0 = t_w0[Y], w1 = t_w1[Y];
+            y_sdf[j] = __fadd_rn(__fmul_rn(w0, z_sdf[i0]), __fmul_rn(w1, z_sdf[i1]));
+            y_std[j] = __fadd_rn(__fmul_rn(w0, z_std[i0]), __fmul_rn(w1, z_std[i1]));
+        }
+        __syncthreads();
+        for (int i = tid; i < H3; i += UP_THREADS) {                           // along x: [X][Y][Z], coalesced stores
+            const int X = i / (H * H), yz = i % (H * H);
+            const int i0 = t_i0[X] * (H * H) + yz, i1 = t_i1[X] * (H * H) + yz;
+            const float w0 = t_w0[X], w1 = t_w1[X];
+            const float o_sdf = __fadd_rn(__fmul_rn(w0, y_sdf[i0]), __fmul_rn(w1, y_sdf[i1]));
+            const float o_std = __fadd_rn(__fmul_rn(w0, y_std[i0]), __fmul_rn(w1, y_std[i1]));
+            cube_sdf[b * H3 + i] = -o_sdf;
+            cube_std[b * H3 + i] = o_std;
+            const bool sel = fabsf(o_sdf) < 0.05f;
+            const unsigned ballot = __ballot_sync(__activemask(), sel);
+            if (sel) {
+                const unsigned lane = tid & 31, leader = __ffs(ballot) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(&s_n, __popc(ballot));
+                base = __shfl_sync(ballot, base, leader);
+                s_list[base + __popc(ballot & ((1u << lane) - 1u))] = (uint16_t)i;
+            }
+        }
+        __syncthreads();
+        const int n = s_n;
+        if (tid == 0 && n) s_base = atomicAdd(n_sel, n);
+        __syncthreads();
+        if (n) {
+            const int base = s_base;
+            const uint32_t g0 = (uint32_t)(b * H3);
+            for (int i = tid; i < n; i += UP_THREADS) list[base + i] = g0 + s_list[i];
+        }
+        __syncthreads();
     }
 }
 
 __global__ void write_counts_kernel(int32_t* counts, int32_t n_low, const int32_t* n_sel) { counts[0] = n_low; counts[1] = n_sel ? *n_sel : 0; }
 
 // ------------------------------------------------------------------------------------------------ marching cubes
-// One CTA per focused PLIVox.  Stage 1: the 27 neighbour batch indices.  Stage 2: the (r+1)^3 blended corner values
-// (each computed once instead of up to 8x as in the reference's per-sub-cube threads).  Stage 3: one thread per
-// sub-cube: case lookup, edge vertices, block-scan of triangle counts, ONE atomicAdd per CTA to reserve output, emit.
+// One CTA per focused PLIVox (grid-stride), compiled per sub-voxel resolution R.
+//   stage 0 (once per CTA): case tables -> shared memory (a divergent __constant__ index serialises), per-axis blend tables
+//            (weights need an IEEE division each: computed R+1 times per CTA instead of 6 times per corner).
+//   stage 1: the 27 neighbour batch indices.
+//   stage 2: the (R+1)^3 blended corner values, each computed once (the reference recomputes a corner in up to 8 sub-cube
+//            threads).  All 16 cube loads of a corner are issued before the first is consumed (no early exit between them),
+//            so a thread has 16 independent L2/HBM requests in flight instead of a chain of 8 round trips.
+//   stage 3: one thread per sub-cube: case lookup, edge vertices, block scan of the triangle counts, ONE atomicAdd per CTA to
+//            reserve output; triangles are staged in shared memory and written out as contiguous float streams (full sectors).
 // Float arithmetic is written with explicit round-to-nearest intrinsics and explicit fmaf in exactly the places where nvcc
 // (-fmad=true) contracts the reference source (read off the reference's PTX; see oracle/mc_oracle.c header), so case indices
 // and vertices are bit-identical to the reference extension and to the scalar restatement in oracle/mc_oracle.c.
 constexpr int MC_THREADS = 128;
 constexpr int MC_MAX_R = 8;
+constexpr int MC_STAGE_TRIS = 160;             // triangles a CTA can stage per PLIVox pass (more -> direct global stores)
 
 struct McArgs {
     const int64_t* indexer; int nx, ny, nz; const int64_t* valid_blocks; int64_t n_valid; const int32_t* mapping; int64_t mapping_len;
     const float* cube_sdf; const float* cube_std; int r; float max_std; float* tri; int64_t* tri_id; float* tri_std; int64_t max_tri;
     int32_t* count;
 };
-
-__device__ __forceinline__ float2 blended_corner(const McArgs& a, const int* nb /*[27]*/, int px, int py, int pz) {
-    const int r = a.r, n = 2 * r;
-    const int rbound = (r - 1) / 2, rstart = r / 2;
-    const float rmid = r / 2.0f, rf = (float)r;
-    const int pos[3] = {px, py, pz};
-    float w_m[3], w_p[3]; int b_m[3], b_p[3], a_m[3], a_p[3], own_is_p[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        if (pos[k] <= rbound) {                      // contributors: previous PLIVox (far half of its cube) and own
-            b_m[k] = -1; b_p[k] = 0; a_m[k] = pos[k] + rstart + r; a_p[k] = pos[k] + rstart;
-            w_p[k] = __fadd_rn((float)pos[k], rmid); w_m[k] = __fsub_rn(rmid, (float)pos[k]); own_is_p[k] = 1;
-        } else {                                     // own and next PLIVox
-            b_m[k] = 0; b_p[k] = 1; a_m[k] = pos[k] + rstart; a_p[k] = pos[k] + rstart - r;
-            w_p[k] = __fsub_rn((float)pos[k], rmid); w_m[k] = __fsub_rn(__fadd_rn(rmid, rf), (float)pos[k]); own_is_p[k] = 0;
-        }
-        w_m[k] = __fdiv_rn(w_m[k], rf); w_p[k] = __fdiv_rn(w_p[k], rf);
-    }
-    const int own = own_is_p[0] * 4 + own_is_p[1] * 2 + own_is_p[2];
-    float s1 = 0.f, s2 = 0.f, s4 = 0.f;
-    const float qnan = __int_as_float(0x7fc00000);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int xp = (k >> 2) & 1, yp = (k >> 1) & 1, zp = k & 1;
-        const int bx = xp ? b_p[0] : b_m[0], by = yp ? b_p[1] : b_m[1], bz = zp ? b_p[2] : b_m[2];
-        const int batch = nb[(bx + 1) * 9 + (by + 1) * 3 + (bz + 1)];
-        float sdf = qnan, sd = qnan;
-        if (batch >= 0) {
-            const int64_t off = (((int64_t)batch * n + (xp ? a_p[0] : a_m[0])) * n + (yp ? a_p[1] : a_m[1])) * n + (zp ? a_p[2] : a_m[2]);
-            sdf = __ldg(a.cube_sdf + off); sd = __ldg(a.cube_std + off);
-        }
-        const float w = __fmul_rn(__fmul_rn(xp ? w_p[0] : w_m[0], yp ? w_p[1] : w_m[1]), zp ? w_p[2] : w_m[2]);
-        if (sdf == sdf) {
-            s1 = __fmaf_rn(__fmul_rn(sdf, w), sd, s1);
-            s2 = __fmaf_rn(w, sd, s2);
-            s4 = __fadd_rn(s4, w);
-        } else if (own == k) {
-            return make_float2(qnan, qnan);
-        }
-    }
-    return make_float2(__fdiv_rn(s1, s2), __fdiv_rn(s2, s4));
-}
 
 __device__ __forceinline__ float4 edge_vertex(float3 p1, float3 p2, float std1, float std2, float v1, float v2) {
     if (fabsf(__fsub_rn(0.0f, v1)) < 1.0e-5f) return make_float4(p1.x, p1.y, p1.z, std1);
@@ -137,52 +128,125 @@ __device__ __forceinline__ float4 edge_vertex(float3 p1, float3 p2, float std1, 
                        __fmaf_rn(p2.z, w2, __fmul_rn(p1.z, w1)), __fmaf_rn(std2, w2, __fmul_rn(std1, w1)));
 }
 
+template <int R>
 __global__ void __launch_bounds__(MC_THREADS) marching_cubes_kernel(McArgs a) {
-    __shared__ int nb[27];
-    __shared__ float c_sdf[(MC_MAX_R + 1) * (MC_MAX_R + 1) * (MC_MAX_R + 1)];
-    __shared__ float c_std[(MC_MAX_R + 1) * (MC_MAX_R + 1) * (MC_MAX_R + 1)];
+    constexpr int R1 = R + 1, NC = R1 * R1 * R1, R3 = R * R * R, N = 2 * R, N3 = N * N * N;
+    constexpr int RBOUND = (R - 1) / 2, RSTART = R / 2;
+    __shared__ int nb2[2][27];                              // double buffered: the next PLIVox's neighbours are fetched one round ahead
+    __shared__ int s_b2[2][3];
+    __shared__ int64_t s_id2[2];
+    __shared__ float c_sdf[NC], c_std[NC];
+    __shared__ float t_wm[R1], t_wp[R1];                    // per-axis blend weights of corner position p (mc_interp_kernel.cu:47-58)
+    __shared__ int t_om[R1], t_op[R1];                      // per-axis cube coordinate read from the "minus" / "plus" contributor
+    __shared__ uint16_t s_emask[256];
+    __shared__ uint8_t s_ntri[256];
+    __shared__ int8_t s_tri[256][16];
+    __shared__ float st_tri[MC_STAGE_TRIS * 9];
+    __shared__ float st_std[MC_STAGE_TRIS * 3];
     __shared__ int warp_tot[MC_THREADS / 32];
     __shared__ int block_base;
-    const int r = a.r, r1 = r + 1, r3 = r * r * r, nc = r1 * r1 * r1;
-    const float sbs = __fdiv_rn(1.0f, (float)r);
+    const int tid = threadIdx.x;
+    const float sbs = __fdiv_rn(1.0f, (float)R);
+    const float qnan = __int_as_float(0x7fc00000);
     const int dx8[8] = {0, 1, 1, 0, 0, 1, 1, 0}, dy8[8] = {0, 0, 1, 1, 0, 0, 1, 1}, dz8[8] = {0, 0, 0, 0, 1, 1, 1, 1};
     const int e_a[12] = {0, 1, 2, 3, 4, 5, 6, 7, 0, 1, 2, 3}, e_b[12] = {1, 2, 3, 0, 5, 6, 7, 4, 4, 5, 6, 7};
 
-    for (int64_t blk = blockIdx.x; blk < a.n_valid; blk += gridDim.x) {
+    for (int i = tid; i < 256; i += MC_THREADS) { s_emask[i] = dif_mc_edge_mask[i]; s_ntri[i] = dif_mc_tri_count[i]; }
+    for (int i = tid; i < 256 * 16; i += MC_THREADS) s_tri[i >> 4][i & 15] = dif_mc_tri_edges[i >> 4][i & 15];
+    if (tid < R1) {
+        const float rmid = R / 2.0f, rf = (float)R, pf = (float)tid;
+        float wm, wp;
+        if (tid <= RBOUND) {                                // contributors: previous PLIVox (far half of its cube) and own
+            wp = __fadd_rn(pf, rmid); wm = __fsub_rn(rmid, pf);
+            t_om[tid] = tid + RSTART + R; t_op[tid] = tid + RSTART;
+        } else {                                            // own and next PLIVox
+            wp = __fsub_rn(pf, rmid); wm = __fsub_rn(__fadd_rn(rmid, rf), pf);
+            t_om[tid] = tid + RSTART; t_op[tid] = tid + RSTART - R;
+        }
+        t_wm[tid] = __fdiv_rn(wm, rf); t_wp[tid] = __fdiv_rn(wp, rf);
+    }
+
+    // neighbour fetch of one PLIVox: valid_blocks -> indexer -> mapping is a chain of three dependent global loads.  It is issued
+    // by the 27 threads [NB_T0, NB_T0 + 27) of the CTA's last warp, which has no corner left in the second corner pass, for the
+    // PLIVox of the NEXT round while the other warps finish the current one.
+    constexpr int NB_T0 = MC_THREADS - 32;
+    auto fetch_neighbours = [&](int64_t blk, int buf) {
+        const int t = tid - NB_T0;
+        if (t < 0 || t >= 27 || blk >= a.n_valid) return;
         const int64_t id = a.valid_blocks[blk];
         const int bx = (int)((id / ((int64_t)a.ny * a.nz)) % a.nx), by = (int)((id / a.nz) % a.ny), bz = (int)(id % a.nz);
-        if (threadIdx.x < 27) {
-            const int ox = threadIdx.x / 9 - 1, oy = (threadIdx.x / 3) % 3 - 1, oz = threadIdx.x % 3 - 1;
-            const int x = bx + ox, y = by + oy, z = bz + oz;
-            int batch = -1;
-            if ((unsigned)x < (unsigned)a.nx && (unsigned)y < (unsigned)a.ny && (unsigned)z < (unsigned)a.nz) {
-                const int64_t slot = a.indexer[((int64_t)x * a.ny + y) * a.nz + z];
-                if (slot != -1 && slot < a.mapping_len) batch = a.mapping[slot];
+        if (t == 0) { s_b2[buf][0] = bx; s_b2[buf][1] = by; s_b2[buf][2] = bz; s_id2[buf] = id; }
+        const int x = bx + t / 9 - 1, y = by + (t / 3) % 3 - 1, z = bz + t % 3 - 1;
+        int batch = -1;
+        if ((unsigned)x < (unsigned)a.nx && (unsigned)y < (unsigned)a.ny && (unsigned)z < (unsigned)a.nz) {
+            const int64_t slot = a.indexer[((int64_t)x * a.ny + y) * a.nz + z];
+            if (slot != -1 && slot < a.mapping_len) batch = a.mapping[slot];
+        }
+        nb2[buf][t] = batch;
+    };
+    fetch_neighbours(blockIdx.x, 0);
+    int buf = 0;
+    for (int64_t blk = blockIdx.x; blk < a.n_valid; blk += gridDim.x, buf ^= 1) {
+        __syncthreads();                                    // nb2[buf] is complete (and, first round, the one-time tables)
+        const int* nb = nb2[buf];
+        const int64_t id = s_id2[buf];
+        const bool own_ok = nb[13] >= 0;                    // a missing own cube makes every corner NaN: nothing to emit
+        if (own_ok) {
+            for (int c = tid; c < NC; c += MC_THREADS) {
+                const int p[3] = {c / (R1 * R1), (c / R1) % R1, c % R1};
+                const int lo[3] = {p[0] <= RBOUND, p[1] <= RBOUND, p[2] <= RBOUND};     // 1: (previous, own)  0: (own, next)
+                const int nb0 = (1 - lo[0]) * 9 + (1 - lo[1]) * 3 + (1 - lo[2]);           // neighbour index of the "minus" contributors
+                const int own = lo[0] * 4 + lo[1] * 2 + lo[2];                             // which k is the own cube
+                const float wx[2] = {t_wm[p[0]], t_wp[p[0]]}, wy[2] = {t_wm[p[1]], t_wp[p[1]]}, wz[2] = {t_wm[p[2]], t_wp[p[2]]};
+                const int ox[2] = {t_om[p[0]] * N * N, t_op[p[0]] * N * N}, oy[2] = {t_om[p[1]] * N, t_op[p[1]] * N}, oz[2] = {t_om[p[2]], t_op[p[2]]};
+                float sv[8], dv[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {               // order mmm, mmp, mpm, mpp, pmm, pmp, ppm, ppp
+                    const int xp = (k >> 2) & 1, yp = (k >> 1) & 1, zp = k & 1;
+                    const int batch = nb[nb0 + xp * 9 + yp * 3 + zp];
+                    sv[k] = qnan; dv[k] = qnan;
+                    if (batch >= 0) {
+                        const int64_t off = (int64_t)batch * N3 + (ox[xp] + oy[yp] + oz[zp]);
+                        sv[k] = __ldg(a.cube_sdf + off); dv[k] = __ldg(a.cube_std + off);
+                    }
+                }
+                float s1 = 0.f, s2 = 0.f, s4 = 0.f;
+                bool own_missing = false;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int xp = (k >> 2) & 1, yp = (k >> 1) & 1, zp = k & 1;
+                    const float w = __fmul_rn(__fmul_rn(wx[xp], wy[yp]), wz[zp]);
+                    if (sv[k] == sv[k]) {
+                        s1 = __fmaf_rn(__fmul_rn(sv[k], w), dv[k], s1);
+                        s2 = __fmaf_rn(w, dv[k], s2);
+                        s4 = __fadd_rn(s4, w);
+                    } else if (own == k) {
+                        own_missing = true;
+                    }
+                }
+                c_sdf[c] = own_missing ? qnan : __fdiv_rn(s1, s2);
+                c_std[c] = own_missing ? qnan : __fdiv_rn(s2, s4);
             }
-            nb[threadIdx.x] = batch;
         }
+        fetch_neighbours(blk + gridDim.x, buf ^ 1);        // other buffer: nobody reads it before the barrier at the loop top
+        if (!own_ok) continue;                              // uniform per CTA
         __syncthreads();
-        for (int c = threadIdx.x; c < nc; c += MC_THREADS) {
-            const float2 v = blended_corner(a, nb, c / (r1 * r1), (c / r1) % r1, c % r1);
-            c_sdf[c] = v.x; c_std[c] = v.y;
-        }
-        __syncthreads();
-        for (int sub0 = 0; sub0 < r3; sub0 += MC_THREADS) {
-            const int sub = sub0 + threadIdx.x;
+        const int bx = s_b2[buf][0], by = s_b2[buf][1], bz = s_b2[buf][2];
+        for (int sub0 = 0; sub0 < R3; sub0 += MC_THREADS) {
+            const int sub = sub0 + tid;
             int n_tri = 0, type = 0;
             float4 vert[12];
-            int rx = 0, ry = 0, rz = 0;
-            if (sub < r3) {
-                rx = sub / (r * r); ry = (sub / r) % r; rz = sub % r;
+            if (sub < R3) {
+                const int rx = sub / (R * R), ry = (sub / R) % R, rz = sub % R;
                 float v[8], sd[8]; bool bad = false;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const int c = ((rx + dx8[i]) * r1 + ry + dy8[i]) * r1 + rz + dz8[i];
+                    const int c = ((rx + dx8[i]) * R1 + ry + dy8[i]) * R1 + rz + dz8[i];
                     v[i] = c_sdf[c]; sd[i] = c_std[c];
                     bad |= !(v[i] == v[i]);
                     if (v[i] < 0.f) type |= 1 << i;
                 }
-                const int emask = bad ? 0 : dif_mc_edge_mask[type];
+                const int emask = bad ? 0 : s_emask[type];
                 if (emask) {
 #pragma unroll
                     for (int e = 0; e < 12; ++e) {
@@ -197,46 +261,68 @@ __global__ void __launch_bounds__(MC_THREADS) marching_cubes_kernel(McArgs a) {
                             vert[e] = edge_vertex(p1, p2, sd[p], sd[q], v[p], v[q]);
                         }
                     }
-                    const int nt = dif_mc_tri_count[type];
+                    const int nt = s_ntri[type];
                     for (int t = 0; t < nt; ++t) {
-                        const float s0 = vert[dif_mc_tri_edges[type][3 * t]].w, s1 = vert[dif_mc_tri_edges[type][3 * t + 1]].w,
-                                    s2 = vert[dif_mc_tri_edges[type][3 * t + 2]].w;
+                        const float s0 = vert[s_tri[type][3 * t]].w, s1 = vert[s_tri[type][3 * t + 1]].w, s2 = vert[s_tri[type][3 * t + 2]].w;
                         if (!(s0 > a.max_std || s1 > a.max_std || s2 > a.max_std)) ++n_tri;
                     }
                 } else {
                     type = 0;
                 }
             }
-            // block exclusive scan of n_tri, one reservation per CTA
+            // block exclusive scan of n_tri; ONE reservation per CTA, issued by thread 0 while everybody stages its triangles
             int incl = n_tri;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += u; }
-            if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += u; }
+            if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
             __syncthreads();
-            if (threadIdx.x == 0) {
-                int tot = 0;
-                for (int w = 0; w < MC_THREADS / 32; ++w) { const int t = warp_tot[w]; warp_tot[w] = tot; tot += t; }
-                block_base = tot ? atomicAdd(a.count, tot) : 0;
-            }
-            __syncthreads();
-            int64_t out = (int64_t)block_base + warp_tot[threadIdx.x >> 5] + incl - n_tri;
-            if (n_tri) {
-                const int nt = dif_mc_tri_count[type];
+            int tot = 0, wpre = 0;
+#pragma unroll
+            for (int w = 0; w < MC_THREADS / 32; ++w) { const int t = warp_tot[w]; if (w < (tid >> 5)) wpre += t; tot += t; }
+            if (tid == 0 && tot) block_base = atomicAdd(a.count, tot);
+            const bool staged = tot <= MC_STAGE_TRIS;                // else (rare): direct stores once the base is known
+            const int local0 = wpre + incl - n_tri;
+            if (staged && n_tri) {
+                int local = local0;
+                const int nt = s_ntri[type];
                 for (int t = 0; t < nt; ++t) {
-                    const float4 v0 = vert[dif_mc_tri_edges[type][3 * t]], v1 = vert[dif_mc_tri_edges[type][3 * t + 1]],
-                                 v2 = vert[dif_mc_tri_edges[type][3 * t + 2]];
+                    const float4 v0 = vert[s_tri[type][3 * t]], v1 = vert[s_tri[type][3 * t + 1]], v2 = vert[s_tri[type][3 * t + 2]];
                     if (v0.w > a.max_std || v1.w > a.max_std || v2.w > a.max_std) continue;
-                    if (out < a.max_tri) {
-                        float* o = a.tri + out * 9;
-                        o[0] = v0.x; o[1] = v0.y; o[2] = v0.z; o[3] = v1.x; o[4] = v1.y; o[5] = v1.z; o[6] = v2.x; o[7] = v2.y; o[8] = v2.z;
-                        float* os = a.tri_std + out * 3;
-                        os[0] = v0.w; os[1] = v1.w; os[2] = v2.w;
-                        a.tri_id[out] = id;
-                    }
-                    ++out;
+                    float* o = st_tri + local * 9;
+                    o[0] = v0.x; o[1] = v0.y; o[2] = v0.z; o[3] = v1.x; o[4] = v1.y; o[5] = v1.z; o[6] = v2.x; o[7] = v2.y; o[8] = v2.z;
+                    float* os = st_std + local * 3;
+                    os[0] = v0.w; os[1] = v1.w; os[2] = v2.w;
+                    ++local;
                 }
             }
-            __syncthreads();
+            __syncthreads();                                         // staging complete, block_base visible
+            if (tot) {
+                const int64_t base = block_base;
+                if (staged) {
+                    const int64_t room = a.max_tri - base;           // triangles past max_tri are counted, not written
+                    const int n_out = room <= 0 ? 0 : (room < tot ? (int)room : tot);
+                    float* gt = a.tri + base * 9; float* gs = a.tri_std + base * 3; int64_t* gi = a.tri_id + base;
+                    for (int i = tid; i < n_out * 9; i += MC_THREADS) gt[i] = st_tri[i];
+                    for (int i = tid; i < n_out * 3; i += MC_THREADS) gs[i] = st_std[i];
+                    for (int i = tid; i < n_out; i += MC_THREADS) gi[i] = id;
+                } else if (n_tri) {
+                    int64_t out = base + local0;
+                    const int nt = s_ntri[type];
+                    for (int t = 0; t < nt; ++t) {
+                        const float4 v0 = vert[s_tri[type][3 * t]], v1 = vert[s_tri[type][3 * t + 1]], v2 = vert[s_tri[type][3 * t + 2]];
+                        if (v0.w > a.max_std || v1.w > a.max_std || v2.w > a.max_std) continue;
+                        if (out < a.max_tri) {
+                            float* o = a.tri + out * 9;
+                            o[0] = v0.x; o[1] = v0.y; o[2] = v0.z; o[3] = v1.x; o[4] = v1.y; o[5] = v1.z; o[6] = v2.x; o[7] = v2.y; o[8] = v2.z;
+                            float* os = a.tri_std + out * 3;
+                            os[0] = v0.w; os[1] = v1.w; os[2] = v2.w;
+                            a.tri_id[out] = id;
+                        }
+                        ++out;
+                    }
+                }
+            }
+            if (sub0 + MC_THREADS < R3) __syncthreads();             // another pass reuses warp_tot / staging / block_base
         }
     }
 }
@@ -297,7 +383,15 @@ int dif_mesh_decode(const dif_map_view* map, const void* decoder_prepared, const
                                low_sdf, low_std, st);
     if (rc) return rc;
     const int64_t total = n_blocks * h3;
-    upsample_select_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(low_sdf, low_std, n_blocks, lr, cube_sdf, cube_std, list, n_sel);
+    {
+        const int64_t cap = (int64_t)DIF_NUM_SMS * 16;
+        const unsigned grid = (unsigned)(n_blocks < cap ? n_blocks : cap);
+        switch (lr) {
+#define DIF_UP_CASE(L) case L: upsample_select_kernel<L><<<grid, UP_THREADS, 0, st>>>(low_sdf, low_std, n_blocks, cube_sdf, cube_std, list, n_sel); break;
+            DIF_UP_CASE(2) DIF_UP_CASE(3) DIF_UP_CASE(4) DIF_UP_CASE(5) DIF_UP_CASE(6) DIF_UP_CASE(7) DIF_UP_CASE(8)
+#undef DIF_UP_CASE
+        }
+    }
     DIF_COUNT_LAUNCH(2);
     rc = launch_decode_lattice(P, map->latent_vecs, block_slots, n_blocks, hr, step_h, (float)sa, list, n_sel, total, -1.f, cube_sdf, cube_std, st);
     if (rc) return rc;
@@ -317,7 +411,12 @@ int dif_marching_cubes(const int64_t* indexer, int nx, int ny, int nz, const int
              tri, tri_flatten_id, tri_std, max_tri, count_dev};
     const int64_t cap = (int64_t)DIF_NUM_SMS * 16;
     prof_begin(DIF_PROF_MC, st);
-    marching_cubes_kernel<<<(unsigned)(n_valid < cap ? n_valid : cap), MC_THREADS, 0, st>>>(a);
+    const unsigned grid = (unsigned)(n_valid < cap ? n_valid : cap);
+    switch (r) {
+#define DIF_MC_CASE(R) case R: marching_cubes_kernel<R><<<grid, MC_THREADS, 0, st>>>(a); break;
+        DIF_MC_CASE(1) DIF_MC_CASE(2) DIF_MC_CASE(3) DIF_MC_CASE(4) DIF_MC_CASE(5) DIF_MC_CASE(6) DIF_MC_CASE(7) DIF_MC_CASE(8)
+#undef DIF_MC_CASE
+    }
     prof_end(DIF_PROF_MC, st);
     DIF_COUNT_LAUNCH(1);
     return check_launch("marching_cubes_kernel");

@@ -39,12 +39,32 @@ def _next_pow2(v: int) -> int:
 
 
 class MeshExtractCache:                                  # reference map.py:116-133
+    """The reference keeps the cached mesh in host numpy arrays and merges on the host (map.py:698-714).  Here the cache lives
+    on the device (``d_vertices`` (T,3,3) world coordinates, ``d_flatten_id`` (T,), ``d_std`` (T,3)) and is merged by
+    ``dif_mesh_cache_merge``; the reference's attribute names ``vertices`` / ``vertices_flatten_id`` / ``vertices_std`` remain
+    readable and download on demand."""
+
     def __init__(self, owner):
         self._owner = owner
-        self.vertices = None
-        self.vertices_flatten_id = None
-        self.vertices_std = None
+        self.d_vertices = None
+        self.d_flatten_id = None
+        self.d_std = None
+        self._host = None
         self.device = owner.device
+
+    def _set(self, tri, fid, std):
+        self.d_vertices, self.d_flatten_id, self.d_std, self._host = tri, fid, std, None
+
+    def _download(self):
+        if self.d_vertices is None:
+            return None
+        if self._host is None:
+            self._host = (self.d_vertices.cpu().numpy(), self.d_flatten_id.cpu().numpy(), self.d_std.cpu().numpy())
+        return self._host
+
+    vertices = property(lambda self: None if self.d_vertices is None else self._download()[0])
+    vertices_flatten_id = property(lambda self: None if self.d_vertices is None else self._download()[1])
+    vertices_std = property(lambda self: None if self.d_vertices is None else self._download()[2])
 
     @property
     def updated_vec_id(self) -> torch.Tensor:
@@ -56,23 +76,36 @@ class MeshExtractCache:                                  # reference map.py:116-
         self._owner._dirty.zero_()
 
     def clear_all(self):
-        self.vertices = None
-        self.vertices_flatten_id = None
-        self.vertices_std = None
+        self._set(None, None, None)
         self.clear_updated_vec()
 
 
 class TriangleMesh:
     """What extract_mesh returns (the reference builds an open3d TriangleMesh, map.py:521-543; open3d is a GUI
-    dependency outside the hot path).  Fields mirror what the reference fills in."""
+    dependency outside the hot path).  Fields mirror what the reference fills in.  Built from device tensors, it downloads
+    lazily: ``n_triangles`` / ``has_triangles()`` cost nothing, ``vertices`` / ``triangles`` / ``vertex_std`` copy on first use;
+    ``d_vertices`` (T,3,3) / ``d_std`` (T,3) are the device views for consumers that stay on the GPU."""
 
-    def __init__(self, vertices: np.ndarray, vertex_std: np.ndarray):
-        self.vertices = vertices.reshape(-1, 3).astype(float)
-        self.triangles = np.arange(self.vertices.shape[0], dtype=np.int32).reshape(-1, 3)
-        self.vertex_std = vertex_std.reshape(-1).astype(float)
+    def __init__(self, vertices, vertex_std):
+        self.d_vertices, self.d_std = (vertices, vertex_std) if torch.is_tensor(vertices) else (None, None)
+        self._v, self._s = (None, None) if torch.is_tensor(vertices) else (vertices, vertex_std)
+        self.n_triangles = int(vertices.shape[0])
+        self._cooked = None
+
+    def _host(self):
+        if self._cooked is None:
+            v = self.d_vertices.cpu().numpy() if self._v is None else self._v
+            s = self.d_std.cpu().numpy() if self._s is None else self._s
+            v = v.reshape(-1, 3).astype(float)
+            self._cooked = (v, np.arange(v.shape[0], dtype=np.int32).reshape(-1, 3), s.reshape(-1).astype(float))
+        return self._cooked
+
+    vertices = property(lambda self: self._host()[0])
+    triangles = property(lambda self: self._host()[1])
+    vertex_std = property(lambda self: self._host()[2])
 
     def has_triangles(self):
-        return self.triangles.shape[0] > 0
+        return self.n_triangles > 0
 
 
 class DenseIndexedMap:
@@ -122,6 +155,7 @@ class DenseIndexedMap:
         self._scratch = None
         self._scratch_points = 0
         self._mesh_persist = None
+        self._cache_persist = None
         self._icp_scratch = None
         self._view_key, self._view_obj = None, None
         self._icp_out = None
@@ -333,9 +367,30 @@ class DenseIndexedMap:
 
     # ------------------------------------------------------------------ mesh extraction (map.py:581-723)
     def _make_mesh_from_cache(self):
-        if self.mesh_cache.vertices is None:
+        if self.mesh_cache.d_vertices is None:
             return TriangleMesh(np.zeros((0, 3, 3), np.float32), np.zeros((0, 3), np.float32))
-        return TriangleMesh(self.mesh_cache.vertices, self.mesh_cache.vertices_std)
+        return TriangleMesh(self.mesh_cache.d_vertices, self.mesh_cache.d_std)
+
+    def _merge_into_cache(self, tri, fid, std):
+        """map.py:698-714 on the device: voxel units -> world, drop cached triangles of PLIVoxes that produced new ones, append."""
+        c, dev = self.mesh_cache, self.device
+        n_cache = 0 if c.d_vertices is None else int(c.d_vertices.size(0))
+        n_new = int(tri.size(0))
+        need = self._L.dif_mesh_cache_scratch_bytes(self._n_cells, n_cache)
+        if self._cache_persist is None or self._cache_persist.numel() < need:
+            self._cache_persist = torch.zeros(self._L.dif_mesh_cache_scratch_bytes(self._n_cells, max(2 * n_cache, 1 << 20)),
+                                              dtype=torch.uint8, device=dev)
+        o_tri = torch.empty((n_cache + n_new, 3, 3), dtype=torch.float32, device=dev)
+        o_id = torch.empty((n_cache + n_new,), dtype=torch.long, device=dev)
+        o_std = torch.empty((n_cache + n_new, 3), dtype=torch.float32, device=dev)
+        totals = torch.zeros(2, dtype=torch.long, device=dev)
+        bm = (ctypes.c_float * 3)(*[float(np.float32(v)) for v in self.args.bound_min])
+        _lib.check(self._L.dif_mesh_cache_merge(
+            _lib.ptr(c.d_vertices), _lib.ptr(c.d_flatten_id), _lib.ptr(c.d_std), n_cache, _lib.ptr(tri), _lib.ptr(fid), _lib.ptr(std), n_new,
+            float(np.float32(self.voxel_size)), bm, self._n_cells, o_tri.data_ptr(), o_id.data_ptr(), o_std.data_ptr(), totals.data_ptr(),
+            self._cache_persist.data_ptr(), self._cache_persist.numel(), _lib.stream_ptr(dev)), "dif_mesh_cache_merge")
+        total = int(totals[1].item())                        # host sync: the merged cache is sliced to its size
+        c._set(o_tri[:total], o_id[:total], o_std[:total])
 
     def mesh_cubes(self, voxel_resolution: int, fast: bool = True, updated_vec_id: torch.Tensor = None):
         """Stages map.py:627-687 on the device: returns (focused_flatten_id (K,), vec_id_batch_mapping (cap,), high_sdf, high_std
@@ -405,18 +460,7 @@ class DenseIndexedMap:
                     return
                 vertices, vertices_flatten_id, vertices_std = _ext.marching_cubes_interp(
                     self.indexer.view(self.n_xyz), focused, mapping, cube_sdf, cube_std, max_n_triangles, self.n_xyz, max_std)
-                vertices = vertices * self.voxel_size + self.bound_min          # map.py:698
-                vertices = vertices.cpu().numpy()
-                vertices_std = vertices_std.cpu().numpy()
-                vertices_flatten_id = vertices_flatten_id.cpu().numpy()
-                c = self.mesh_cache
-                if c.vertices is None:
-                    c.vertices, c.vertices_flatten_id, c.vertices_std = vertices, vertices_flatten_id, vertices_std
-                else:                                        # map.py:708-714: drop cached triangles of re-meshed PLIVoxes
-                    keep = ~np.isin(c.vertices_flatten_id, np.unique(vertices_flatten_id))
-                    c.vertices = np.concatenate([c.vertices[keep], vertices], axis=0)
-                    c.vertices_flatten_id = np.concatenate([c.vertices_flatten_id[keep], vertices_flatten_id], axis=0)
-                    c.vertices_std = np.concatenate([c.vertices_std[keep], vertices_std], axis=0)
+                self._merge_into_cache(vertices.contiguous(), vertices_flatten_id.contiguous(), vertices_std.contiguous())
 
         if extract_async:
             self.meshing_thread = threading.Thread(target=do_meshing, args=(voxel_resolution,), daemon=True)

@@ -154,6 +154,19 @@ int dif_marching_cubes(const int64_t* indexer, int nx, int ny, int nz, const int
                        int r, float max_std, float* tri /*[max_tri][3][3]*/, int64_t* tri_flatten_id /*[max_tri]*/,
                        float* tri_std /*[max_tri][3]*/, int64_t max_tri, int32_t* count_dev, void* stream);
 
+/* ---- device-side mesh cache merge  (replaces the host code of system/map.py:698-714 + _get_valid_idx :20-26) --
+ * out = [cached triangles whose PLIVox id does not occur in new_id, in their old order] ++ [new triangles, voxel units -> world:
+ * v * voxel_size + bound_min (map.py:698)].  Rows: tri [.][3][3] f32, id [.] i64 (linear PLIVox id), std [.][3] f32.
+ * out_* must hold n_cache + n_new rows and may not alias the inputs.  totals_dev[2] (int64) = {kept, kept + n_new}.
+ * persist: dif_mesh_cache_scratch_bytes(n_cells, n_cache) bytes, zero-filled ONCE by the caller; left zeroed (self-cleaning), so
+ * it can be reused while n_cache does not outgrow it. */
+size_t dif_mesh_cache_scratch_bytes(int64_t n_cells, int64_t n_cache);
+int dif_mesh_cache_merge(const float* cache_tri, const int64_t* cache_id, const float* cache_std, int64_t n_cache,
+                         const float* new_tri, const int64_t* new_id, const float* new_std, int64_t n_new,
+                         float voxel_size, const float* bound_min /*[3], host*/, int64_t n_cells,
+                         float* out_tri, int64_t* out_id, float* out_std, int64_t* totals_dev,
+                         void* persist, size_t persist_bytes, void* stream);
+
 /* ---- groupby_sum  (system/ext/indexing/indexing.cu:59-109; indexing.cpp:4) -----------------------------
  * sum[indices[i]][:] += values[i][:];  count[indices[i]] += L  (the reference bumps the count once per column, :70).
  * sum/count must be zero-filled by the caller (the reference allocates zeros, :96-97). */

@@ -63,6 +63,8 @@ def build(names=None, verbose: bool = False) -> list[Path]:
         bdir.mkdir(parents=True, exist_ok=True)
         load(name=n, sources=[str(REF_EXT / s) for s in MODULES[n]], build_directory=str(bdir), verbose=verbose,
              is_python_module=False)       # compile + link only; importing it needs libcuda
+        for junk in list(bdir.glob("*.o")) + list(bdir.glob("*.d")):      # only the .so has to travel to the GPU box
+            junk.unlink()
     return [so_path(n) for n in names if available(n)]
 
 

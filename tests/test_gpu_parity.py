@@ -507,3 +507,64 @@ def test_mesh_scene_against_oracle(model, dev):
     mesh_inc = m.extract_mesh(5, int(6e6), max_std=0.15)
     assert mesh_inc.triangles.shape[0] > 0 and m.mesh_cache.updated_vec_id.numel() == 0
     assert abs(mesh_inc.triangles.shape[0] - mesh_all.triangles.shape[0]) < 0.2 * mesh_all.triangles.shape[0]
+
+
+def test_device_mesh_cache_merge_matches_reference_host_merge(model, dev):
+    """dif_mesh_cache_merge vs a numpy restatement of the reference's host merge (map.py:698-714,
+    _get_valid_idx :20-26): bit-exact rows, reference order (kept cached rows, then new rows), world transform of :698."""
+    import ctypes
+    from difusion_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(3)
+    n_cells, vs, bmin = 50_000, np.float32(0.05), np.array([-1.5, 0.25, 2.0], np.float32)
+    persist = torch.zeros(L.dif_mesh_cache_scratch_bytes(n_cells, 1 << 16), dtype=torch.uint8, device=dev)
+    cache = None
+    for step, (n_new, id_hi) in enumerate([(5000, 400), (3000, 800), (0, 1), (7777, 50_000), (1, 3)]):
+        tri = rng.uniform(0, 40, (n_new, 3, 3)).astype(np.float32)
+        fid = np.sort(rng.integers(0, id_hi, n_new)).astype(np.int64)          # MC emits per-PLIVox runs; any order must work
+        rng.shuffle(fid)
+        std = rng.uniform(0, 0.15, (n_new, 3)).astype(np.float32)
+        world = tri * vs + bmin                                                # map.py:698 (two rounded fp32 ops)
+        if cache is None:
+            exp = (world, fid, std)
+        else:
+            keep = ~np.isin(cache[1], np.unique(fid))                          # == _get_valid_idx
+            exp = tuple(np.concatenate([c[keep], n], 0) for c, n in zip(cache, (world, fid, std)))
+        n_cache = 0 if cache is None else cache[0].shape[0]
+        d_cache = [None] * 3 if cache is None else [_t(c, dev) for c in cache]
+        d_new = [_t(tri, dev), _t(fid, dev), _t(std, dev)]
+        o_tri = torch.empty((n_cache + n_new, 3, 3), device=dev); o_id = torch.empty(n_cache + n_new, dtype=torch.long, device=dev)
+        o_std = torch.empty((n_cache + n_new, 3), device=dev); totals = torch.zeros(2, dtype=torch.long, device=dev)
+        _lib.check(L.dif_mesh_cache_merge(_lib.ptr(d_cache[0]), _lib.ptr(d_cache[1]), _lib.ptr(d_cache[2]), n_cache,
+                                          d_new[0].data_ptr(), d_new[1].data_ptr(), d_new[2].data_ptr(), n_new, float(vs),
+                                          (ctypes.c_float * 3)(*bmin.tolist()), n_cells, o_tri.data_ptr(), o_id.data_ptr(), o_std.data_ptr(),
+                                          totals.data_ptr(), persist.data_ptr(), persist.numel(), _lib.stream_ptr(dev)), "merge")
+        kept, total = totals.tolist()
+        assert total == exp[0].shape[0] and kept == total - n_new, (step, kept, total, exp[0].shape)
+        assert np.array_equal(o_id[:total].cpu().numpy(), exp[1])
+        assert np.array_equal(o_tri[:total].cpu().numpy().view(np.uint32), exp[0].view(np.uint32))
+        assert np.array_equal(o_std[:total].cpu().numpy().view(np.uint32), exp[2].view(np.uint32))
+        assert int(persist[:n_cells].sum()) == 0                               # the flag plane cleaned itself
+        cache = exp
+    # and through extract_mesh (lazy download, cache bookkeeping)
+    from difusion_b200 import synthetic as S
+    from difusion_b200.system.map import DenseIndexedMap
+    sc = S.scene_S0()
+    m = DenseIndexedMap(model, sc.map_args(), 29, dev)
+    for yaw in (0.0, 0.15):
+        R, t = S.yaw_pose(yaw); pc, nc = S.frame_points(sc, R, t); xw, nw = S.to_world(pc, nc, R, t)
+        m.integrate_keyframe(_t(xw, dev), _t(nw, dev))
+        upd_ids = m.latent_vecs_pos[m.mesh_cache.updated_vec_id].cpu().numpy()
+        inc = m.extract_mesh(4, int(2e6), max_std=0.15)
+    assert inc.n_triangles == m.mesh_cache.d_vertices.size(0) == m.mesh_cache.vertices.shape[0] > 1000
+    assert inc.vertices.shape == (3 * inc.n_triangles, 3) and inc.triangles.shape == (inc.n_triangles, 3)
+    v_inc, id_inc = m.mesh_cache.vertices.reshape(-1, 9).copy(), m.mesh_cache.vertices_flatten_id.copy()
+    full = m.extract_mesh(4, int(2e6), max_std=0.15, no_cache=True)
+    v_full, id_full = m.mesh_cache.vertices.reshape(-1, 9), m.mesh_cache.vertices_flatten_id
+    assert 0.9 * full.n_triangles < inc.n_triangles < 1.1 * full.n_triangles
+    # PLIVoxes re-meshed incrementally see only their 6 face neighbours in the decode batch (map.py:628-631), a full extraction
+    # sees all 26, so rows may differ where a diagonal neighbour contributes; most re-meshed triangles are identical bit for bit
+    a = np.unique(v_inc[np.isin(id_inc, upd_ids)], axis=0)
+    b = set(map(bytes, np.unique(v_full[np.isin(id_full, upd_ids)], axis=0)))
+    assert a.shape[0] > 500 and sum(bytes(r) in b for r in a) > 0.8 * a.shape[0]
+    assert set(np.unique(id_inc[np.isin(id_inc, upd_ids)]).tolist()) <= set(upd_ids.tolist())

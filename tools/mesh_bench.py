@@ -41,7 +41,7 @@ for rep in range(3):
     n_low, n_high = cnt.tolist()
     res = dict(B=int(cs.size(0)), K=int(focused.numel()), n_low=n_low, n_high=n_high, triangles=int(tri.size(0)),
                select_decode_ms=e[0].elapsed_time(e[1]), marching_cubes_ms=e[1].elapsed_time(e[2]))
-print(json.dumps(res))
+    print(json.dumps(res))
 # MC alone with events around the kernel only
 L = _lib.lib()
 k0, k1 = ev(), ev()
@@ -59,5 +59,16 @@ print(f"marching_cubes_kernel: {mc_ms*1e3:.1f} us for K={focused.numel()} PLIVox
 v = tri.reshape(-1, 3) * sc.voxel_size + torch.tensor(sc.bound_min, device=dev)
 rad = v.norm(dim=1)
 print(f"vertex radius: mean {rad.mean().item():.4f} m, max |r-R| {(rad - R).abs().max().item():.4f} m (voxel 0.05 m); max vertex std {tstd.max().item():.3f} (<= 0.15)")
-full = m.extract_mesh(5, int(12e6), max_std=0.15, no_cache=True)
-print(f"extract_mesh (incl. D2H + host cache): {full.triangles.shape[0]} triangles")
+for rep in range(2):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    full = m.extract_mesh(5, int(12e6), max_std=0.15, no_cache=True)
+    torch.cuda.synchronize(); t1 = time.perf_counter()
+    print(f"extract_mesh no_cache (select + decode + MC + device cache merge, mesh left on the device): {full.n_triangles} triangles, {1e3 * (t1 - t0):.2f} ms wall")
+t0 = time.perf_counter(); v = full.vertices; t1 = time.perf_counter()
+print(f"download of the mesh on demand: {v.shape[0]} vertices, {1e3 * (t1 - t0):.1f} ms")
+# incremental: touch a patch, re-extract (device-side merge of the cache)
+m.integrate_keyframe(torch.from_numpy(pts[:30000]).to(dev), torch.from_numpy(nrm[:30000]).to(dev))
+torch.cuda.synchronize(); t0 = time.perf_counter()
+inc = m.extract_mesh(5, int(12e6), max_std=0.15)
+torch.cuda.synchronize(); t1 = time.perf_counter()
+print(f"incremental extract_mesh after one 30k-point frame: {inc.n_triangles} triangles in cache, {1e3 * (t1 - t0):.2f} ms wall")

@@ -24,7 +24,7 @@ def main():
     hdr, units, vals = rows[0], rows[1], rows[2]
     with open(out + "_metrics.csv", "w") as f:
         for i, h in enumerate(hdr):
-            if h in KEEP or "tensor" in h and "pct" in h:
+            if h in KEEP or ("tensor" in h and "pct" in h and vals[i] not in ("0", "0.000000", "")):
                 f.write(f"{h},{units[i]},{vals[i]}\n")
         for i, h in enumerate(hdr):
             if h == "Kernel Name":
