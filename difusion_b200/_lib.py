@@ -27,6 +27,7 @@ class MapView(C.Structure):
 
 _P, _I64, _I32, _F, _SZ = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_size_t
 _MV = C.POINTER(MapView)
+_FP = C.POINTER(C.c_float)          # small HOST float arrays (intrinsics, K R K^-1, K t, bound_min)
 
 # name -> (restype, argtypes); this table is also what tests/test_abi.py checks against include/difusion_b200.h
 SIGNATURES = {
@@ -54,6 +55,13 @@ SIGNATURES = {
     "dif_mesh_decode": (C.c_int, [_MV, _P, _P, _I64, C.c_int, C.c_int, _P, _P, _P, _SZ, _P, _P]),
     "dif_marching_cubes": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _I64, _P, _I64, _P, _P, C.c_int, _F, _P, _P, _P, _I64, _P, _P]),
     "dif_groupby_sum": (C.c_int, [_P, _P, _I64, _I32, _I64, _P, _P, _P]),
+    "dif_unproject_depth": (C.c_int, [_P, C.c_int, C.c_int, _F, _F, _F, _F, _P, _P]),
+    "dif_box_filter_scratch_bytes": (_SZ, [_I64, _I64]),
+    "dif_point_box_filter": (C.c_int, [_P, _P, _I64, _F, _I64, _P, _P, _P, _P, _SZ, _P]),
+    "dif_gradient_xy": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
+    "dif_rgb_odometry": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _FP, _FP, _FP, _F, _F, _P, _P, _P]),
+    "dif_rgb_scratch_bytes": (_SZ, []),
+    "dif_rgb_linearize": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _FP, _FP, _FP, _F, _F, C.c_int, _F, _F, C.c_int, _P, _SZ, _P, _P]),
     "dif_mesh_cache_scratch_bytes": (_SZ, [_I64, _I64]),
     "dif_mesh_cache_merge": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _I64, _F, C.POINTER(C.c_float), _I64, _P, _P, _P, _P, _P, _SZ, _P]),
 }
@@ -98,6 +106,12 @@ def ptr(t):
         return None
     assert t.is_contiguous(), "difusion_b200 kernels need contiguous tensors"
     return t.data_ptr()
+
+
+def host_floats(values):
+    """ctypes float array for the small host-side parameter vectors of the ABI."""
+    vals = [float(v) for v in values]
+    return (C.c_float * len(vals))(*vals)
 
 
 def stream_ptr(device=None):

@@ -175,3 +175,19 @@ def stream_frames(scene: Scene, n_frames: int, noise_sigma: float = 0.0):
         R, t = orbit_pose(f, 200)
         pc, n = frame_points(scene, R, t, noise_sigma=noise_sigma, seed=f)
         yield pc, n, R, t
+
+
+def render_rgbd(scene: Scene, R: np.ndarray, t: np.ndarray, step: int = 1, noise_sigma: float = 0.0, seed: int = 0):
+    """A synthetic RGB-D frame for the photometric term: depth as render_depth, colour from a smooth procedural texture that is
+    a function of the WORLD hit point (so two views of the same surface agree, which is what rgb_odometry assumes).
+    Returns rgb (H/step, W/step, 3) float32 in [0,1] and depth (H/step, W/step) float32 (NaN = invalid)."""
+    depth, _ = render_depth(scene, R, t, noise_sigma, seed, step=step)
+    u, v = np.meshgrid(np.arange(0, IMG_W, step, dtype=np.float64), np.arange(0, IMG_H, step, dtype=np.float64))
+    d_c = np.stack([(u - ICL_CX) / ICL_FX, (v - ICL_CY) / ICL_FY, np.ones_like(u)], axis=-1)
+    z = np.where(np.isnan(depth), 0.0, depth.astype(np.float64))
+    p = t.reshape(1, 1, 3) + (d_c @ R.T) * z[..., None]
+    base = 0.5 + 0.2 * np.sin(5.0 * p[..., 0]) * np.cos(4.0 * p[..., 1]) + 0.2 * np.sin(3.0 * p[..., 2] + 2.0 * p[..., 0])
+    rgb = np.stack([base, 0.9 * base + 0.05 * np.cos(7.0 * p[..., 1]), 0.8 * base + 0.1 * np.sin(6.0 * p[..., 2])], -1)
+    rgb = np.clip(rgb, 0.0, 1.0)
+    rgb[np.isnan(depth)] = 0.0
+    return rgb.astype(np.float32), depth

@@ -1,6 +1,7 @@
 """Drop-in replacements for the reference's native op table ``system.ext`` (ext/__init__.py:15-44) on the hot path:
-``marching_cubes_interp`` (mc.cpp:3-16) and ``groupby_sum`` (indexing.cpp:4).  Same argument meaning and return
-values; torch tensors in, torch tensors out; the work is done by libdifusion_b200.so on the current stream.
+``marching_cubes_interp`` (mc.cpp:3-16), ``groupby_sum`` (indexing.cpp:4) and, from the image side,
+``unproject_depth`` (imgproc.cu:26-44), ``gradient_xy`` and ``rgb_odometry`` (photometric.cu:80-138).  Same argument meaning and
+return values; torch tensors in, torch tensors out; the work is done by libdifusion_b200.so on the current stream.
 """
 from __future__ import annotations
 
@@ -55,3 +56,72 @@ def groupby_sum(values: torch.Tensor, indices: torch.Tensor, C: int):
     _lib.check(_lib.lib().dif_groupby_sum(values.data_ptr(), indices.data_ptr(), n, Lc, C, s.data_ptr(), c.data_ptr(),
                                           _lib.stream_ptr(values.device)), "dif_groupby_sum")
     return [s, c]
+
+
+def gradient_xy(cur_intensity: torch.Tensor):
+    """(H,W) f32 -> (H,W,2) f32 Sobel gradients / 8, NaN on the border (photometric.cu:3-22,80-93)."""
+    _check_input(cur_intensity, "cur_intensity")
+    h, w = cur_intensity.shape
+    out = torch.empty((h, w, 2), dtype=torch.float32, device=cur_intensity.device)
+    _lib.check(_lib.lib().dif_gradient_xy(cur_intensity.data_ptr(), h, w, out.data_ptr(), _lib.stream_ptr(cur_intensity.device)), "dif_gradient_xy")
+    return out
+
+
+def rgb_odometry(prev_intensity, prev_depth, cur_intensity, cur_depth, cur_dIdxy, intr, krkinv_data, kt_data,
+                 min_grad_scale: float, max_depth_delta: float, compute_J: bool):
+    """-> [f_img (H,W)] or [f_img, J_img (H,W,6)]; NaN in f_img marks rejected pixels (photometric.cu:24-78,95-138)."""
+    for t, nm in ((prev_intensity, "prev_intensity"), (prev_depth, "prev_depth"), (cur_intensity, "cur_intensity"),
+                  (cur_depth, "cur_depth"), (cur_dIdxy, "cur_dIdxy")):
+        _check_input(t, nm)
+    h, w = cur_intensity.shape
+    dev = cur_intensity.device
+    f_img = torch.empty((h, w), dtype=torch.float32, device=dev)
+    J_img = torch.empty((h, w, 6), dtype=torch.float32, device=dev) if compute_J else None
+    _lib.check(_lib.lib().dif_rgb_odometry(prev_intensity.data_ptr(), prev_depth.data_ptr(), cur_intensity.data_ptr(), cur_depth.data_ptr(),
+                                           cur_dIdxy.data_ptr(), h, w, _lib.host_floats(intr), _lib.host_floats(krkinv_data),
+                                           _lib.host_floats(kt_data), float(min_grad_scale), float(max_depth_delta), f_img.data_ptr(),
+                                           _lib.ptr(J_img), _lib.stream_ptr(dev)), "dif_rgb_odometry")
+    return [f_img, J_img] if compute_J else [f_img]
+
+
+def unproject_depth(depth: torch.Tensor, fx: float, fy: float, cx: float, cy: float):
+    """(H,W) f32 depth (NaN = invalid) -> (H,W,3) camera-frame points (imgproc.cu:5-44); invalid pixels are NaN."""
+    _check_input(depth, "depth")
+    h, w = depth.shape
+    pc = torch.empty((h, w, 3), dtype=torch.float32, device=depth.device)
+    _lib.check(_lib.lib().dif_unproject_depth(depth.data_ptr(), h, w, float(fx), float(fy), float(cx), float(cy), pc.data_ptr(),
+                                              _lib.stream_ptr(depth.device)), "dif_unproject_depth")
+    return pc
+
+
+_BOX_MAX_CELLS = 1 << 27                 # 2 cm cells: a ~10 m cube of bounding box (16 MB bitmap + 16 MB ranks)
+_box_scratch = {}                        # device -> (zero-filled scratch, points it was sized for)
+
+
+def point_box_filter(points: torch.Tensor, normals: torch.Tensor, voxel_size: float):
+    """tracker.point_box_filter (tracker.py:13-23): (N,3),(N,3) -> (M,3),(M,3) per-cell means, cells in ascending key order."""
+    _check_input(points, "points")
+    _check_input(normals, "normals")
+    L, dev, n = _lib.lib(), points.device, points.size(0)
+    sc = _box_scratch.get(dev)
+    if sc is None or sc[1] < n:
+        cap = max(n, 1 << 17)
+        sc = (torch.zeros(L.dif_box_filter_scratch_bytes(cap, _BOX_MAX_CELLS), dtype=torch.uint8, device=dev), cap)
+        _box_scratch[dev] = sc
+    out_p = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    out_n = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    n_out = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.check(L.dif_point_box_filter(points.data_ptr(), normals.data_ptr(), n, float(voxel_size), _BOX_MAX_CELLS, out_p.data_ptr(),
+                                      out_n.data_ptr(), n_out.data_ptr(), sc[0].data_ptr(), sc[0].numel(), _lib.stream_ptr(dev)), "dif_point_box_filter")
+    m = int(n_out.item())                        # host sync: output shape (the reference syncs at tracker.py:18 and inside unique)
+    if m < 0:
+        raise RuntimeError("point_box_filter: the frame's bounding box exceeds the cell budget of the filter scratch")
+    return out_p[:m], out_n[:m]
+
+
+def remove_radius_outlier(input_pc: torch.Tensor, nb_points: int, radius: float):
+    raise NotImplementedError("remove_radius_outlier (pcproc.cu:172-196, kd-tree 16-NN) - SURVEY 8 f-1, not built yet")
+
+
+def estimate_normals(input_pc: torch.Tensor, max_nn: int, radius: float, cam_xyz):
+    raise NotImplementedError("estimate_normals (pcproc.cu:198-220, kd-tree 16-NN + PCA) - SURVEY 8 f-1, not built yet")

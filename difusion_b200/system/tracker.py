@@ -4,9 +4,14 @@ On the hot path (SURVEY a-9): ``compute_sdf_Hg`` and the Gauss-Newton driver ``g
 reference evaluates the decoder through ``map.get_sdf`` + ``torch.autograd.grad`` and syncs three times per iteration
 (tracker.py:191,210,215-216); here one fused kernel (dif_icp_linearize) returns H, g, energy in a single 352-byte readback.
 
-Frame pre-processing (``track_camera``: kd-tree outlier removal / normals, tracker.py:88-117) and the photometric term
-(``compute_rgb_Hg``, tracker.py:131-172) are the "next" rows of SURVEY 8(f) and are not built: ``track_camera`` therefore
-takes the already pre-processed point cloud through ``track_points``.
+The photometric term: ``compute_rgb_Hg`` (tracker.py:131-172) is ONE launch of dif_rgb_linearize (warp, residual,
+Jacobian, robust weight, 6x6 reduction) instead of the reference's rgb_odometry kernel + boolean-mask compaction + einsum +
+three host syncs; ``_make_image_pyramid`` (tracker.py:41-56) keeps torch's interpolate for the three small resamplings and uses
+dif_gradient_xy for the Sobel gradients.
+
+Frame pre-processing inside ``track_camera`` (tracker.py:88-117) goes through ``system.ext`` (unproject_depth,
+remove_radius_outlier, estimate_normals) and ``point_box_filter``; callers that already hold a pre-processed cloud use
+``track_points``.
 """
 from __future__ import annotations
 
@@ -15,7 +20,9 @@ import copy
 import numpy as np
 import torch
 
+from .. import _lib
 from ..utils.motion_util import Isometry
+from . import ext as _ext
 
 
 class _Args:
@@ -36,6 +43,7 @@ class SDFTracker:
         self.cur_gt_pose = None
         self.last_colored_pcd = None
         self.n_unstable = 0
+        self._rgb_scratch = None
 
     # -------------------------------------------------------------------------------------------------
     def compute_sdf_Hg(self, n_iter: int, last_pose: Isometry, cur_delta_pose: Isometry, obs_xyz: torch.Tensor, no_grad: bool = False):
@@ -51,8 +59,52 @@ class SDFTracker:
             return None, None, float(o[42])
         return o[:36].reshape(6, 6).astype(float), o[36:42].astype(float), float(o[42])
 
-    def compute_rgb_Hg(self, *a, **k):
-        raise NotImplementedError("photometric term (tracker.py:131-172) is SURVEY 8(f)-3, not part of this build")
+    # ------------------------------------------------------------------------------------------------- photometric term
+    def _make_image_pyramid(self, intensity_img: torch.Tensor, depth_img: torch.Tensor):
+        """tracker.py:41-56: three levels of (intensity bilinear, depth nearest) and their Sobel gradients."""
+        F = torch.nn.functional
+        d0_w, d0_h = intensity_img.size(1), intensity_img.size(0)
+        d1_w, d1_h = d0_w // 2, d0_h // 2
+        d2_w, d2_h = d1_w // 2, d1_h // 2
+        d0_i = intensity_img.view(1, 1, d0_h, d0_w)
+        d0_d = depth_img.view(1, 1, d0_h, d0_w)
+        d1_i = F.interpolate(d0_i, (d1_h, d1_w), mode="bilinear")
+        d1_d = F.interpolate(d0_d, (d1_h, d1_w), mode="nearest")
+        d2_i = F.interpolate(d1_i, (d2_h, d2_w), mode="bilinear")
+        d2_d = F.interpolate(d1_d, (d2_h, d2_w), mode="nearest")
+        ints = [t.squeeze(0).squeeze(0).contiguous() for t in (d0_i, d1_i, d2_i)]
+        deps = [t.squeeze(0).squeeze(0).contiguous() for t in (d0_d, d1_d, d2_d)]
+        return ints, deps, [_ext.gradient_xy(t) for t in ints]
+
+    def compute_rgb_Hg(self, pyramid_level: int, cur_delta_pose: Isometry, cur_intensity_pyramid: list, cur_depth_pyramid: list,
+                       cur_dIdxy_pyramid: list, calib, no_grad: bool = False):
+        """tracker.py:131-172.  Returns (H (6,6) float64, g (6,) float64, energy) or (None, None, energy) if no_grad."""
+        a = self.rgb_args
+        kind = {None: 0, "huber": 1, "tukey": 2}.get(a.robust_kernel, -1)
+        if kind < 0:
+            raise NotImplementedError(a.robust_kernel)                      # as tracker.py:70-71
+        K = calib.to_K()
+        KRKinv = K @ cur_delta_pose.q.rotation_matrix @ np.linalg.inv(K)
+        Kt = K @ cur_delta_pose.t
+        prev_i, prev_d = self.last_intensity[pyramid_level], self.last_depth[pyramid_level]
+        cur_i, cur_d, cur_g = cur_intensity_pyramid[pyramid_level], cur_depth_pyramid[pyramid_level], cur_dIdxy_pyramid[pyramid_level]
+        dev = cur_i.device
+        L = _lib.lib()
+        if self._rgb_scratch is None:
+            self._rgb_scratch = torch.zeros(L.dif_rgb_scratch_bytes(), dtype=torch.uint8, device=dev)       # zero-filled once (ABI)
+        out = torch.empty(44, dtype=torch.float64, device=dev)
+        h, w = cur_i.shape
+        _lib.check(L.dif_rgb_linearize(_lib.ptr(prev_i), _lib.ptr(prev_d), _lib.ptr(cur_i), _lib.ptr(cur_d), _lib.ptr(cur_g), h, w,
+                                       _lib.host_floats([calib.fx, calib.fy, calib.cx, calib.cy]), _lib.host_floats(KRKinv.flatten().tolist()),
+                                       _lib.host_floats(Kt.flatten().tolist()), float(a.min_grad_scale), float(a.max_depth_delta), kind,
+                                       float(a.robust_k or 0.0), float(a.weight), int(not no_grad), self._rgb_scratch.data_ptr(),
+                                       self._rgb_scratch.numel(), out.data_ptr(), _lib.stream_ptr(dev)), "dif_rgb_linearize")
+        o = out.cpu().numpy()                          # the only host sync of the term
+        if not o[43] > 0:
+            raise ZeroDivisionError("float division by zero")               # tracker.py:165 with an empty valid set
+        if no_grad:
+            return None, None, float(o[42])
+        return o[:36].reshape(6, 6).astype(float), o[36:42].astype(float), float(o[42])
 
     def gauss_newton(self, init_pose: Isometry, cur_intensity_pyramid, cur_depth_pyramid, cur_dIdxy_pyramid, obs_xyz: torch.Tensor, calib):
         """tracker.py:220-283 for iter_config entries made of 'sdf' terms."""
@@ -73,8 +125,15 @@ class SDFTracker:
                         if i_iter != -1:
                             H += sH
                             g += sg
+                    elif loss_config[0] == "rgb":
+                        rH, rg, rE = self.compute_rgb_Hg(loss_config[1], cur_delta_pose, cur_intensity_pyramid, cur_depth_pyramid,
+                                                         cur_dIdxy_pyramid, calib, i_iter == -1)
+                        cur_energy += rE
+                        if i_iter != -1:
+                            H += rH
+                            g += rg
                     else:
-                        raise NotImplementedError(f"loss term {loss_config[0]!r} is outside the hot path (SURVEY 8f)")
+                        raise NotImplementedError(f"loss term {loss_config[0]!r} (tracker.py:254-262 'motion' is not used by the shipped configs)")
                 if cur_energy > last_energy:
                     cur_delta_pose = last_delta_pose
                     break
@@ -83,8 +142,10 @@ class SDFTracker:
                 if i_iter != -1:
                     xi = np.linalg.solve(H, -g)
                     cur_delta_pose = Isometry.from_twist(xi) @ cur_delta_pose
-        if i_iter >= 10:
+        if i_iter >= 10:                                    # tracker.py:276-281
             self.n_unstable += 1
+            if self.n_unstable >= 3 and self.rgb_args is not None:
+                self.rgb_args.weight = max(self.rgb_args.weight, 500.)
         return last_pose.dot(cur_delta_pose)
 
     def track_points(self, pc_cam: torch.Tensor, normal_cam: torch.Tensor, set_pose: Isometry = None) -> Isometry:
@@ -98,6 +159,41 @@ class SDFTracker:
         self.all_pd_pose.append(final_pose)
         return final_pose
 
-    def track_camera(self, rgb_data, depth_data, calib, set_pose: Isometry = None):
-        raise NotImplementedError("depth pre-processing (unproject / kd-tree outliers / PCA normals, tracker.py:88-116) is SURVEY 8(f)-1; "
-                                  "feed pre-processed points to track_points()")
+    def track_camera(self, rgb_data: torch.Tensor, depth_data: torch.Tensor, calib, set_pose: Isometry = None) -> Isometry:
+        """tracker.py:74-129.  rgb (H,W,3) f32, depth (H,W) f32 with NaN = invalid, calib: fx/fy/cx/cy + to_K()."""
+        F = torch.nn.functional
+        cur_intensity = torch.mean(rgb_data, dim=-1)
+        cur_intensity, cur_depth, cur_dIdxy = self._make_image_pyramid(cur_intensity, depth_data)
+        cur_rgb = rgb_data.permute(2, 0, 1)
+        pc_scale = self.sdf_args.subsample
+        pc_data = F.interpolate(cur_depth[0].unsqueeze(0).unsqueeze(0), scale_factor=pc_scale, mode="nearest",
+                                recompute_scale_factor=False).squeeze(0).squeeze(0).contiguous()
+        cur_rgb = F.interpolate(cur_rgb.unsqueeze(0), scale_factor=pc_scale, mode="bilinear", recompute_scale_factor=False).squeeze(0)
+        pc_data = _ext.unproject_depth(pc_data, calib.fx * pc_scale, calib.fy * pc_scale, calib.cx * pc_scale, calib.cy * pc_scale)
+        pc_data = torch.cat([pc_data, torch.zeros((pc_data.size(0), pc_data.size(1), 1), device=pc_data.device)], dim=-1).reshape(-1, 4)
+        cur_rgb = cur_rgb.permute(1, 2, 0).reshape(-1, 3)
+        nan_mask = ~torch.isnan(pc_data[..., 0])
+        pc_data, cur_rgb = pc_data[nan_mask], cur_rgb[nan_mask]
+        with torch.cuda.device(self.map.device):
+            valid = _ext.remove_radius_outlier(pc_data.contiguous(), 16, 0.05)
+            pc_data, cur_rgb = pc_data[valid], cur_rgb[valid]
+            normal_data = _ext.estimate_normals(pc_data.contiguous(), 16, 0.1, [0.0, 0.0, 0.0])
+            normal_valid = ~torch.isnan(normal_data[..., 0])
+            normal_data, cur_rgb, pc_data = normal_data[normal_valid], cur_rgb[normal_valid], pc_data[normal_valid, :3]
+        self.last_colored_pcd = [pc_data, cur_rgb]
+        pc_data, normal_data = point_box_filter(pc_data, normal_data, 0.02)
+        self.last_processed_pc = [pc_data, normal_data]
+        if set_pose is not None:
+            final_pose = set_pose
+        else:
+            assert len(self.all_pd_pose) > 0
+            final_pose = self.gauss_newton(self.all_pd_pose[-1].dot(Isometry()), cur_intensity, cur_depth, cur_dIdxy, pc_data, calib)
+        self.last_intensity = cur_intensity
+        self.last_depth = cur_depth
+        self.all_pd_pose.append(final_pose)
+        return final_pose
+
+
+def point_box_filter(points: torch.Tensor, normals: torch.Tensor, voxel_size: float):
+    """tracker.py:13-23: per-cell mean of points and normals over a `voxel_size` grid, cells in ascending key order."""
+    return _ext.point_box_filter(points, normals, voxel_size)

@@ -167,6 +167,36 @@ int dif_mesh_cache_merge(const float* cache_tri, const int64_t* cache_id, const 
                          float* out_tri, int64_t* out_id, float* out_std, int64_t* totals_dev,
                          void* persist, size_t persist_bytes, void* stream);
 
+/* ---- frame pre-processing  (system/tracker.py:88-117, :13-23; system/ext/imgproc/imgproc.cu:5-44) -------------
+ * dif_unproject_depth : ext op unproject_depth: pc[v][u] = ((u - cx) / fx * d, (v - cy) / fy * d, d); NaN depth -> NaN point.
+ * dif_point_box_filter: tracker.point_box_filter (:13-23): mean point / mean normal per voxel_size cell of the frame's bounding box,
+ *   rows in ascending cell-key order (== torch.unique's order).  out_* hold up to n rows; *n_out_dev = rows written, or -1 when
+ *   the bounding box has more than max_cells cells.  scratch: dif_box_filter_scratch_bytes(max n, max_cells) bytes, zero-filled
+ *   ONCE by the caller and left zeroed by every call. */
+int dif_unproject_depth(const float* depth, int h, int w, float fx, float fy, float cx, float cy, float* pc_out /*[h][w][3]*/, void* stream);
+size_t dif_box_filter_scratch_bytes(int64_t max_points, int64_t max_cells);
+int dif_point_box_filter(const float* points /*[n][3]*/, const float* normals /*[n][3]*/, int64_t n, float voxel_size, int64_t max_cells,
+                         float* out_points, float* out_normals, int32_t* n_out_dev, void* scratch, size_t scratch_bytes, void* stream);
+
+/* ---- photometric term  (system/ext/imgproc/photometric.cu:3-138, system/tracker.py:131-172) -------------------
+ * Images are row-major [h][w] f32 (NaN = invalid depth); gradients [h][w][2]; intr = {fx, fy, cx, cy}; krkinv = K R K^-1 (row
+ * major, 9), kt = K t (3) - host arrays, exactly the lists the reference passes to rgb_odometry (tracker.py:139-146).
+ * dif_gradient_xy : ext op gradient_xy (photometric.cu:3-22,80-93): Sobel/8, NaN on the one-pixel border.
+ * dif_rgb_odometry: ext op rgb_odometry (photometric.cu:24-78,95-138): f_out [h][w] (NaN = rejected pixel); J_out [h][w][6] or NULL
+ *                   (compute_J = false); J rows of rejected pixels are left untouched, as in the reference (torch::empty).
+ * dif_rgb_linearize: compute_rgb_Hg (tracker.py:131-172) in one launch: out_dev[44] doubles = H (36, row major), g (6), energy,
+ *                   M (valid pixels); J is negated as in :157, error_scale = weight / M (:165).  robust_kind 0 none / 1 huber /
+ *                   2 tukey (:58-71).  want_grad = 0 fills only energy and M.  scratch: dif_rgb_scratch_bytes(), zero-filled once. */
+int dif_gradient_xy(const float* intensity, int h, int w, float* out_grad, void* stream);
+int dif_rgb_odometry(const float* prev_intensity, const float* prev_depth, const float* cur_intensity, const float* cur_depth,
+                     const float* cur_dIdxy, int h, int w, const float* intr, const float* krkinv, const float* kt,
+                     float min_grad_scale, float max_depth_delta, float* f_out, float* J_out, void* stream);
+size_t dif_rgb_scratch_bytes(void);
+int dif_rgb_linearize(const float* prev_intensity, const float* prev_depth, const float* cur_intensity, const float* cur_depth,
+                      const float* cur_dIdxy, int h, int w, const float* intr, const float* krkinv, const float* kt,
+                      float min_grad_scale, float max_depth_delta, int robust_kind, float robust_k, float weight, int want_grad,
+                      void* scratch, size_t scratch_bytes, double* out_dev, void* stream);
+
 /* ---- groupby_sum  (system/ext/indexing/indexing.cu:59-109; indexing.cpp:4) -----------------------------
  * sum[indices[i]][:] += values[i][:];  count[indices[i]] += L  (the reference bumps the count once per column, :70).
  * sum/count must be zero-filled by the caller (the reference allocates zeros, :96-97). */

@@ -13,8 +13,8 @@ _LIB = None
 
 def build(force: bool = False) -> Path:
     out = _HERE / "_build" / "libdif_oracle.so"
-    src = _HERE / "mc_oracle.c"
-    if force or not out.exists() or out.stat().st_mtime < src.stat().st_mtime:
+    srcs = [_HERE / "mc_oracle.c", _HERE / "imgproc_oracle.c", _HERE / "Makefile"]
+    if force or not out.exists() or out.stat().st_mtime < max(s.stat().st_mtime for s in srcs):
         subprocess.check_call(["make", "-C", str(_HERE), "-s"] + (["-B"] if force else []))
     return out
 

@@ -7,6 +7,8 @@ Fixtures (inputs AND reference outputs are stored, so the CPU tests need neither
   ref_ext_mc_r{2,4,5}.npz  marching_cubes_sparse_interp (ext/marching_cubes/mc_interp_kernel.cu) on analytic sphere cubes with a missing
                            PLIVox, PLIVoxes left out of the batch, noisy std; outputs for max_std = 10 and 0.15, canonically sorted
   ref_ext_groupby.npz      groupby_sum (ext/indexing/indexing.cu:59-109)
+  ref_ext_photo.npz        gradient_xy + rgb_odometry (ext/imgproc/photometric.cu) on two 160x120 synthetic RGB-D views of scene S1
+  ref_ext_unproject.npz    unproject_depth (ext/imgproc/imgproc.cu:5-44)
 The reference ships no vectors of its own, so these executions are the pin for the two CUDA-only ops.
 """
 import sys
@@ -37,6 +39,30 @@ def mc_case(r: int, seed: int = 0):
     blocks = np.sort(rng.choice(B, int(B * 0.8), replace=False)).astype(np.int64)
     blocks = blocks[indexer.reshape(-1)[blocks] != -1]
     return dict(n_xyz=np.asarray(n_xyz), indexer=indexer, blocks=blocks, mapping=mapping, cube_sdf=sdf, cube_std=std)
+
+
+def photo_case():
+    """Two 160x120 views (frames 0 and 6 of the S1 orbit) + the relative pose handed to rgb_odometry, as tracker.py:134-146 builds it."""
+    from difusion_b200 import synthetic as S
+    sc = S.scene_S1(0.05)
+    out = {}
+    poses = []
+    for tag, f in (("prev", 0), ("cur", 6)):
+        R, t = S.orbit_pose(f)
+        rgb, depth = S.render_rgbd(sc, R, t, step=4)
+        out[f"{tag}_i"] = rgb.mean(-1).astype(np.float32)
+        out[f"{tag}_d"] = depth
+        poses.append((R, t))
+    (R0, t0), (R1, t1) = poses
+    # delta = last^-1 . cur (tracker.py:223), then perturbed so that the residuals are not at their minimum
+    Rd = R0.T @ R1
+    td = R0.T @ (t1 - t0) + np.array([0.004, -0.003, 0.002])
+    fx, fy, cx, cy = S.ICL_FX / 4, S.ICL_FY / 4, S.ICL_CX / 4, S.ICL_CY / 4
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
+    out.update(intr=np.array([fx, fy, cx, cy], np.float32), K=K, Rd=Rd, td=td,
+               krkinv=(K @ Rd @ np.linalg.inv(K)).flatten(), kt=(K @ td).flatten(),
+               min_grad_scale=np.float32(1e-5), max_depth_delta=np.float32(0.2))
+    return out
 
 
 def canon(tri, fid, std):
@@ -70,6 +96,24 @@ def main():
     s, cnt = ix.groupby_sum(v.to(dev), idx.to(dev), 40)
     np.savez_compressed(out / "ref_ext_groupby.npz", values=v.numpy(), indices=idx.numpy(), C=40, sum=s.cpu().numpy(), count=cnt.cpu().numpy())
     print("groupby_sum:", s.shape, cnt.dtype, int(cnt.sum()))
+    im = build_ref.load_module("imgproc")
+    c = photo_case()
+    t = {k: torch.from_numpy(np.ascontiguousarray(c[k])).to(dev) for k in ("prev_i", "prev_d", "cur_i", "cur_d")}
+    grad = im.gradient_xy(t["cur_i"])
+    f_img, J_img = im.rgb_odometry(t["prev_i"], t["prev_d"], t["cur_i"], t["cur_d"], grad, c["intr"].tolist(), c["krkinv"].tolist(), c["kt"].tolist(),
+                                   float(c["min_grad_scale"]), float(c["max_depth_delta"]), True)
+    f_only, = im.rgb_odometry(t["prev_i"], t["prev_d"], t["cur_i"], t["cur_d"], grad, c["intr"].tolist(), c["krkinv"].tolist(), c["kt"].tolist(),
+                              float(c["min_grad_scale"]), float(c["max_depth_delta"]), False)
+    f_np, J_np = f_img.cpu().numpy(), J_img.cpu().numpy()
+    assert np.array_equal(np.isnan(f_np), np.isnan(f_only.cpu().numpy()))
+    J_np[np.isnan(f_np)] = np.nan                          # uninitialised memory in the reference: not part of the contract
+    np.savez_compressed(out / "ref_ext_photo.npz", **c, grad=grad.cpu().numpy(), f=f_np, J=J_np)
+    print("photo: valid pixels", int((~np.isnan(f_np)).sum()), "of", f_np.size)
+    depth = c["cur_d"]
+    pc = im.unproject_depth(torch.from_numpy(depth).to(dev), float(c["intr"][0]), float(c["intr"][1]), float(c["intr"][2]), float(c["intr"][3])).cpu().numpy()
+    pc[np.isnan(depth)] = np.nan                           # only x = NaN is written for invalid pixels (imgproc.cu:21)
+    np.savez_compressed(out / "ref_ext_unproject.npz", depth=depth, intr=c["intr"], pc=pc)
+    print("unproject:", pc.shape)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,188 @@
+"""GPU: the rows of SURVEY 8(f) around the fusion path - photometric term (f-3) and frame pre-processing (f-1) - through the
+reference-shaped Python surface -> C ABI, against (1) the UNMODIFIED reference CUDA extension executed on the same device
+(oracle/_ref/imgproc, bit-exact), (2) the CPU oracle (oracle/imgproc_oracle.c, bit-exact; numpy restatement of the torch part,
+1e-4) and (3) the committed golden vectors."""
+import argparse
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, close
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def _t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def _ref(name):
+    from oracle import build_ref
+    if not build_ref.available(name):
+        pytest.skip(f"oracle/_ref/{name} not built")
+    return build_ref.load_module(name)
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def _photo_inputs(dev):
+    from golden.make_golden_gpu import photo_case
+    c = photo_case()
+    t = {k: _t(c[k], dev) for k in ("prev_i", "prev_d", "cur_i", "cur_d")}
+    return c, t
+
+
+def test_gradient_and_rgb_odometry_bit_exact(dev):
+    from difusion_b200.system import ext
+    from oracle import imgproc_oracle as O
+    c, t = _photo_inputs(dev)
+    fx = np.load(GOLDEN / "ref_ext_photo.npz")
+    grad = ext.gradient_xy(t["cur_i"])
+    g_np = grad.cpu().numpy()
+    o_grad = O.gradient_xy(c["cur_i"])
+    assert np.array_equal(_bits(g_np), _bits(o_grad)) and np.array_equal(_bits(g_np), _bits(fx["grad"]))
+    args = (c["intr"].tolist(), c["krkinv"].tolist(), c["kt"].tolist(), float(c["min_grad_scale"]), float(c["max_depth_delta"]))
+    f_img, J_img = ext.rgb_odometry(t["prev_i"], t["prev_d"], t["cur_i"], t["cur_d"], grad, *args, True)
+    f_only, = ext.rgb_odometry(t["prev_i"], t["prev_d"], t["cur_i"], t["cur_d"], grad, *args, False)
+    f_np, J_np = f_img.cpu().numpy(), J_img.cpu().numpy()
+    valid = ~np.isnan(f_np)
+    assert valid.sum() > 10000 and np.array_equal(_bits(f_np), _bits(f_only.cpu().numpy()))
+    o_f, o_J = O.rgb_odometry(c["prev_i"], c["prev_d"], c["cur_i"], c["cur_d"], o_grad, *args)
+    for rf, rJ in ((o_f, o_J), (fx["f"], fx["J"])):                    # CPU oracle, then the executed reference (golden)
+        assert np.array_equal(valid, ~np.isnan(rf))
+        assert np.array_equal(_bits(f_np[valid]), _bits(rf[valid])) and np.array_equal(_bits(J_np[valid]), _bits(rJ[valid]))
+    with pytest.raises(RuntimeError):
+        ext.gradient_xy(t["cur_i"].cpu())
+
+
+def test_against_the_reference_extension_live(dev):
+    """Same device tensors into the reference's imgproc module and into ours; other sizes and parameters than the fixture."""
+    from difusion_b200 import synthetic as S
+    from difusion_b200.system import ext
+    im = _ref("imgproc")
+    sc = S.scene_S1(0.05)
+    for step, (fa, fb), mgs, mdd in ((2, (10, 13), 0.0, 0.2), (1, (40, 41), 1e-4, 0.05)):
+        (Ra, ta), (Rb, tb) = S.orbit_pose(fa), S.orbit_pose(fb)
+        rgb_a, d_a = S.render_rgbd(sc, Ra, ta, step=step)
+        rgb_b, d_b = S.render_rgbd(sc, Rb, tb, step=step, noise_sigma=0.002, seed=3)
+        ia, ib = _t(rgb_a.mean(-1), dev), _t(rgb_b.mean(-1), dev)
+        da, db = _t(d_a, dev), _t(d_b, dev)
+        K = np.array([[S.ICL_FX / step, 0, S.ICL_CX / step], [0, S.ICL_FY / step, S.ICL_CY / step], [0, 0, 1.0]])
+        Rd, td = Ra.T @ Rb, Ra.T @ (tb - ta)
+        intr = [K[0, 0], K[1, 1], K[0, 2], K[1, 2]]
+        krk, kt = (K @ Rd @ np.linalg.inv(K)).flatten().tolist(), (K @ td).flatten().tolist()
+        g_ours, g_ref = ext.gradient_xy(ib), im.gradient_xy(ib)
+        assert np.array_equal(_bits(g_ours.cpu().numpy()), _bits(g_ref.cpu().numpy()))
+        f1, J1 = ext.rgb_odometry(ia, da, ib, db, g_ours, intr, krk, kt, mgs, mdd, True)
+        f2, J2 = im.rgb_odometry(ia, da, ib, db, g_ref, intr, krk, kt, mgs, mdd, True)
+        f1, f2, J1, J2 = f1.cpu().numpy(), f2.cpu().numpy(), J1.cpu().numpy(), J2.cpu().numpy()
+        v = ~np.isnan(f2)
+        assert v.sum() > 2000 and np.array_equal(v, ~np.isnan(f1))
+        assert np.array_equal(_bits(f1[v]), _bits(f2[v])) and np.array_equal(_bits(J1[v]), _bits(J2[v]))
+        p1 = ext.unproject_depth(db, *intr)
+        p2 = im.unproject_depth(db, *intr)
+        ok = ~torch.isnan(db)
+        assert torch.equal(p1[ok].view(torch.int32), p2[ok].view(torch.int32)) and bool(torch.isnan(p1[~ok]).all())
+
+
+def test_unproject_against_golden(dev):
+    from difusion_b200.system import ext
+    from oracle import imgproc_oracle as O
+    fx = np.load(GOLDEN / "ref_ext_unproject.npz")
+    pc = ext.unproject_depth(_t(fx["depth"], dev), *[float(v) for v in fx["intr"]]).cpu().numpy()
+    assert np.array_equal(_bits(pc), _bits(fx["pc"]))
+    assert np.array_equal(_bits(O.unproject_depth(fx["depth"], *[float(v) for v in fx["intr"]])), _bits(fx["pc"]))
+
+
+class _Calib:
+    def __init__(self, fx, fy, cx, cy):
+        self.fx, self.fy, self.cx, self.cy = fx, fy, cx, cy
+
+    def to_K(self):
+        return np.asarray([[self.fx, 0.0, self.cx], [0.0, self.fy, self.cy], [0.0, 0.0, 1.0]])
+
+
+@pytest.mark.parametrize("robust,k", [(None, 0.01), ("huber", 0.004), ("tukey", 0.02)])
+def test_compute_rgb_Hg_matches_oracle(dev, robust, k):
+    """SDFTracker.compute_rgb_Hg (one fused launch) vs the numpy restatement of tracker.py:131-172 over the C oracle."""
+    from difusion_b200.system.tracker import SDFTracker
+    from difusion_b200.utils.motion_util import Isometry, Rotation
+    from oracle import imgproc_oracle as O
+    c, t = _photo_inputs(dev)
+    args = argparse.Namespace(sdf=dict(robust_kernel="huber", robust_k=5.0, subsample=0.5),
+                              rgb=dict(weight=500.0, robust_kernel=robust, robust_k=k, min_grad_scale=float(c["min_grad_scale"]), max_depth_delta=0.2),
+                              iter_config=[])
+    trk = SDFTracker(None, args)
+    from difusion_b200.system import ext
+    grad = ext.gradient_xy(t["cur_i"])
+    trk.last_intensity, trk.last_depth = [t["prev_i"]], [t["prev_d"]]
+    calib = _Calib(*[float(v) for v in c["intr"]])
+    delta = Isometry(q=Rotation(matrix=c["Rd"]), t=c["td"])
+    H, g, E = trk.compute_rgb_Hg(0, delta, [t["cur_i"]], [t["cur_d"]], [grad], calib)
+    oH, og, oE, oM = O.compute_rgb_Hg(c["prev_i"], c["prev_d"], c["cur_i"], c["cur_d"], grad.cpu().numpy(), c["intr"], calib.to_K(),
+                                      delta.q.rotation_matrix, delta.t, float(c["min_grad_scale"]), 0.2, 500.0, robust, k)
+    assert H.dtype == np.float64 and H.shape == (6, 6) and g.shape == (6,)
+    assert np.abs(H - oH).max() <= 2e-4 * np.abs(oH).max() and np.abs(g - og).max() <= 2e-4 * np.abs(og).max()
+    assert abs(E - oE) <= TOL * abs(oE)
+    _, _, E2 = trk.compute_rgb_Hg(0, delta, [t["cur_i"]], [t["cur_d"]], [grad], calib, no_grad=True)
+    assert E2 == E
+
+
+def test_rgb_gauss_newton_recovers_the_relative_pose(dev):
+    """track_camera's photometric Gauss-Newton (tracker.py:220-283 with ['rgb', level] terms) on two synthetic views."""
+    from difusion_b200 import synthetic as S
+    from difusion_b200.system.tracker import SDFTracker
+    from difusion_b200.utils.motion_util import Isometry, Rotation
+    sc = S.scene_S1(0.05)
+    (R0, t0), (R1, t1) = S.orbit_pose(20), S.orbit_pose(22)
+    rgb0, d0 = S.render_rgbd(sc, R0, t0, step=2)
+    rgb1, d1 = S.render_rgbd(sc, R1, t1, step=2)
+    calib = _Calib(S.ICL_FX / 2, S.ICL_FY / 2, S.ICL_CX / 2, S.ICL_CY / 2)
+    args = argparse.Namespace(sdf=dict(robust_kernel="huber", robust_k=5.0, subsample=0.5),
+                              rgb=dict(weight=500.0, robust_kernel=None, robust_k=0.01, min_grad_scale=0.0, max_depth_delta=0.2),
+                              iter_config=[{"n": 15, "type": [["rgb", 0]]}])
+    trk = SDFTracker(None, args)
+    i0, dd0, _ = trk._make_image_pyramid(_t(rgb0.mean(-1), dev), _t(d0, dev))
+    i1, dd1, g1 = trk._make_image_pyramid(_t(rgb1.mean(-1), dev), _t(d1, dev))
+    assert [tuple(x.shape) for x in i1] == [(240, 320), (120, 160), (60, 80)] and g1[2].shape == (60, 80, 2)
+    trk.last_intensity, trk.last_depth = i0, dd0
+    p0 = Isometry(q=Rotation(matrix=R0), t=t0)
+    trk.all_pd_pose.append(p0)
+    est = trk.gauss_newton(p0, i1, dd1, g1, None, calib)
+    err0 = np.linalg.norm(t1 - t0)
+    err = np.linalg.norm(est.t - t1)
+    ang = np.arccos(np.clip((np.trace(est.q.rotation_matrix.T @ R1) - 1) / 2, -1, 1))
+    ang0 = np.arccos(np.clip((np.trace(R0.T @ R1) - 1) / 2, -1, 1))
+    assert err < 0.35 * err0 and ang < 0.35 * ang0, (err, err0, ang, ang0)
+
+
+def test_point_box_filter_matches_restatement(dev):
+    """tracker.point_box_filter (tracker.py:13-23): same cells, same row order, means within fp32 summation noise."""
+    from difusion_b200 import synthetic as S
+    from difusion_b200.system import ext
+    from difusion_b200.system.tracker import point_box_filter
+    sc = S.scene_S1(0.05)
+    R, t = S.orbit_pose(5)
+    pc, nc = S.frame_points(sc, R, t, box=0.0)                       # raw unprojected cloud, ~75 k points
+    for pts, nrm, vs in ((pc, nc, 0.02), (pc[:5000] * np.float32(3.0), nc[:5000], 0.05), (pc[:1], nc[:1], 0.02)):
+        exp_p, exp_n = S.box_filter(pts, nrm, vs)
+        out_p, out_n = point_box_filter(_t(pts, dev), _t(nrm, dev), vs)
+        assert out_p.shape == exp_p.shape and out_n.shape == exp_n.shape
+        assert np.abs(out_p.cpu().numpy() - exp_p).max() <= 2e-6 * max(1.0, np.abs(exp_p).max())
+        assert np.abs(out_n.cpu().numpy() - exp_n).max() <= 2e-6
+    a, b = ext.point_box_filter(_t(pc, dev), _t(nc, dev), 0.02)     # scratch is self-cleaning: a second call gives the same rows
+    c, d = ext.point_box_filter(_t(pc, dev), _t(nc, dev), 0.02)
+    assert a.shape == c.shape and float((a - c).abs().max()) <= 1e-6
+    with pytest.raises(RuntimeError):
+        ext.point_box_filter(_t(pc, dev).cpu(), _t(nc, dev), 0.02)
