@@ -58,6 +58,9 @@ SIGNATURES = {
     "dif_unproject_depth": (C.c_int, [_P, C.c_int, C.c_int, _F, _F, _F, _F, _P, _P]),
     "dif_box_filter_scratch_bytes": (_SZ, [_I64, _I64]),
     "dif_point_box_filter": (C.c_int, [_P, _P, _I64, _F, _I64, _P, _P, _P, _P, _SZ, _P]),
+    "dif_knn_scratch_bytes": (_SZ, [_I64, _I64]),
+    "dif_remove_radius_outlier": (C.c_int, [_P, C.c_int, _I64, C.c_int, _F, _I64, _P, _P, _P, _SZ, _P]),
+    "dif_estimate_normals": (C.c_int, [_P, C.c_int, _I64, C.c_int, _F, _FP, _I64, _P, _P, _P, _SZ, _P]),
     "dif_gradient_xy": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "dif_rgb_odometry": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _FP, _FP, _FP, _F, _F, _P, _P, _P]),
     "dif_rgb_scratch_bytes": (_SZ, []),

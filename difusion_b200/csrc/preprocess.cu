@@ -243,3 +243,327 @@ int dif_point_box_filter(const float* points, const float* normals, int64_t n, f
 }
 
 }  // extern "C"
+
+// ================================================================================================ 16-NN ops (pcproc.cu:98-220)
+// remove_radius_outlier and estimate_normals of the reference build a thrust kd-tree per call (cuda_kdtree.cu:644-1239) and run
+// an exact k-NN search.  Both only ever look at neighbours closer than a fixed radius (5 cm / 10 cm), so an exact answer comes
+// from a uniform grid with cell edge = radius: counting sort of the points into cells (count, ordered scan, fill), then every
+// query scans the 27 cells around it.  Distances are evaluated as the kd-tree does (CudaL2::dist = dot(diff, diff), contracted by
+// nvcc to fma(dz,dz,fma(dy,dy,dx*dx))); ties are broken by point index, which makes the result deterministic.
+namespace dif {
+
+struct KnnGrid {                        // device-resident header in the scratch buffer
+    float mn[3], mx[3];
+    int n[3];
+    int overflow;
+    unsigned long long n_words;         // (reused BoxState layout up to here: box_minmax_kernel fills mn/mx)
+    int n_cells;
+};
+static_assert(sizeof(KnnGrid) == sizeof(BoxState), "KnnGrid mirrors BoxState so the min/max kernels can be shared");
+
+__global__ void knn_minmax_kernel(const float* __restrict__ p, int stride, int n, BoxState* s) {
+    float mn[3] = {__int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0x7f800000)};
+    float mx[3] = {__int_as_float(0xff800000), __int_as_float(0xff800000), __int_as_float(0xff800000)};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { const float v = p[(size_t)stride * i + k]; mn[k] = fminf(mn[k], v); mx[k] = fmaxf(mx[k], v); }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        for (int o = 16; o; o >>= 1) { mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o)); mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o)); }
+        if ((threadIdx.x & 31) == 0) { atomic_min_f(&s->mn[k], mn[k]); atomic_max_f(&s->mx[k], mx[k]); }
+    }
+}
+
+__global__ void knn_dims_kernel(BoxState* s, float cell, long long max_cells) {
+    long long cells = 1;
+    for (int k = 0; k < 3; ++k) {
+        const long long nk = (long long)floorf((s->mx[k] - s->mn[k]) / cell) + 1;
+        s->n[k] = (int)(nk > 0 ? nk : 1);
+        cells *= s->n[k];
+    }
+    s->n_cells = (int)cells;
+    if (cells > max_cells) { s->overflow = 1; s->n_cells = 0; }
+}
+
+__device__ __forceinline__ int knn_axis(const BoxState* s, float v, int k, float cell) {
+    int c = (int)floorf((v - s->mn[k]) / cell);
+    return c < 0 ? 0 : (c >= s->n[k] ? s->n[k] - 1 : c);
+}
+__device__ __forceinline__ int knn_cell(const BoxState* s, const float* p, float cell) {
+    return (knn_axis(s, p[0], 0, cell) * s->n[1] + knn_axis(s, p[1], 1, cell)) * s->n[2] + knn_axis(s, p[2], 2, cell);
+}
+
+__global__ void knn_count_kernel(const float* __restrict__ p, int stride, int n, const BoxState* __restrict__ s, float cell, uint32_t* __restrict__ cell_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || s->overflow) return;
+    atomicAdd(cell_count + knn_cell(s, p + (size_t)stride * i, cell), 1u);
+}
+
+// exclusive scan of cell_count (in place -> cell_start), same three-pass scheme as the box filter
+__global__ void __launch_bounds__(BOX_SCAN_T) knn_scan1_kernel(uint32_t* __restrict__ cells, const BoxState* __restrict__ s, uint32_t* __restrict__ chunk_sum) {
+    __shared__ uint32_t s_warp[BOX_SCAN_T / 32];
+    __shared__ uint32_t s_run;
+    const long long n_cells = s->n_cells;
+    const long long base = (long long)blockIdx.x * BOX_SCAN_W;
+    if (base >= n_cells) return;
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    for (int k = 0; k < BOX_SCAN_W / BOX_SCAN_T; ++k) {
+        const long long w = base + (long long)k * BOX_SCAN_T + threadIdx.x;
+        const uint32_t c = w < n_cells ? cells[w] : 0;
+        uint32_t incl = c;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += u; }
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        uint32_t wpre = 0, tot = 0;
+        for (int q = 0; q < BOX_SCAN_T / 32; ++q) { const uint32_t t = s_warp[q]; if (q < (int)(threadIdx.x >> 5)) wpre += t; tot += t; }
+        const uint32_t run = s_run;
+        if (w < n_cells) cells[w] = run + wpre + incl - c;
+        __syncthreads();
+        if (threadIdx.x == 0) s_run = run + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) chunk_sum[blockIdx.x] = s_run;
+}
+
+__global__ void __launch_bounds__(1024) knn_scan2_kernel(uint32_t* __restrict__ chunk_sum, const BoxState* __restrict__ s) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const long long n_chunks = ((long long)s->n_cells + BOX_SCAN_W - 1) / BOX_SCAN_W;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (long long c0 = 0; c0 < n_chunks; c0 += 1024) {
+        const long long c = c0 + threadIdx.x;
+        const uint32_t v = c < n_chunks ? chunk_sum[c] : 0;
+        uint32_t incl = v;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += u; }
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        uint32_t wpre = 0, tot = 0;
+        for (int q = 0; q < 32; ++q) { const uint32_t t = s_warp[q]; if (q < (int)(threadIdx.x >> 5)) wpre += t; tot += t; }
+        const uint32_t carry = s_carry;
+        if (c < n_chunks) chunk_sum[c] = carry + wpre + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + tot;
+        __syncthreads();
+    }
+}
+
+// cell_start[c] = chunk offset + in-chunk offset; cell_fill[c] = same (cursor used by the fill pass)
+__global__ void knn_offsets_kernel(uint32_t* __restrict__ cell_start, uint32_t* __restrict__ cell_fill, const uint32_t* __restrict__ chunk_sum,
+                                   const BoxState* __restrict__ s) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= s->n_cells) return;
+    const uint32_t v = cell_start[c] + chunk_sum[c / BOX_SCAN_W];
+    cell_start[c] = v; cell_fill[c] = v;
+}
+
+__global__ void knn_fill_kernel(const float* __restrict__ p, int stride, int n, const BoxState* __restrict__ s, float cell,
+                                uint32_t* __restrict__ cell_fill, int* __restrict__ sorted_idx, float4* __restrict__ sorted_pt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || s->overflow) return;
+    const float* q = p + (size_t)stride * i;
+    const uint32_t dst = atomicAdd(cell_fill + knn_cell(s, q, cell), 1u);
+    sorted_idx[dst] = i;
+    sorted_pt[dst] = make_float4(q[0], q[1], q[2], __int_as_float(i));
+}
+
+// after the fill pass cell_fill[c] == end of cell c.  The last kernel of a call zeroes both cell arrays over the bounding box again
+// (the scan wrote a prefix into every cell of the box, occupied or not), so the scratch is all-zero between calls.
+__global__ void knn_clear_kernel(const BoxState* __restrict__ s, uint32_t* __restrict__ cell_start, uint32_t* __restrict__ cell_fill) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= s->n_cells) return;
+    cell_start[c] = 0u; cell_fill[c] = 0u;
+}
+
+__device__ __forceinline__ float knn_d2(float qx, float qy, float qz, float4 b) {
+    const float dx = __fsub_rn(qx, b.x), dy = __fsub_rn(qy, b.y), dz = __fsub_rn(qz, b.z);
+    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+
+// pcproc.cu:98-105 + :172-196: mask = (16th smallest squared distance, the point itself included) < radius^2
+//                              <=> at least nb_points points (itself included) lie strictly inside the radius.
+__global__ void radius_count_kernel(const float* __restrict__ p, int stride, int n, const BoxState* __restrict__ s, float cell,
+                                    const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end,
+                                    const float4* __restrict__ sorted_pt, int nb_points, float r2, uint8_t* __restrict__ mask) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || s->overflow) return;
+    const float* q = p + (size_t)stride * i;
+    const float qx = q[0], qy = q[1], qz = q[2];
+    const int cx = knn_axis(s, qx, 0, cell), cy = knn_axis(s, qy, 1, cell), cz = knn_axis(s, qz, 2, cell);
+    int found = 0;
+    for (int ox = -1; ox <= 1 && found < nb_points; ++ox) {
+        const int x = cx + ox; if (x < 0 || x >= s->n[0]) continue;
+        for (int oy = -1; oy <= 1 && found < nb_points; ++oy) {
+            const int y = cy + oy; if (y < 0 || y >= s->n[1]) continue;
+            const int z0 = max(cz - 1, 0), z1 = min(cz + 1, s->n[2] - 1);          // cells along z are contiguous: one run
+            const int c0 = (x * s->n[1] + y) * s->n[2];
+            const uint32_t b = cell_start[c0 + z0], e = cell_end[c0 + z1];
+            for (uint32_t j = b; j < e && found < nb_points; ++j) found += knn_d2(qx, qy, qz, sorted_pt[j]) < r2;
+        }
+    }
+    mask[i] = found >= nb_points;
+}
+
+// Closed-form eigen-decomposition of a symmetric 3x3 matrix (rows x1, x2, x3): returns the unit eigenvector of the SMALLEST
+// eigenvalue.  Same formulas, operation order and float/double mix as the reference's sym3eig (pcproc.cu:21-96) so that both
+// compile to the same arithmetic: trigonometric eigenvalue, then the largest cross product of two rows of (A - lambda I).
+__device__ float3 smallest_eigenvector(float3 x1, float3 x2, float3 x3) {
+    const float p1 = x1.y * x1.y + x1.z * x1.z + x2.z * x2.z;
+    const float q = (x1.x + x2.y + x3.z) / 3.0f;
+    const float p2 = (x1.x - q) * (x1.x - q) + (x2.y - q) * (x2.y - q) + (x3.z - q) * (x3.z - q) + 2 * p1;
+    const float p = sqrt(p2 / 6.0f);
+    const float ip = 1.0f / p;
+    const float b11 = ip * (x1.x - q), b12 = ip * x1.y, b13 = ip * x1.z;
+    const float b21 = ip * x2.x, b22 = ip * (x2.y - q), b23 = ip * x2.z;
+    const float b31 = ip * x3.x, b32 = ip * x3.y, b33 = ip * (x3.z - q);
+    float r = b11 * b22 * b33 + b12 * b23 * b31 + b13 * b21 * b32 - b13 * b22 * b31 - b12 * b21 * b33 - b11 * b23 * b32;
+    r = r / 2.0f;
+    float phi;
+    if (r <= -1) phi = M_PI / 3.0f;
+    else if (r >= 1) phi = 0;
+    else phi = acos(r) / 3.0f;
+    const float lam = q + 2 * p * cos(phi + (2 * M_PI / 3));           // double arithmetic, rounded once (as in the reference)
+    x1.x -= lam; x2.y -= lam; x3.z -= lam;
+    const float3 r12 = make_float3(x1.y * x2.z - x1.z * x2.y, x1.z * x2.x - x1.x * x2.z, x1.x * x2.y - x1.y * x2.x);
+    const float3 r13 = make_float3(x1.y * x3.z - x1.z * x3.y, x1.z * x3.x - x1.x * x3.z, x1.x * x3.y - x1.y * x3.x);
+    const float3 r23 = make_float3(x2.y * x3.z - x2.z * x3.y, x2.z * x3.x - x2.x * x3.z, x2.x * x3.y - x2.y * x3.x);
+    const float d1 = r12.x * r12.x + r12.y * r12.y + r12.z * r12.z;
+    const float d2 = r13.x * r13.x + r13.y * r13.y + r13.z * r13.z;
+    const float d3 = r23.x * r23.x + r23.y * r23.y + r23.z * r23.z;
+    float d_max = d1; int i_max = 0;
+    if (d2 > d_max) { d_max = d2; i_max = 1; }
+    if (d3 > d_max) i_max = 2;
+    if (i_max == 0) return make_float3(r12.x / sqrt(d1), r12.y / sqrt(d1), r12.z / sqrt(d1));
+    if (i_max == 1) return make_float3(r13.x / sqrt(d2), r13.y / sqrt(d2), r13.z / sqrt(d2));
+    return make_float3(r23.x / sqrt(d3), r23.y / sqrt(d3), r23.z / sqrt(d3));
+}
+
+// pcproc.cu:107-170 + :198-220.  k nearest (the point itself included, KNN_MAX >= max_nn) by (distance, index); entry 0 is skipped
+// like the reference's loop from nn_i = 1; neighbours beyond the radius end the list; fewer than 5 -> NaN normal.
+constexpr int KNN_MAX = 32;
+
+__global__ void __launch_bounds__(128) estimate_normals_kernel(const float* __restrict__ p, int stride, int n, const BoxState* __restrict__ s, float cell,
+                                                                const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end,
+                                                                const float4* __restrict__ sorted_pt, int max_nn, float r2, float3 cam,
+                                                                float* __restrict__ normal_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || s->overflow) return;
+    const float* q = p + (size_t)stride * i;
+    const float qx = q[0], qy = q[1], qz = q[2];
+    const int cx = knn_axis(s, qx, 0, cell), cy = knn_axis(s, qy, 1, cell), cz = knn_axis(s, qz, 2, cell);
+    float bd[KNN_MAX]; uint32_t bj[KNN_MAX];        // ascending by (distance, original index); bj = position in sorted_pt
+    int bi[KNN_MAX];
+    int cnt = 0;
+    for (int ox = -1; ox <= 1; ++ox) {
+        const int x = cx + ox; if (x < 0 || x >= s->n[0]) continue;
+        for (int oy = -1; oy <= 1; ++oy) {
+            const int y = cy + oy; if (y < 0 || y >= s->n[1]) continue;
+            const int z0 = max(cz - 1, 0), z1 = min(cz + 1, s->n[2] - 1);
+            const int c0 = (x * s->n[1] + y) * s->n[2];
+            const uint32_t b = cell_start[c0 + z0], e = cell_end[c0 + z1];
+            for (uint32_t j = b; j < e; ++j) {
+                const float4 c = sorted_pt[j];
+                const float d = knn_d2(qx, qy, qz, c);
+                if (!(d < r2)) continue;                                   // outside the radius: can never be used (:126,147)
+                const int ci = __float_as_int(c.w);
+                if (cnt == max_nn && !(d < bd[cnt - 1] || (d == bd[cnt - 1] && ci < bi[cnt - 1]))) continue;
+                int k = cnt < max_nn ? cnt : max_nn - 1;                   // insertion from the back
+                while (k > 0 && (d < bd[k - 1] || (d == bd[k - 1] && ci < bi[k - 1]))) { bd[k] = bd[k - 1]; bj[k] = bj[k - 1]; bi[k] = bi[k - 1]; --k; }
+                bd[k] = d; bj[k] = j; bi[k] = ci;
+                if (cnt < max_nn) ++cnt;
+            }
+        }
+    }
+    const float qnan = __int_as_float(0x7fc00000);
+    float3 mean = make_float3(0.f, 0.f, 0.f);
+    float valid = 0.f;
+    for (int k = 1; k < cnt; ++k) { const float4 c = sorted_pt[bj[k]]; mean.x += c.x; mean.y += c.y; mean.z += c.z; valid += 1.0f; }
+    if (valid < 5.0f) { normal_out[3 * i] = normal_out[3 * i + 1] = normal_out[3 * i + 2] = qnan; return; }
+    mean.x /= valid; mean.y /= valid; mean.z /= valid;
+    float3 c1 = make_float3(0.f, 0.f, 0.f), c2 = c1, c3 = c1;
+    for (int k = 1; k < cnt; ++k) {
+        const float4 c = sorted_pt[bj[k]];
+        const float3 d = make_float3(c.x - mean.x, c.y - mean.y, c.z - mean.z);
+        c1.x += d.x * d.x; c1.y += d.x * d.y; c1.z += d.x * d.z;
+        c2.x += d.y * d.x; c2.y += d.y * d.y; c2.z += d.y * d.z;
+        c3.x += d.z * d.x; c3.y += d.z * d.y; c3.z += d.z * d.z;
+    }
+    float3 nrm = smallest_eigenvector(c1, c2, c3);
+    if (nrm.x * (qx - cam.x) + nrm.y * (qy - cam.y) + nrm.z * (qz - cam.z) > 0.0f) { nrm.x = -nrm.x; nrm.y = -nrm.y; nrm.z = -nrm.z; }
+    normal_out[3 * i] = nrm.x; normal_out[3 * i + 1] = nrm.y; normal_out[3 * i + 2] = nrm.z;
+}
+
+struct KnnPlan { BoxState* s; uint32_t *cell_start, *cell_fill, *chunk_sum; int* sorted_idx; float4* sorted_pt; long long max_cells; };
+
+static size_t knn_scratch_bytes(int64_t n, int64_t max_cells) {
+    return 256 + 2 * align_up((size_t)(max_cells + 1) * 4) + align_up((size_t)(max_cells / BOX_SCAN_W + 2) * 4) + align_up((size_t)n * 4) + align_up((size_t)n * 16) + 256;
+}
+
+// builds the cell lists for `n` points; returns the plan (device pointers inside `scratch`)
+static KnnPlan knn_build(const float* p, int stride, int n, float cell, int64_t max_cells, void* scratch, cudaStream_t st) {
+    Carver c(scratch);
+    KnnPlan k;
+    k.s = c.take<BoxState>(1);
+    k.cell_start = c.take<uint32_t>(max_cells + 1);                 // zero on entry / exit
+    k.cell_fill = c.take<uint32_t>(max_cells + 1);                  // zero on entry / exit
+    k.chunk_sum = c.take<uint32_t>(max_cells / BOX_SCAN_W + 2);
+    k.sorted_idx = c.take<int>(n);
+    k.sorted_pt = c.take<float4>(n);
+    k.max_cells = max_cells;
+    const unsigned gp = (unsigned)((n + 255) / 256);
+    box_init_kernel<<<1, 1, 0, st>>>(k.s);
+    knn_minmax_kernel<<<DIF_NUM_SMS, 256, 0, st>>>(p, stride, n, k.s);
+    knn_dims_kernel<<<1, 1, 0, st>>>(k.s, cell, max_cells);
+    knn_count_kernel<<<gp, 256, 0, st>>>(p, stride, n, k.s, cell, k.cell_start);
+    const unsigned chunks = (unsigned)((max_cells + BOX_SCAN_W - 1) / BOX_SCAN_W);
+    knn_scan1_kernel<<<chunks, BOX_SCAN_T, 0, st>>>(k.cell_start, k.s, k.chunk_sum);
+    knn_scan2_kernel<<<1, 1024, 0, st>>>(k.chunk_sum, k.s);
+    knn_offsets_kernel<<<(unsigned)((max_cells + 255) / 256), 256, 0, st>>>(k.cell_start, k.cell_fill, k.chunk_sum, k.s);
+    knn_fill_kernel<<<gp, 256, 0, st>>>(p, stride, n, k.s, cell, k.cell_fill, k.sorted_idx, k.sorted_pt);
+    DIF_COUNT_LAUNCH(8);
+    return k;
+}
+
+}  // namespace dif
+
+extern "C" {
+
+size_t dif_knn_scratch_bytes(int64_t max_points, int64_t max_cells) { return dif::knn_scratch_bytes(max_points, max_cells); }
+
+int dif_remove_radius_outlier(const float* pc, int stride, int64_t n, int nb_points, float radius, int64_t max_cells,
+                              uint8_t* mask_out, int32_t* status_dev, void* scratch, size_t scratch_bytes, void* stream) {
+    if (n < 0 || n >= (int64_t(1) << 31) || stride < 3 || nb_points < 1 || !(radius > 0.f) || max_cells <= 0 || !scratch || !status_dev) return DIF_E_INVALID;
+    if (n > 0 && (!pc || !mask_out)) return DIF_E_INVALID;
+    if (scratch_bytes < dif::knn_scratch_bytes(n, max_cells)) return DIF_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) { cudaMemsetAsync(status_dev, 0, 4, st); return check_launch("dif_remove_radius_outlier"); }
+    const unsigned gp = (unsigned)((n + 255) / 256);
+    dif::KnnPlan k = dif::knn_build(pc, stride, (int)n, radius, max_cells, scratch, st);
+    dif::radius_count_kernel<<<gp, 256, 0, st>>>(pc, stride, (int)n, k.s, radius, k.cell_start, k.cell_fill, k.sorted_pt, nb_points,
+                                                 radius * radius, mask_out);
+    dif::knn_clear_kernel<<<(unsigned)((max_cells + 255) / 256), 256, 0, st>>>(k.s, k.cell_start, k.cell_fill);
+    cudaMemcpyAsync(status_dev, &k.s->overflow, 4, cudaMemcpyDeviceToDevice, st);
+    DIF_COUNT_LAUNCH(2);
+    return check_launch("dif_remove_radius_outlier");
+}
+
+int dif_estimate_normals(const float* pc, int stride, int64_t n, int max_nn, float radius, const float* cam_xyz, int64_t max_cells,
+                         float* normal_out, int32_t* status_dev, void* scratch, size_t scratch_bytes, void* stream) {
+    if (n < 0 || n >= (int64_t(1) << 31) || stride < 3 || max_nn < 2 || max_nn > dif::KNN_MAX || !(radius > 0.f) || max_cells <= 0 || !scratch ||
+        !status_dev || !cam_xyz) return DIF_E_INVALID;
+    if (n > 0 && (!pc || !normal_out)) return DIF_E_INVALID;
+    if (scratch_bytes < dif::knn_scratch_bytes(n, max_cells)) return DIF_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) { cudaMemsetAsync(status_dev, 0, 4, st); return check_launch("dif_estimate_normals"); }
+    const unsigned gp = (unsigned)((n + 255) / 256);
+    dif::KnnPlan k = dif::knn_build(pc, stride, (int)n, radius, max_cells, scratch, st);
+    dif::estimate_normals_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(pc, stride, (int)n, k.s, radius, k.cell_start, k.cell_fill, k.sorted_pt,
+                                                                                max_nn, radius * radius, make_float3(cam_xyz[0], cam_xyz[1], cam_xyz[2]), normal_out);
+    dif::knn_clear_kernel<<<(unsigned)((max_cells + 255) / 256), 256, 0, st>>>(k.s, k.cell_start, k.cell_fill);
+    cudaMemcpyAsync(status_dev, &k.s->overflow, 4, cudaMemcpyDeviceToDevice, st);
+    DIF_COUNT_LAUNCH(2);
+    return check_launch("dif_estimate_normals");
+}
+
+}  // extern "C"

@@ -119,9 +119,46 @@ def point_box_filter(points: torch.Tensor, normals: torch.Tensor, voxel_size: fl
     return out_p[:m], out_n[:m]
 
 
+_KNN_MAX_CELLS = 1 << 23                 # cell edge = search radius: 5 cm cells cover a ~10 m cube of bounding box
+_knn_scratch = {}
+
+
+def _knn_buffers(dev, n):
+    L = _lib.lib()
+    sc = _knn_scratch.get(dev)
+    if sc is None or sc[1] < n:
+        cap = max(n, 1 << 17)
+        sc = (torch.zeros(L.dif_knn_scratch_bytes(cap, _KNN_MAX_CELLS), dtype=torch.uint8, device=dev), cap)
+        _knn_scratch[dev] = sc
+    return sc[0]
+
+
 def remove_radius_outlier(input_pc: torch.Tensor, nb_points: int, radius: float):
-    raise NotImplementedError("remove_radius_outlier (pcproc.cu:172-196, kd-tree 16-NN) - SURVEY 8 f-1, not built yet")
+    """(N,4) [or (N,3)] f32 -> (N,) bool: the nb_points-th nearest point (self included) lies within `radius` (pcproc.cu:172-196)."""
+    _check_input(input_pc, "input_pc")
+    dev, n = input_pc.device, input_pc.size(0)
+    sc = _knn_buffers(dev, n)
+    mask = torch.empty(n, dtype=torch.uint8, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.check(_lib.lib().dif_remove_radius_outlier(input_pc.data_ptr(), input_pc.size(1), n, int(nb_points), float(radius), _KNN_MAX_CELLS,
+                                                    mask.data_ptr(), status.data_ptr(), sc.data_ptr(), sc.numel(), _lib.stream_ptr(dev)),
+               "dif_remove_radius_outlier")
+    if int(status.item()):
+        raise RuntimeError("remove_radius_outlier: the cloud's bounding box exceeds the neighbour grid budget")
+    return mask.view(torch.bool)
 
 
 def estimate_normals(input_pc: torch.Tensor, max_nn: int, radius: float, cam_xyz):
-    raise NotImplementedError("estimate_normals (pcproc.cu:198-220, kd-tree 16-NN + PCA) - SURVEY 8 f-1, not built yet")
+    """(N,4) [or (N,3)] f32 -> (N,3) f32 PCA normals over the <= max_nn-1 nearest neighbours within `radius`, oriented towards
+    cam_xyz; NaN rows where fewer than 5 neighbours exist (pcproc.cu:107-170,198-220)."""
+    _check_input(input_pc, "input_pc")
+    dev, n = input_pc.device, input_pc.size(0)
+    sc = _knn_buffers(dev, n)
+    normals = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.check(_lib.lib().dif_estimate_normals(input_pc.data_ptr(), input_pc.size(1), n, int(max_nn), float(radius), _lib.host_floats(cam_xyz),
+                                               _KNN_MAX_CELLS, normals.data_ptr(), status.data_ptr(), sc.data_ptr(), sc.numel(),
+                                               _lib.stream_ptr(dev)), "dif_estimate_normals")
+    if int(status.item()):
+        raise RuntimeError("estimate_normals: the cloud's bounding box exceeds the neighbour grid budget")
+    return normals

@@ -172,7 +172,19 @@ int dif_mesh_cache_merge(const float* cache_tri, const int64_t* cache_id, const 
  * dif_point_box_filter: tracker.point_box_filter (:13-23): mean point / mean normal per voxel_size cell of the frame's bounding box,
  *   rows in ascending cell-key order (== torch.unique's order).  out_* hold up to n rows; *n_out_dev = rows written, or -1 when
  *   the bounding box has more than max_cells cells.  scratch: dif_box_filter_scratch_bytes(max n, max_cells) bytes, zero-filled
- *   ONCE by the caller and left zeroed by every call. */
+ *   ONCE by the caller and left zeroed by every call.
+ * dif_remove_radius_outlier: ext op remove_radius_outlier (pcproc.cu:98-105,172-196): mask[i] = the nb_points-th nearest point
+ *   (i itself included) is closer than radius.  pc: rows of `stride` floats (the reference passes (N,4) rows), xyz first.
+ * dif_estimate_normals: ext op estimate_normals (pcproc.cu:107-170,198-220): PCA normal of the <= max_nn - 1 nearest neighbours
+ *   within radius (max_nn <= 32), NaN if fewer than 5, flipped towards cam_xyz (host float[3]).
+ *   Both replace the reference's per-call kd-tree (cuda_kdtree.cu) by a uniform grid of cell edge = radius over the frame's
+ *   bounding box; *status_dev = 1 when that box has more than max_cells cells (outputs are then undefined).
+ *   scratch: dif_knn_scratch_bytes(max n, max_cells), zero-filled ONCE by the caller, left zeroed by every call. */
+size_t dif_knn_scratch_bytes(int64_t max_points, int64_t max_cells);
+int dif_remove_radius_outlier(const float* pc, int stride, int64_t n, int nb_points, float radius, int64_t max_cells,
+                              uint8_t* mask_out, int32_t* status_dev, void* scratch, size_t scratch_bytes, void* stream);
+int dif_estimate_normals(const float* pc, int stride, int64_t n, int max_nn, float radius, const float* cam_xyz, int64_t max_cells,
+                         float* normal_out /*[n][3]*/, int32_t* status_dev, void* scratch, size_t scratch_bytes, void* stream);
 int dif_unproject_depth(const float* depth, int h, int w, float fx, float fy, float cx, float cy, float* pc_out /*[h][w][3]*/, void* stream);
 size_t dif_box_filter_scratch_bytes(int64_t max_points, int64_t max_cells);
 int dif_point_box_filter(const float* points /*[n][3]*/, const float* normals /*[n][3]*/, int64_t n, float voxel_size, int64_t max_cells,

@@ -9,6 +9,7 @@ Fixtures (inputs AND reference outputs are stored, so the CPU tests need neither
   ref_ext_groupby.npz      groupby_sum (ext/indexing/indexing.cu:59-109)
   ref_ext_photo.npz        gradient_xy + rgb_odometry (ext/imgproc/photometric.cu) on two 160x120 synthetic RGB-D views of scene S1
   ref_ext_unproject.npz    unproject_depth (ext/imgproc/imgproc.cu:5-44)
+  ref_ext_pcproc.npz       remove_radius_outlier + estimate_normals (ext/pcproc/pcproc.cu) on a noisy 160x120 view of scene S1
 The reference ships no vectors of its own, so these executions are the pin for the two CUDA-only ops.
 """
 import sys
@@ -65,6 +66,23 @@ def photo_case():
     return out
 
 
+def cloud_case(step: int = 4, noise: float = 0.004, seed: int = 11):
+    """The point cloud track_camera hands to the kd-tree ops (tracker.py:92-104): unprojected sub-sampled depth, (N,4) rows."""
+    from difusion_b200 import synthetic as S
+    sc = S.scene_S1(0.05)
+    R, t = S.orbit_pose(30)
+    depth, _ = S.render_depth(sc, R, t, noise_sigma=noise, seed=seed, step=step)
+    rng = np.random.default_rng(seed)
+    depth = depth.copy()
+    fly = rng.random(depth.shape) < 0.01                      # isolated flying pixels: what the radius filter is for
+    depth[fly] = depth[fly] * np.float32(0.8)
+    h, w = depth.shape
+    fx, fy, cx, cy = (np.float32(S.ICL_FX / step), np.float32(S.ICL_FY / step), np.float32(S.ICL_CX / step), np.float32(S.ICL_CY / step))
+    uu, vv = np.meshgrid(np.arange(w, dtype=np.float32), np.arange(h, dtype=np.float32))
+    pc = np.stack([(uu - cx) / fx * depth, (vv - cy) / fy * depth, depth, np.zeros_like(depth)], -1).reshape(-1, 4)
+    return np.ascontiguousarray(pc[~np.isnan(pc[:, 0])].astype(np.float32))
+
+
 def canon(tri, fid, std):
     """Canonical order: by PLIVox id, then by the 9 vertex coordinates (exact floats)."""
     key = np.concatenate([fid[:, None].astype(np.float64), tri.reshape(len(tri), 9).astype(np.float64)], 1)
@@ -114,6 +132,19 @@ def main():
     pc[np.isnan(depth)] = np.nan                           # only x = NaN is written for invalid pixels (imgproc.cu:21)
     np.savez_compressed(out / "ref_ext_unproject.npz", depth=depth, intr=c["intr"], pc=pc)
     print("unproject:", pc.shape)
+    pp = build_ref.load_module("pcproc")
+    cloud = cloud_case()
+    d_cloud = torch.from_numpy(cloud).to(dev)
+    res = {}
+    for tag, radius in (("r5", 0.05), ("r8", 0.08)):           # 0.05 is the tracker's setting; at 160x120 it rejects most points
+        mask = pp.remove_radius_outlier(d_cloud, 16, radius)
+        kept = d_cloud[mask].contiguous()
+        normals = pp.estimate_normals(kept, 16, 2 * radius, [0.0, 0.0, 0.0])
+        res[f"{tag}.radius"] = np.float32(radius)
+        res[f"{tag}.mask"] = mask.cpu().numpy()
+        res[f"{tag}.normals"] = normals.cpu().numpy()
+        print(f"pcproc radius {radius}: kept {int(mask.sum())} of {cloud.shape[0]}, NaN normals {int(torch.isnan(normals[:, 0]).sum())}")
+    np.savez_compressed(out / "ref_ext_pcproc.npz", cloud=cloud, **res)
 
 
 if __name__ == "__main__":

@@ -186,3 +186,79 @@ def test_point_box_filter_matches_restatement(dev):
     assert a.shape == c.shape and float((a - c).abs().max()) <= 1e-6
     with pytest.raises(RuntimeError):
         ext.point_box_filter(_t(pc, dev).cpu(), _t(nc, dev), 0.02)
+
+
+def _normal_agreement(a, b):
+    """(fraction of rows whose NaN-ness differs, fraction of common rows whose angle exceeds 1e-3 rad)."""
+    na, nb = np.isnan(a[:, 0]), np.isnan(b[:, 0])
+    both = ~na & ~nb
+    cosang = np.abs((a[both].astype(np.float64) * b[both]).sum(1))
+    return float((na != nb).mean()), float((cosang < np.cos(1e-3)).mean())
+
+
+@pytest.mark.parametrize("radius", [0.05, 0.08])
+def test_knn_ops_against_reference_extension_and_oracle(dev, radius):
+    """remove_radius_outlier / estimate_normals: uniform-grid k-NN vs the reference's CUDA kd-tree executed on the same tensors
+    (mask bit-exact; normals to 1e-3 rad except where equal-distance ties or a 1-ulp radius test change the neighbour set) and vs
+    the scipy/numpy oracle."""
+    from difusion_b200.system import ext
+    from golden.make_golden_gpu import cloud_case
+    from oracle import pcproc_oracle as P
+    cloud = cloud_case()
+    d_cloud = _t(cloud, dev)
+    mask = ext.remove_radius_outlier(d_cloud, 16, radius)
+    m_np = mask.cpu().numpy()
+    assert mask.dtype == torch.bool and 0 < m_np.sum() < cloud.shape[0]
+    o_mask = P.remove_radius_outlier(cloud, 16, radius)
+    assert (m_np != o_mask).mean() <= 1e-3
+    kept = d_cloud[mask].contiguous()
+    normals = ext.estimate_normals(kept, 16, 2 * radius, [0.0, 0.0, 0.0])
+    n_np = normals.cpu().numpy()
+    ok = ~np.isnan(n_np[:, 0])
+    assert ok.mean() > 0.9 and np.abs(np.linalg.norm(n_np[ok], axis=1) - 1).max() < 1e-5
+    assert ((n_np[ok] * kept.cpu().numpy()[ok, :3]).sum(1) <= 0).all()              # oriented towards the camera at the origin
+    nan_diff, ang_diff = _normal_agreement(n_np, P.estimate_normals(cloud[m_np], 16, 2 * radius, [0.0, 0.0, 0.0]))
+    assert nan_diff <= 2e-3 and ang_diff <= 5e-3, (nan_diff, ang_diff)
+    fx = np.load(GOLDEN / "ref_ext_pcproc.npz")
+    tag = "r5" if radius == 0.05 else "r8"
+    assert np.array_equal(m_np, fx[f"{tag}.mask"])                                   # vs the executed reference (golden)
+    nan_diff, ang_diff = _normal_agreement(n_np, fx[f"{tag}.normals"])
+    assert nan_diff <= 1e-3 and ang_diff <= 2e-3, (nan_diff, ang_diff)
+    pp = _ref("pcproc")                                                              # ... and live, same device tensors, (N,3) layout too
+    assert torch.equal(pp.remove_radius_outlier(d_cloud, 16, radius), mask)
+    assert torch.equal(ext.remove_radius_outlier(d_cloud[:, :3].contiguous(), 16, radius), mask)
+    nan_diff, ang_diff = _normal_agreement(n_np, pp.estimate_normals(kept, 16, 2 * radius, [0.0, 0.0, 0.0]).cpu().numpy())
+    assert nan_diff <= 1e-3 and ang_diff <= 2e-3, (nan_diff, ang_diff)
+    again = ext.estimate_normals(kept, 16, 2 * radius, [0.0, 0.0, 0.0])              # deterministic, scratch cleaned itself
+    assert torch.equal(again.view(torch.int32), normals.view(torch.int32))
+
+
+def test_track_camera_end_to_end(dev):
+    """The whole reference front end through the mirror (tracker.py:74-129): pyramid, unproject, outlier removal, normals, box
+    filter, then integrate the processed cloud and track the next frame with the default 3-group iter_config (rgb + sdf terms)."""
+    from difusion_b200 import synthetic as S
+    from difusion_b200.network import utility as net_util
+    from difusion_b200.system.map import DenseIndexedMap
+    from difusion_b200.system.tracker import SDFTracker
+    from difusion_b200.utils.motion_util import Isometry, Rotation
+    model, _ = net_util.load_model(str(GOLDEN / "weights.npz"))
+    sc = S.scene_S1(0.05)
+    m = DenseIndexedMap(model, sc.map_args(), 29, dev)
+    args = argparse.Namespace(sdf=dict(robust_kernel="huber", robust_k=5.0, subsample=0.5),
+                              rgb=dict(weight=500.0, robust_kernel=None, robust_k=0.01, min_grad_scale=0.0, max_depth_delta=0.2),
+                              iter_config=[{"n": 10, "type": [["sdf"], ["rgb", 0]]}])
+    trk = SDFTracker(m, args)
+    calib = _Calib(S.ICL_FX, S.ICL_FY, S.ICL_CX, S.ICL_CY)
+    poses = [S.orbit_pose(f) for f in (50, 51)]
+    est = []
+    for f, (R, t) in enumerate(poses):
+        rgb, depth = S.render_rgbd(sc, R, t, step=1)
+        gt = Isometry(q=Rotation(matrix=R), t=t)
+        pose = trk.track_camera(_t(rgb, dev), _t(depth, dev), calib, set_pose=gt if f == 0 else None)
+        est.append(pose)
+        pc, nrm = trk.last_processed_pc
+        assert pc.shape == nrm.shape and pc.size(0) > 15000 and bool(torch.isfinite(pc).all()) and bool(torch.isfinite(nrm).all())
+        m.integrate_keyframe(pose @ pc, pose.rotation @ nrm)
+    assert m.n_occupied > 3000
+    err = np.linalg.norm(est[1].t - poses[1][1])
+    assert err < 0.6 * np.linalg.norm(poses[1][1] - poses[0][1]) + 2e-3, err      # moved towards the true pose from the previous one
