@@ -55,6 +55,21 @@ mc_ms = k0.elapsed_time(k1)
 T = tri.size(0); B = cs.size(0)
 alg_bytes = 8 * 1000 * B + 8 * focused.numel() + 56 * T
 print(f"marching_cubes_kernel: {mc_ms*1e3:.1f} us for K={focused.numel()} PLIVoxes, T={T} triangles; algorithmic {alg_bytes/1e6:.1f} MB -> {alg_bytes/mc_ms/1e6:.1f} GB/s")
+# the reference's own kernel (oracle/_ref, unmodified) on the same cubes, timed the same way
+from oracle import build_ref
+if build_ref.available("marching_cubes"):
+    rmc = build_ref.load_module("marching_cubes")
+    args = (m.indexer.view(m.n_xyz), focused, mapping, cs, cd, int(12e6), m.n_xyz, 0.15)
+    for _ in range(2):
+        rmc.marching_cubes_sparse_interp(*args)
+    ts = []
+    for _ in range(5):
+        e0, e1 = ev(), ev(); e0.record(); rt = rmc.marching_cubes_sparse_interp(*args); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+    print(f"reference marching_cubes_sparse_interp (allocation + kernel + sync + trim, as shipped): {min(ts)*1e3:.1f} us, T={rt[0].size(0)}")
+    ts = []
+    for _ in range(5):
+        e0, e1 = ev(), ev(); e0.record(); ot = ext.marching_cubes_interp(*args); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+    print(f"ours     system.ext.marching_cubes_interp (same call shape):                           {min(ts)*1e3:.1f} us, T={ot[0].size(0)}")
 # properties: vertices on the sphere, std filter respected
 v = tri.reshape(-1, 3) * sc.voxel_size + torch.tensor(sc.bound_min, device=dev)
 rad = v.norm(dim=1)
