@@ -259,22 +259,21 @@ def main():
     # The upload of frame f+1 is issued on a copy stream before frame f is computed (double-buffered device staging), the way a
     # streaming SLAM front end would; it is inside the timed region.  Timed by wall clock around the whole loop (no L2 flush:
     # every step's inputs are fresh host data) with a device sync on both sides.
-    h_frames = [dict(pc=torch.from_numpy(fr["pc"]).pin_memory(), xw=torch.from_numpy(fr["xw"]).pin_memory(), nw=torch.from_numpy(fr["nw"]).pin_memory())
-                for fr in frames]
+    # one pinned block per frame [3][n][3] = (points cam, points world, normals world) -> ONE H2D copy per frame
+    h_frames = [torch.from_numpy(np.stack([fr["pc"], fr["xw"], fr["nw"]])).pin_memory() for fr in frames]
     max_n = max(fr["pc"].shape[0] for fr in frames)
-    stage = [dict(pc=torch.empty((max_n, 3), device=dev), xw=torch.empty((max_n, 3), device=dev), nw=torch.empty((max_n, 3), device=dev)) for _ in range(2)]
+    stage = [torch.empty((3 * max_n, 3), device=dev) for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
     copied = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
     h2d = d2h = 0
 
     def upload(f):
-        hf, st_ = h_frames[f], stage[f % 2]
-        n_f = hf["pc"].size(0)
+        hf = h_frames[f]
+        n_f = hf.size(1)
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[f % 2])                  # the previous user of this staging buffer is done
-            for k in ("pc", "xw", "nw"):
-                st_[k][:n_f].copy_(hf[k], non_blocking=True)
+            stage[f % 2][:3 * n_f].copy_(hf.view(3 * n_f, 3), non_blocking=True)
             copied[f % 2].record(copy_stream)
         return 3 * n_f * 3 * 4
 
@@ -290,9 +289,9 @@ def main():
         if f + 1 < K:
             h2d += upload(f + 1)                                     # overlaps with this frame's kernels
         main.wait_event(copied[f % 2])
-        n_f = h_frames[f]["pc"].size(0)
+        n_f = h_frames[f].size(1)
         st_ = stage[f % 2]
-        pc, xw, nw = st_["pc"][:n_f], st_["xw"][:n_f], st_["nw"][:n_f]
+        pc, xw, nw = st_[:n_f], st_[n_f:2 * n_f], st_[2 * n_f:3 * n_f]
         if f >= 1:
             H, g, E = trk.compute_sdf_Hg(0, poses[f], ident, pc, no_grad=False)        # D2H of 44 doubles + sync inside
         m3.integrate_keyframe(xw, nw)

@@ -33,6 +33,9 @@ _FP = C.POINTER(C.c_float)          # small HOST float arrays (intrinsics, K R K
 SIGNATURES = {
     "dif_abi_version": (C.c_int, []),
     "dif_shard_owner": (C.c_int, [_I64, C.c_int]),
+    "dif_shard_xchg_bytes": (_SZ, [_I64]),
+    "dif_shard_pack": (C.c_int, [_MV, _P, _I64, _P, _P]),
+    "dif_shard_unpack": (C.c_int, [_MV, _P, C.c_int, _I64, _P, _P]),
     "dif_profile_hook": (C.c_int, [C.c_int, _P, _P]),
     "dif_launch_count": (C.c_uint64, [C.c_int]),
     "dif_debug_tc_timing": (C.c_int, [_P]),

@@ -4,8 +4,12 @@
   ``latent_vecs_pos`` and ``voxel_obs_count`` are replicated and stay bit-identical to the single-GPU map.
 * Floating-point work is sharded by ``owner(cell) = splitmix64(linear id) % world``: the encoder MLP and the latent
   fusion of a PLIVox run only on its owner (``dif_map_view.shard_rank/shard_world``).
-* One exchange per frame: each rank publishes the (slot, latent row) pairs it owns and changed; after the all-gather every
-  rank holds every latent, so decoding / meshing need no further communication.
+* One exchange per frame, ONE collective: each rank packs the (slot, latent row) pairs it owns and changed into a fixed-size
+  buffer with a count header (dif_shard_pack), a single NCCL all-gather moves the buffers, dif_shard_unpack scatters the other
+  ranks' rows into the local table - no host synchronisation, sizes never leave the device.  After it every rank holds every
+  latent, so decoding / meshing need no further communication.  A rank that ever publishes more rows than the buffer holds
+  raises a device flag; the host notices it at the next frame, doubles the buffer and re-synchronises all owned rows
+  (variable-length path, also used by the CPU/gloo test).
 * ICP linearisation: each rank processes a contiguous slice of the frame's points, one all-reduce of 44 doubles.
 * Mesh extraction: each rank meshes the PLIVoxes it owns (neighbour cubes are decoded locally).
 
@@ -71,6 +75,10 @@ class ShardGroup:
         dist.all_gather(gr, pad_r, group=self.group)
         return torch.cat([g[:c] for g, c in zip(gs, counts)]), torch.cat([g[:c] for g, c in zip(gr, counts)])
 
+    def all_gather_fixed(self, send: torch.Tensor, recv: torch.Tensor):
+        """recv[rank] = send of that rank; one collective, sizes known statically."""
+        dist.all_gather_into_tensor(recv, send, group=self.group)
+
     def all_reduce_sum(self, t: torch.Tensor):
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t
@@ -96,19 +104,62 @@ def make_sharded_map(model, args, latent_dim, device, group: ShardGroup, **kw):
             self._shard_rank, self._shard_world = group.rank, group.world
             self._xchg = torch.empty(1 << 16, dtype=torch.int32, device=self.device)
 
+        def _alloc_xchg(self, cap_rows: int):
+            from . import _lib
+            L = _lib.lib()
+            self._xcap = cap_rows
+            nfl = L.dif_shard_xchg_bytes(cap_rows) // 4
+            self._xsend = torch.zeros(nfl, dtype=torch.float32, device=self.device)
+            self._xrecv = torch.zeros(nfl * self.shard.world, dtype=torch.float32, device=self.device)
+            self._xflag = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self._xflag_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self._xflag_ev = None
+
+        def resync(self):
+            """Publish ALL owned latent rows (variable-length path): recovery after an exchange-buffer overflow."""
+            slots = self.owned_slots(torch.arange(self.n_occupied, device=self.device))
+            slots_all, rows_all = self.shard.all_gather_rows(slots.int(), self._latent[slots])
+            if slots_all.numel():
+                self._latent.index_copy_(0, slots_all.long(), rows_all)
+
         def integrate_keyframe(self, surface_xyz, surface_normal, do_optimize=False, async_optimize=False):
+            import ctypes
+            from . import _lib
+            L = _lib.lib()
             need = min(8 * surface_xyz.size(0), self._cap_phys) + 1
             if self._xchg.numel() < need:
                 self._xchg = torch.empty(need, dtype=torch.int32, device=self.device)
+            if getattr(self, "_xcap", 0) == 0:
+                self._alloc_xchg(1 << 14)
+            self._xframe = getattr(self, "_xframe", 0) + 1
+            if self._xflag_ev is not None and self._xframe >= self._xflag_frame + 4:
+                # did an exchange overflow?  Checked a fixed number of frames after the flag was copied (long complete, so the
+                # wait is free) so that every rank takes the collective recovery path in the same frame; the flag itself is
+                # identical on every rank because every rank sees every header.
+                self._xflag_ev.synchronize()
+                self._xflag_ev = None
+                if int(self._xflag_host[0]):
+                    self._alloc_xchg(self._xcap * 2)
+                    self.resync()
             mask = super().integrate_keyframe(surface_xyz, surface_normal, do_optimize, async_optimize)
-            self._sync_stats()                                   # the exchange is sized by a device-side count
-            n_x = int(self._stats_last[7])
-            slots = self._xchg[:n_x].long()
-            slots_all, rows_all = self.shard.all_gather_rows(slots, self._latent[slots])
-            if slots_all.numel():
-                self._latent.index_copy_(0, slots_all, rows_all)
-            self.last_exchange = dict(rows_sent=n_x, rows_total=int(slots_all.numel()))
+            view, st = self._view(), _lib.stream_ptr(self.device)
+            n_x = self._stats_dev[_lib.STAT_N_XCHG:]
+            _lib.check(L.dif_shard_pack(ctypes.byref(view), n_x.data_ptr(), self._xcap, self._xsend.data_ptr(), st), "dif_shard_pack")
+            self.shard.all_gather_fixed(self._xsend, self._xrecv)
+            _lib.check(L.dif_shard_unpack(ctypes.byref(view), self._xrecv.data_ptr(), self.shard.world, self._xcap, self._xflag.data_ptr(), st),
+                       "dif_shard_unpack")
+            if self._xflag_ev is None:
+                self._xflag_host.copy_(self._xflag, non_blocking=True)
+                self._xflag_ev = torch.cuda.Event()
+                self._xflag_ev.record(torch.cuda.current_stream(self.device))
+                self._xflag_frame = self._xframe
             return mask
+
+        @property
+        def last_exchange(self):
+            """Rows this rank published / all ranks published in the last frame (reads the headers: host sync; diagnostics only)."""
+            per = self._xrecv.view(self.shard.world, -1)[:, 0].contiguous().view(torch.int32).tolist()
+            return dict(rows_sent=per[self.shard.rank], rows_total=sum(per), capacity=self._xcap)
 
         def icp_linearize(self, obs_xyz, R_last, t_last, R_delta, t_delta, huber_k=5.0, want_grad=True):
             n = obs_xyz.size(0)

@@ -31,6 +31,13 @@ from . import ext as _ext
 LATENT_DIM = 29
 
 
+def _as_f32(t: torch.Tensor) -> torch.Tensor:
+    """Contiguous fp32 view of a caller tensor without the three no-op dispatches of .detach().contiguous().float()."""
+    if t.dtype == torch.float32 and t.is_contiguous() and not t.requires_grad:
+        return t
+    return t.detach().contiguous().float()
+
+
 def _next_pow2(v: int) -> int:
     p = 1
     while p < v:
@@ -302,8 +309,7 @@ class DenseIndexedMap:
             f"Device of map {self.device} and input observation {surface_xyz.device, surface_normal.device} must be the same."
         if do_optimize and getattr(self.args, "optim_n_iters", 0) > 0:
             raise NotImplementedError("latent optimisation (map.py:456-516) is outside the hot path and not built")
-        xyz = surface_xyz.detach().contiguous().float()
-        nrm = surface_normal.detach().contiguous().float()
+        xyz, nrm = _as_f32(surface_xyz), _as_f32(surface_normal)
         n = xyz.size(0)
         with self.modifying_lock:
             # capacity: a call allocates at most 7 cells per point (own cell + 6 face neighbours); calls still in flight
@@ -352,11 +358,14 @@ class DenseIndexedMap:
     # ------------------------------------------------------------------ fused ICP linearisation (tracker.py:174-218)
     def icp_linearize(self, obs_xyz: torch.Tensor, R_last, t_last, R_delta, t_delta, huber_k: float = 5.0, want_grad: bool = True):
         """One launch: returns a pinned-host-bound device tensor out[44] (fp64): H[36], g[6], energy, M."""
-        x = obs_xyz.detach().contiguous().float()
+        x = _as_f32(obs_xyz)
         n = x.size(0)
         if self._icp_scratch is None:
             self._icp_scratch = torch.zeros(self._L.dif_icp_scratch_bytes(n), dtype=torch.uint8, device=self.device)   # zero-filled once (ABI)
-        out = torch.empty(44, dtype=torch.float64, device=self.device)
+            self._icp_ring = torch.empty((16, 44), dtype=torch.float64, device=self.device)    # results of the last 16 calls stay valid
+            self._icp_next = 0
+        out = self._icp_ring[self._icp_next]
+        self._icp_next = (self._icp_next + 1) % 16
         pose = np.empty(24, np.float32)
         pose[0:9], pose[9:12], pose[12:21], pose[21:24] = np.ravel(R_last), np.ravel(t_last), np.ravel(R_delta), np.ravel(t_delta)
         view = self._view()

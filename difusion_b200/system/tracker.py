@@ -44,6 +44,18 @@ class SDFTracker:
         self.last_colored_pcd = None
         self.n_unstable = 0
         self._rgb_scratch = None
+        self._pin = None
+
+    def _read44(self, out: torch.Tensor) -> np.ndarray:
+        """44 doubles device -> host through a pinned buffer and an event (cheaper than .cpu(): no pageable staging copy)."""
+        if self._pin is None:
+            self._pin = torch.empty(44, dtype=torch.float64).pin_memory()
+            self._pin_np = self._pin.numpy()
+            self._pin_ev = torch.cuda.Event()
+        self._pin.copy_(out, non_blocking=True)
+        self._pin_ev.record(torch.cuda.current_stream(out.device))
+        self._pin_ev.synchronize()
+        return self._pin_np.copy()
 
     # -------------------------------------------------------------------------------------------------
     def compute_sdf_Hg(self, n_iter: int, last_pose: Isometry, cur_delta_pose: Isometry, obs_xyz: torch.Tensor, no_grad: bool = False):
@@ -53,7 +65,7 @@ class SDFTracker:
             raise NotImplementedError("only the huber kernel is built (fusion-lr-kt.yaml:47)")
         out = self.map.icp_linearize(obs_xyz, last_pose.q.rotation_matrix, last_pose.t, cur_delta_pose.q.rotation_matrix,
                                      cur_delta_pose.t, huber_k=k, want_grad=not no_grad)
-        o = out.cpu().numpy()                        # the only host sync of the iteration
+        o = self._read44(out)                        # the only host sync of the iteration
         assert o[43] > 0                              # the reference asserts on an empty valid set (utility.py:84-85)
         if no_grad:
             return None, None, float(o[42])
@@ -99,7 +111,7 @@ class SDFTracker:
                                        _lib.host_floats(Kt.flatten().tolist()), float(a.min_grad_scale), float(a.max_depth_delta), kind,
                                        float(a.robust_k or 0.0), float(a.weight), int(not no_grad), self._rgb_scratch.data_ptr(),
                                        self._rgb_scratch.numel(), out.data_ptr(), _lib.stream_ptr(dev)), "dif_rgb_linearize")
-        o = out.cpu().numpy()                          # the only host sync of the term
+        o = self._read44(out)                          # the only host sync of the term
         if not o[43] > 0:
             raise ZeroDivisionError("float division by zero")               # tracker.py:165 with an empty valid set
         if no_grad:

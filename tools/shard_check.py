@@ -38,6 +38,20 @@ for f in range(n_frames):
     if rank == 0:
         print(f"frame {f}: n_occ {sm.n_occupied}  encoder samples on rank0 {sm.last_integrate_stats['n_samples']} of {ref.last_integrate_stats['n_samples']}"
               f"  rows sent {sm.last_exchange['rows_sent']} / exchanged {sm.last_exchange['rows_total']}  max|dlatent| {d:.2e}")
+# exchange-buffer overflow: shrink the buffer to 64 rows, keep integrating; the device flag is picked up 4 frames later on every
+# rank at once, the buffer doubles and all owned rows are re-published -> the replicas must be identical again at the end
+sm._alloc_xchg(64)
+for f in range(n_frames, n_frames + 12):
+    R, t = S.orbit_pose(f * 10); pc, nc = S.frame_points(sc, R, t); xw, nw = S.to_world(pc, nc, R, t)
+    xw_d, nw_d = torch.from_numpy(xw).to(dev), torch.from_numpy(nw).to(dev)
+    ref.integrate_keyframe(xw_d, nw_d); sm.integrate_keyframe(xw_d, nw_d)
+for _ in range(5):                                   # idle frames (no new points) give the lazy recovery time to fire on a quiet map
+    sm.integrate_keyframe(xw_d[:0], nw_d[:0]); ref.integrate_keyframe(xw_d[:0], nw_d[:0])
+d = (ref.latent_vecs - sm.latent_vecs).abs().max().item()
+grew = sm._xcap > 64
+ok &= grew and d <= 2e-6 and torch.equal(ref.indexer, sm.indexer)
+if rank == 0:
+    print(f"overflow recovery: buffer 64 -> {sm._xcap} rows, max|dlatent| after recovery {d:.2e}")
 mesh_ref = ref.extract_mesh(4, int(4e6), max_std=0.15, no_cache=True)
 mesh_s = sm.extract_mesh(4, int(4e6), max_std=0.15, no_cache=True)
 cnt = torch.tensor([mesh_s.triangles.shape[0]], device=dev); dist.all_reduce(cnt)
