@@ -439,59 +439,84 @@ __device__ float3 smallest_eigenvector(float3 x1, float3 x2, float3 x3) {
     return make_float3(r23.x / sqrt(d3), r23.y / sqrt(d3), r23.z / sqrt(d3));
 }
 
-// pcproc.cu:107-170 + :198-220.  k nearest (the point itself included, KNN_MAX >= max_nn) by (distance, index); entry 0 is skipped
+// pcproc.cu:107-170 + :198-220.  k nearest (the point itself included, max_nn <= 32) by (distance, index); entry 0 is skipped
 // like the reference's loop from nn_i = 1; neighbours beyond the radius end the list; fewer than 5 -> NaN normal.
+// ONE WARP PER QUERY: the 32 lanes read 32 consecutive candidates of a cell run (coalesced float4 loads), the running top-k list
+// lives in registers - lane k holds entry k - and a candidate that beats the current k-th entry is inserted with one ballot
+// (its position = number of entries not greater) and one shuffle (entries behind it move up a lane).  After the first few dozen
+// candidates insertions are rare, so the scan runs at one coalesced load + one distance + one ballot per 32 candidates.
 constexpr int KNN_MAX = 32;
+constexpr int NRM_WARPS = 8;
 
-__global__ void __launch_bounds__(128) estimate_normals_kernel(const float* __restrict__ p, int stride, int n, const BoxState* __restrict__ s, float cell,
-                                                                const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end,
-                                                                const float4* __restrict__ sorted_pt, int max_nn, float r2, float3 cam,
-                                                                float* __restrict__ normal_out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || s->overflow) return;
+__global__ void __launch_bounds__(NRM_WARPS * 32) estimate_normals_kernel(const float* __restrict__ p, int stride, int n, const BoxState* __restrict__ s,
+        float cell, const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end, const float4* __restrict__ sorted_pt,
+        int max_nn, float r2, float3 cam, float* __restrict__ normal_out) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * NRM_WARPS + (threadIdx.x >> 5);
+    if (i >= n || s->overflow) return;                              // warp-uniform
     const float* q = p + (size_t)stride * i;
     const float qx = q[0], qy = q[1], qz = q[2];
     const int cx = knn_axis(s, qx, 0, cell), cy = knn_axis(s, qy, 1, cell), cz = knn_axis(s, qz, 2, cell);
-    float bd[KNN_MAX]; uint32_t bj[KNN_MAX];        // ascending by (distance, original index); bj = position in sorted_pt
-    int bi[KNN_MAX];
+    const float inf = __int_as_float(0x7f800000);
+    float e_d = inf; int e_i = 0x7fffffff; float4 e_p = make_float4(0.f, 0.f, 0.f, 0.f);      // list entry `lane` (valid if lane < cnt)
     int cnt = 0;
-    for (int ox = -1; ox <= 1; ++ox) {
-        const int x = cx + ox; if (x < 0 || x >= s->n[0]) continue;
-        for (int oy = -1; oy <= 1; ++oy) {
-            const int y = cy + oy; if (y < 0 || y >= s->n[1]) continue;
-            const int z0 = max(cz - 1, 0), z1 = min(cz + 1, s->n[2] - 1);
-            const int c0 = (x * s->n[1] + y) * s->n[2];
-            const uint32_t b = cell_start[c0 + z0], e = cell_end[c0 + z1];
-            for (uint32_t j = b; j < e; ++j) {
-                const float4 c = sorted_pt[j];
-                const float d = knn_d2(qx, qy, qz, c);
-                if (!(d < r2)) continue;                                   // outside the radius: can never be used (:126,147)
-                const int ci = __float_as_int(c.w);
-                if (cnt == max_nn && !(d < bd[cnt - 1] || (d == bd[cnt - 1] && ci < bi[cnt - 1]))) continue;
-                int k = cnt < max_nn ? cnt : max_nn - 1;                   // insertion from the back
-                while (k > 0 && (d < bd[k - 1] || (d == bd[k - 1] && ci < bi[k - 1]))) { bd[k] = bd[k - 1]; bj[k] = bj[k - 1]; bi[k] = bi[k - 1]; --k; }
-                bd[k] = d; bj[k] = j; bi[k] = ci;
+    float worst_d = inf; int worst_i = 0x7fffffff;                  // entry max_nn - 1 once the list is full
+    for (int oxy = 0; oxy < 9; ++oxy) {
+        const int x = cx + oxy / 3 - 1, y = cy + oxy % 3 - 1;
+        if (x < 0 || x >= s->n[0] || y < 0 || y >= s->n[1]) continue;
+        const int z0 = max(cz - 1, 0), z1 = min(cz + 1, s->n[2] - 1);
+        const int c0 = (x * s->n[1] + y) * s->n[2];
+        const uint32_t b = cell_start[c0 + z0], e = cell_end[c0 + z1];
+        for (uint32_t j0 = b; j0 < e; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+            float d = inf; int ci = 0x7fffffff;
+            if (j < e) { c = sorted_pt[j]; d = knn_d2(qx, qy, qz, c); ci = __float_as_int(c.w); }
+            bool want = d < r2 && (cnt < max_nn || d < worst_d || (d == worst_d && ci < worst_i));
+            unsigned pending = __ballot_sync(0xffffffffu, want);
+            while (pending) {
+                const int src = __ffs(pending) - 1;
+                pending &= pending - 1;
+                const float nd = __shfl_sync(0xffffffffu, d, src);
+                const int ni = __shfl_sync(0xffffffffu, ci, src);
+                if (cnt == max_nn && !(nd < worst_d || (nd == worst_d && ni < worst_i))) continue;     // beaten by an earlier insert of this batch
+                const float4 np = make_float4(__shfl_sync(0xffffffffu, c.x, src), __shfl_sync(0xffffffffu, c.y, src),
+                                              __shfl_sync(0xffffffffu, c.z, src), 0.f);
+                const bool le = lane < cnt && (e_d < nd || (e_d == nd && e_i < ni));                   // my entry stays in front of the new one
+                const int pos = __popc(__ballot_sync(0xffffffffu, le));
+                const float up_d = __shfl_up_sync(0xffffffffu, e_d, 1);
+                const int up_i = __shfl_up_sync(0xffffffffu, e_i, 1);
+                const float4 up_p = make_float4(__shfl_up_sync(0xffffffffu, e_p.x, 1), __shfl_up_sync(0xffffffffu, e_p.y, 1),
+                                                __shfl_up_sync(0xffffffffu, e_p.z, 1), 0.f);
+                if (lane == pos) { e_d = nd; e_i = ni; e_p = np; }
+                else if (lane > pos) { e_d = up_d; e_i = up_i; e_p = up_p; }
                 if (cnt < max_nn) ++cnt;
+                if (cnt == max_nn) { worst_d = __shfl_sync(0xffffffffu, e_d, max_nn - 1); worst_i = __shfl_sync(0xffffffffu, e_i, max_nn - 1); }
             }
         }
     }
+    // mean and covariance in the reference's order (ascending distance, entry 0 skipped): every lane runs the same sequential
+    // sums on broadcast values, so the arithmetic does not depend on the warp layout
     const float qnan = __int_as_float(0x7fc00000);
     float3 mean = make_float3(0.f, 0.f, 0.f);
     float valid = 0.f;
-    for (int k = 1; k < cnt; ++k) { const float4 c = sorted_pt[bj[k]]; mean.x += c.x; mean.y += c.y; mean.z += c.z; valid += 1.0f; }
-    if (valid < 5.0f) { normal_out[3 * i] = normal_out[3 * i + 1] = normal_out[3 * i + 2] = qnan; return; }
+    for (int k = 1; k < cnt; ++k) {
+        mean.x += __shfl_sync(0xffffffffu, e_p.x, k); mean.y += __shfl_sync(0xffffffffu, e_p.y, k); mean.z += __shfl_sync(0xffffffffu, e_p.z, k);
+        valid += 1.0f;
+    }
+    if (valid < 5.0f) { if (lane < 3) normal_out[3 * i + lane] = qnan; return; }
     mean.x /= valid; mean.y /= valid; mean.z /= valid;
     float3 c1 = make_float3(0.f, 0.f, 0.f), c2 = c1, c3 = c1;
     for (int k = 1; k < cnt; ++k) {
-        const float4 c = sorted_pt[bj[k]];
-        const float3 d = make_float3(c.x - mean.x, c.y - mean.y, c.z - mean.z);
+        const float3 d = make_float3(__shfl_sync(0xffffffffu, e_p.x, k) - mean.x, __shfl_sync(0xffffffffu, e_p.y, k) - mean.y,
+                                     __shfl_sync(0xffffffffu, e_p.z, k) - mean.z);
         c1.x += d.x * d.x; c1.y += d.x * d.y; c1.z += d.x * d.z;
         c2.x += d.y * d.x; c2.y += d.y * d.y; c2.z += d.y * d.z;
         c3.x += d.z * d.x; c3.y += d.z * d.y; c3.z += d.z * d.z;
     }
     float3 nrm = smallest_eigenvector(c1, c2, c3);
     if (nrm.x * (qx - cam.x) + nrm.y * (qy - cam.y) + nrm.z * (qz - cam.z) > 0.0f) { nrm.x = -nrm.x; nrm.y = -nrm.y; nrm.z = -nrm.z; }
-    normal_out[3 * i] = nrm.x; normal_out[3 * i + 1] = nrm.y; normal_out[3 * i + 2] = nrm.z;
+    if (lane == 0) { normal_out[3 * i] = nrm.x; normal_out[3 * i + 1] = nrm.y; normal_out[3 * i + 2] = nrm.z; }
 }
 
 struct KnnPlan { BoxState* s; uint32_t *cell_start, *cell_fill, *chunk_sum; int* sorted_idx; float4* sorted_pt; long long max_cells; };
@@ -558,7 +583,7 @@ int dif_estimate_normals(const float* pc, int stride, int64_t n, int max_nn, flo
     if (n == 0) { cudaMemsetAsync(status_dev, 0, 4, st); return check_launch("dif_estimate_normals"); }
     const unsigned gp = (unsigned)((n + 255) / 256);
     dif::KnnPlan k = dif::knn_build(pc, stride, (int)n, radius, max_cells, scratch, st);
-    dif::estimate_normals_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(pc, stride, (int)n, k.s, radius, k.cell_start, k.cell_fill, k.sorted_pt,
+    dif::estimate_normals_kernel<<<(unsigned)((n + dif::NRM_WARPS - 1) / dif::NRM_WARPS), dif::NRM_WARPS * 32, 0, st>>>(pc, stride, (int)n, k.s, radius, k.cell_start, k.cell_fill, k.sorted_pt,
                                                                                 max_nn, radius * radius, make_float3(cam_xyz[0], cam_xyz[1], cam_xyz[2]), normal_out);
     dif::knn_clear_kernel<<<(unsigned)((max_cells + 255) / 256), 256, 0, st>>>(k.s, k.cell_start, k.cell_fill);
     cudaMemcpyAsync(status_dev, &k.s->overflow, 4, cudaMemcpyDeviceToDevice, st);
