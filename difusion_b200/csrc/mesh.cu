@@ -184,9 +184,18 @@ __global__ void __launch_bounds__(MC_THREADS) marching_cubes_kernel(McArgs a) {
         }
         nb2[buf][t] = batch;
     };
-    fetch_neighbours(blockIdx.x, 0);
+#ifndef DIF_MC_ORDER
+#define DIF_MC_ORDER 0                  // 0: grid-stride (CTAs sweep the sorted block list in lockstep windows)  1: one contiguous run per CTA
+#endif
+#if DIF_MC_ORDER == 1
+    const int64_t per_cta = (a.n_valid + gridDim.x - 1) / gridDim.x;
+    const int64_t blk_begin = blockIdx.x * per_cta, blk_end = blk_begin + per_cta < a.n_valid ? blk_begin + per_cta : a.n_valid, blk_step = 1;
+#else
+    const int64_t blk_begin = blockIdx.x, blk_end = a.n_valid, blk_step = gridDim.x;
+#endif
+    if (blk_begin < blk_end) fetch_neighbours(blk_begin, 0);
     int buf = 0;
-    for (int64_t blk = blockIdx.x; blk < a.n_valid; blk += gridDim.x, buf ^= 1) {
+    for (int64_t blk = blk_begin; blk < blk_end; blk += blk_step, buf ^= 1) {
         __syncthreads();                                    // nb2[buf] is complete (and, first round, the one-time tables)
         const int* nb = nb2[buf];
         const int64_t id = s_id2[buf];
@@ -228,7 +237,7 @@ __global__ void __launch_bounds__(MC_THREADS) marching_cubes_kernel(McArgs a) {
                 c_std[c] = own_missing ? qnan : __fdiv_rn(s2, s4);
             }
         }
-        fetch_neighbours(blk + gridDim.x, buf ^ 1);        // other buffer: nobody reads it before the barrier at the loop top
+        if (blk + blk_step < blk_end) fetch_neighbours(blk + blk_step, buf ^ 1);   // other buffer: nobody reads it before the barrier at the loop top
         if (!own_ok) continue;                              // uniform per CTA
         __syncthreads();
         const int bx = s_b2[buf][0], by = s_b2[buf][1], bz = s_b2[buf][2];
@@ -409,7 +418,10 @@ int dif_marching_cubes(const int64_t* indexer, int nx, int ny, int nz, const int
     if (n_valid == 0) return check_launch("dif_marching_cubes");
     McArgs a{indexer, nx, ny, nz, valid_blocks, n_valid, vec_batch_mapping, mapping_len, cube_sdf, cube_std, r, max_std,
              tri, tri_flatten_id, tri_std, max_tri, count_dev};
-    const int64_t cap = (int64_t)DIF_NUM_SMS * 16;
+#ifndef DIF_MC_CTAS_PER_SM
+#define DIF_MC_CTAS_PER_SM 32
+#endif
+    const int64_t cap = (int64_t)DIF_NUM_SMS * DIF_MC_CTAS_PER_SM;
     prof_begin(DIF_PROF_MC, st);
     const unsigned grid = (unsigned)(n_valid < cap ? n_valid : cap);
     switch (r) {

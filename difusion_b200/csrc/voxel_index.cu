@@ -362,9 +362,15 @@ __global__ void gather_kernel(MapDev m, int n, const float* __restrict__ p_hat, 
     }
     // per-PLIVox observation counters first (they do not need the list position), then the warp-aggregated reservation in
     // the sample list: both atomic round trips are in flight together
+    // Neighbouring points of a warp mostly hit the same PLIVox: lanes with equal slot elect a leader (match_any) that adds the
+    // whole group's count with ONE returning atomic, so the contended per-slot counters see a fraction of the traffic.
     unsigned before[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) before[k] = slots[k] >= 0 ? atomicAdd(slot_cnt + slots[k], 1u) : 1u;
+    for (int k = 0; k < 8; ++k) {
+        const unsigned grp = __match_any_sync(0xffffffffu, slots[k]);
+        const bool leader = lane == __ffs(grp) - 1;
+        before[k] = (slots[k] >= 0 && leader) ? atomicAdd(slot_cnt + slots[k], (unsigned)__popc(grp)) : 1u;
+    }
     int incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
