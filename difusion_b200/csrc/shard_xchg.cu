@@ -30,7 +30,7 @@ __global__ void shard_unpack_kernel(float* __restrict__ latent, int64_t capacity
     const int src = blockIdx.y;
     const float* buf = gathered + (int64_t)src * (cap_rows + 1) * XROW;
     const int count = __float_as_int(buf[0]);
-    if (count > cap_rows && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(overflow, 1);      // every rank sees every header: same flag everywhere
+    if (count > cap_rows && blockIdx.x == 0 && threadIdx.x == 0) atomicMax(overflow, count); // every rank sees every header: same value everywhere
     if (src == my_rank) return;                                                 // own rows are already in place
     const int64_t rows = count < cap_rows ? count : cap_rows;
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

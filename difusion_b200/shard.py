@@ -94,6 +94,23 @@ def combine_icp(out: torch.Tensor, group: ShardGroup) -> torch.Tensor:
     return raw
 
 
+def expand_26(indexer: torch.Tensor, pos: torch.Tensor, n_xyz, slots: torch.Tensor) -> torch.Tensor:
+    """Slots of the occupied cells in the 3x3x3 neighbourhood (own cell included) of the given slots, sorted unique.
+    Owner-wise meshing decodes this set so that every cube the marching-cubes blend of an OWNED PLIVox can touch
+    (mc_interp_kernel.cu:103-181: +-1 per axis, diagonals included) is in the decode batch, exactly as in a full single-GPU extraction."""
+    if slots.numel() == 0:
+        return slots.to(torch.int64)
+    nx, ny, nz = [int(v) for v in n_xyz]
+    lin = pos[slots.long()]
+    x, y, z = lin // (ny * nz), (lin // nz) % ny, lin % nz
+    r = torch.arange(-1, 2, device=lin.device)
+    ox, oy, oz = [t.reshape(1, -1) for t in torch.meshgrid(r, r, r, indexing="ij")]
+    X, Y, Z = x[:, None] + ox, y[:, None] + oy, z[:, None] + oz
+    ok = (X >= 0) & (X < nx) & (Y >= 0) & (Y < ny) & (Z >= 0) & (Z < nz)
+    s = indexer[((X * ny + Y) * nz + Z)[ok]]
+    return torch.unique(s[s >= 0])
+
+
 def make_sharded_map(model, args, latent_dim, device, group: ShardGroup, **kw):
     from .system.map import DenseIndexedMap
 
@@ -138,8 +155,12 @@ def make_sharded_map(model, args, latent_dim, device, group: ShardGroup, **kw):
                 # identical on every rank because every rank sees every header.
                 self._xflag_ev.synchronize()
                 self._xflag_ev = None
-                if int(self._xflag_host[0]):
-                    self._alloc_xchg(self._xcap * 2)
+                need = int(self._xflag_host[0])                                 # largest row count any rank tried to publish
+                if need:
+                    cap = self._xcap * 2
+                    while cap < 2 * need:
+                        cap *= 2
+                    self._alloc_xchg(cap)
                     self.resync()
             mask = super().integrate_keyframe(surface_xyz, surface_normal, do_optimize, async_optimize)
             view, st = self._view(), _lib.stream_ptr(self.device)
@@ -166,6 +187,9 @@ def make_sharded_map(model, args, latent_dim, device, group: ShardGroup, **kw):
             lo, hi = n * self.shard.rank // self.shard.world, n * (self.shard.rank + 1) // self.shard.world
             out = super().icp_linearize(obs_xyz[lo:hi].contiguous(), R_last, t_last, R_delta, t_delta, huber_k, want_grad)
             return combine_icp(out, self.shard)
+
+        def decode_set(self, owned: torch.Tensor) -> torch.Tensor:
+            return expand_26(self._indexer, self._pos, self.n_xyz, owned)
 
         def owned_slots(self, slots: torch.Tensor) -> torch.Tensor:
             return slots[owner_of(self._pos[slots], self.shard.world) == self.shard.rank]

@@ -459,13 +459,18 @@ class DenseIndexedMap:
             if self._shard_world > 1:                       # hash-sharded map: every rank meshes the PLIVoxes it owns
                 if updated is None:
                     updated = torch.arange(self.n_occupied, device=self.device)
-                updated = self.owned_slots(updated)
+                owned = self.owned_slots(updated)
+                updated = self.decode_set(owned)            # owned + their 26 neighbours: same decode batch as a full extraction sees
+            else:
+                owned = None
 
         def do_meshing(res):
             torch.cuda.synchronize(self.device)
             with torch.cuda.stream(self.meshing_stream):
                 focused, mapping, cube_sdf, cube_std, _, _ = self.mesh_cubes(res, fast, updated)
-                if cube_sdf.size(0) == 0:
+                if owned is not None:                       # sharded map: triangles only for the PLIVoxes this rank owns
+                    focused = self._pos[owned].contiguous()
+                if cube_sdf.size(0) == 0 or focused.numel() == 0:
                     return
                 vertices, vertices_flatten_id, vertices_std = _ext.marching_cubes_interp(
                     self.indexer.view(self.n_xyz), focused, mapping, cube_sdf, cube_std, max_n_triangles, self.n_xyz, max_std)

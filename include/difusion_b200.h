@@ -231,7 +231,7 @@ int dif_debug_tc_timing(void* dev_buf);
  * send_buf = [1 + cap_rows][32] floats (row 0: header, word 0 = row count; row 1+i: slot bits, 29 latents, 2 pad words); ONE NCCL
  * all-gather of dif_shard_xchg_bytes(cap_rows) per rank moves them (torch.distributed.all_gather_into_tensor); dif_shard_unpack
  * writes the rows of all other ranks into map->latent_vecs.  No host synchronisation: a rank publishing more than cap_rows rows
- * sets *overflow_dev (checked lazily by the host, which then re-synchronises and grows cap_rows). */
+ * raises *overflow_dev to its row count (atomicMax; checked lazily by the host, which then grows cap_rows past it and re-synchronises). */
 size_t dif_shard_xchg_bytes(int64_t cap_rows);
 int dif_shard_pack(const dif_map_view* map, const int32_t* n_xchg_dev, int64_t cap_rows, float* send_buf, void* stream);
 int dif_shard_unpack(const dif_map_view* map, const float* gathered /*[world][1 + cap_rows][32]*/, int world, int64_t cap_rows,

@@ -65,3 +65,33 @@ def test_shard_host_logic_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_expand_26_matches_brute_force():
+    """Owner-wise meshing decodes the owned PLIVoxes plus every occupied cell in their 3x3x3 neighbourhoods (shard.expand_26)."""
+    from difusion_b200 import shard
+    rng = np.random.default_rng(4)
+    n_xyz = [7, 5, 6]
+    n_cells = int(np.prod(n_xyz))
+    occ = np.sort(rng.choice(n_cells, 90, replace=False))
+    order = rng.permutation(occ.size)                                    # slot numbering is arbitrary
+    indexer = np.full(n_cells, -1, np.int64)
+    pos = np.full(128, -1, np.int64)
+    indexer[occ[order]] = np.arange(occ.size)
+    pos[:occ.size] = occ[order]
+    owned = np.sort(rng.choice(occ.size, 25, replace=False))
+    got = shard.expand_26(torch.from_numpy(indexer), torch.from_numpy(pos), n_xyz, torch.from_numpy(owned)).numpy()
+    exp = set()
+    for s in owned:
+        lin = pos[s]
+        x, y, z = lin // (n_xyz[1] * n_xyz[2]), (lin // n_xyz[2]) % n_xyz[1], lin % n_xyz[2]
+        for dx in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                for dz in (-1, 0, 1):
+                    X, Y, Z = x + dx, y + dy, z + dz
+                    if 0 <= X < n_xyz[0] and 0 <= Y < n_xyz[1] and 0 <= Z < n_xyz[2]:
+                        t = indexer[(X * n_xyz[1] + Y) * n_xyz[2] + Z]
+                        if t >= 0:
+                            exp.add(int(t))
+    assert got.tolist() == sorted(exp) and set(owned.tolist()) <= exp
+    assert shard.expand_26(torch.from_numpy(indexer), torch.from_numpy(pos), n_xyz, torch.zeros(0, dtype=torch.int64)).numel() == 0
