@@ -252,15 +252,6 @@ int dif_point_box_filter(const float* points, const float* normals, int64_t n, f
 // nvcc to fma(dz,dz,fma(dy,dy,dx*dx))); ties are broken by point index, which makes the result deterministic.
 namespace dif {
 
-struct KnnGrid {                        // device-resident header in the scratch buffer
-    float mn[3], mx[3];
-    int n[3];
-    int overflow;
-    unsigned long long n_words;         // (reused BoxState layout up to here: box_minmax_kernel fills mn/mx)
-    int n_cells;
-};
-static_assert(sizeof(KnnGrid) == sizeof(BoxState), "KnnGrid mirrors BoxState so the min/max kernels can be shared");
-
 __global__ void knn_minmax_kernel(const float* __restrict__ p, int stride, int n, BoxState* s) {
     float mn[3] = {__int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0x7f800000)};
     float mx[3] = {__int_as_float(0xff800000), __int_as_float(0xff800000), __int_as_float(0xff800000)};
