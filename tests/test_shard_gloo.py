@@ -41,6 +41,35 @@ def _worker(rank, world, port, q):
     table.index_copy_(0, s_all.long(), r_all)
     ref = torch.arange(world_rows, dtype=torch.float32)[:, None] + torch.arange(29, dtype=torch.float32)[None, :] / 100
     ok &= bool(torch.equal(table, ref))
+    # --- the per-frame exchange protocol (dif_shard_pack / one all_gather_into_tensor / dif_shard_unpack), restated with torch ops:
+    #     [1 + cap][32] floats per rank, row 0 word 0 = row count (int bits), row 1+i = slot bits, 29 latents, 2 pad words
+    cap = 64
+    for counts in ([10, 64], [0, 3], [70, 5]):                                   # the last one overflows rank 0's buffer
+        n = counts[rank]
+        slots = torch.from_numpy(rng.choice(1000, n, replace=False).astype(np.int32)) + 1000 * rank
+        rows = torch.from_numpy(rng.normal(size=(n, 29)).astype(np.float32))
+        send = torch.zeros((cap + 1) * 32)
+        send[0] = torch.tensor([n], dtype=torch.int32).view(torch.float32)[0]
+        k = min(n, cap)
+        body = send[32:].view(cap, 32)
+        body[:k, 0] = slots[:k].view(torch.float32)
+        body[:k, 1:30] = rows[:k]
+        recv = torch.zeros(world * (cap + 1) * 32)
+        g.all_gather_fixed(send, recv)
+        table, overflow = torch.zeros(2000, 29), 0
+        for src in range(world):
+            buf = recv.view(world, cap + 1, 32)[src]
+            cnt = int(buf[0, :1].view(torch.int32)[0])
+            overflow = max(overflow, cnt if cnt > cap else 0)
+            if src != rank:
+                kk = min(cnt, cap)
+                table[buf[1:1 + kk, 0].contiguous().view(torch.int32).long()] = buf[1:1 + kk, 1:30]
+        ok &= overflow == (70 if max(counts) > cap else 0)                       # every rank sees the same overflow value
+        s_all, r_all = g.all_gather_rows(slots[:k], rows[:k])                    # what the other rank really published (first cap rows)
+        other = 1 - rank
+        off, ko = (0 if other == 0 else min(counts[0], cap)), min(counts[other], cap)
+        ok &= bool(torch.equal(table[s_all[off:off + ko].long()], r_all[off:off + ko]))
+        ok &= int((table.abs().sum(1) > 0).sum()) == ko
     # --- ICP combine: per-rank (already normalised) partial systems -> the global one
     rng = np.random.default_rng(7)
     J = rng.normal(size=(1000, 6)); r = rng.normal(size=1000)
