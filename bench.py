@@ -12,7 +12,11 @@ encoder/decoder, a 200-frame yaw-sweep stream, integrate_interval = 1.  One STEP
 `e2e`    : the same steps through the reference-shaped Python API (DenseIndexedMap / SDFTracker) from PINNED HOST buffers:
            H2D of the frame's points+normals inside the timed region, D2H of the 44-double ICP result and of the
            integrate counters, host sync every frame (a tracking loop needs H,g on the host to update the pose).
+           One packed pinned block per frame -> ONE H2D copy per frame, issued one frame ahead on a copy stream.
 L2 is flushed (256 MiB write) between timed steps; per-step CUDA events exclude the flush.
+Extras in the same JSON line (rank 0, outside the timed region): `decoder_sweep` (BASELINE config 3, 2^14..2^22 samples) and
+`full_loop` (the whole reference loop through the mirror: track_camera on RGB-D images with the shipped iter_config + integrate +
+incremental meshing).
 --impl reference: the CPU restatement of the reference's own Python path (oracle/dif_oracle.py; the reference has no CPU
 mode and its CUDA extensions cannot be built without its source tree on the box) on all host cores, same steps.
 """
