@@ -399,6 +399,25 @@ def main():
                                  "extract_mesh every 10 frames; 640x480 device-resident images; wall clock"}
         except Exception as e:                                      # the extra must never take the bench line down
             full_loop = {"error": f"{type(e).__name__}: {e}"}
+        # the same loop on the host cores: oracle/loop_oracle.py (the reference's tracker front end + Gauss-Newton driver sequenced
+        # over the pinned oracle pieces), bounded sample of 3 frames of the same stream, no meshing
+        try:
+            from difusion_b200 import synthetic as S
+            from oracle import dif_oracle as O, loop_oracle as Lp
+            torch.set_num_threads(cores)
+            Wc = O.load_weights_npz(ROOT / "tests" / "golden" / "weights.npz")
+            cpu_frames = []
+            for f in range(3):
+                R, t = S.orbit_pose(f, STREAM_LEN)
+                rgb, depth = S.render_rgbd(sc, R, t, step=1)
+                cpu_frames.append((rgb, depth, (R, t)))
+            c0 = time.perf_counter()
+            Lp.run_loop(Wc, sc.map_args(), cpu_frames, full_args.iter_config, S.ICL_FX, S.ICL_FY, S.ICL_CX, S.ICL_CY)
+            c1 = time.perf_counter()
+            full_loop["cpu_port"] = {"frames_per_s": 3 / (c1 - c0), "cores": cores, "kind": "port",
+                                     "sample": "frames 0..2 of the same RGB-D stream, oracle/loop_oracle.py, same iter_config, no meshing"}
+        except Exception as e:
+            full_loop["cpu_port"] = {"error": f"{type(e).__name__}: {e}"}
 
     # ------------------------------------------------------------------ config 3 extras: decoder batch sweep (samples/s)
     sweep = {}

@@ -46,21 +46,29 @@ def remove_radius_outlier(pc, nb_points: int, radius: float):
 
 
 def estimate_normals(pc, max_nn: int, radius: float, cam_xyz):
+    """pcproc.cu:107-170 vectorised: neighbours 1..max_nn-1 up to the first one outside the radius, mean, covariance, eigenvector of
+    the smallest eigenvalue (batched LAPACK eigh), flipped towards cam_xyz; NaN rows with fewer than 5 neighbours."""
     xyz = np.asarray(pc, np.float32)[:, :3]
+    n = xyz.shape[0]
+    out = np.full((n, 3), np.nan, np.float32)
+    if n == 0:
+        return out
     d2, idx = _knn(xyz, max_nn)
     r2 = np.float32(radius) * np.float32(radius)
-    out = np.full((xyz.shape[0], 3), np.nan, np.float32)
-    cam = np.asarray(cam_xyz, np.float64)
-    for i in range(xyz.shape[0]):
-        ok = d2[i, 1:] < r2
-        n_ok = int(np.argmin(ok)) if not ok.all() else ok.size      # the reference stops at the first neighbour outside the radius
-        if n_ok < 5:
-            continue
-        nb = xyz[idx[i, 1:1 + n_ok]].astype(np.float64)
-        c = nb - nb.mean(0)
-        w, v = np.linalg.eigh(c.T @ c)
-        n = v[:, 0]
-        if n @ (xyz[i].astype(np.float64) - cam) > 0:
-            n = -n
-        out[i] = n
+    inside = d2[:, 1:] < r2
+    use = np.logical_and.accumulate(inside, axis=1)               # the reference stops at the first neighbour outside the radius
+    cnt = use.sum(1)
+    ok = cnt >= 5
+    if not ok.any():
+        return out
+    nb = xyz[np.where(idx[:, 1:] >= 0, idx[:, 1:], 0)].astype(np.float64)          # (n, k-1, 3)
+    w = use[..., None].astype(np.float64)
+    mean = (nb * w).sum(1) / np.maximum(cnt, 1)[:, None]
+    c = (nb - mean[:, None, :]) * w
+    cov = np.einsum("nka,nkb->nab", c, c)
+    _, vec = np.linalg.eigh(cov[ok])
+    nrm = vec[:, :, 0]
+    flip = np.einsum("na,na->n", nrm, xyz[ok].astype(np.float64) - np.asarray(cam_xyz, np.float64)) > 0
+    nrm[flip] = -nrm[flip]
+    out[ok] = nrm
     return out
