@@ -391,6 +391,7 @@ def main():
                     if f % 10 == 9:
                         m4.extract_mesh(4, int(4e6), max_std=0.15)
                     t_err.append(float(np.linalg.norm(pose.t - gt.t)))
+                    gpu_t = (gpu_t + [np.asarray(pose.t, float)]) if f else [np.asarray(pose.t, float)]
                 torch.cuda.synchronize(dev)
                 w1 = time.perf_counter()
             full_loop = {"frames": n_full, "frames_per_s": n_full / (w1 - w0), "ms_per_frame": 1e3 * (w1 - w0) / n_full,
@@ -412,10 +413,15 @@ def main():
                 rgb, depth = S.render_rgbd(sc, R, t, step=1)
                 cpu_frames.append((rgb, depth, (R, t)))
             c0 = time.perf_counter()
-            Lp.run_loop(Wc, sc.map_args(), cpu_frames, full_args.iter_config, S.ICL_FX, S.ICL_FY, S.ICL_CX, S.ICL_CY)
+            cpu_poses, _, _ = Lp.run_loop(Wc, sc.map_args(), cpu_frames, full_args.iter_config, S.ICL_FX, S.ICL_FY, S.ICL_CX, S.ICL_CY)
             c1 = time.perf_counter()
             full_loop["cpu_port"] = {"frames_per_s": 3 / (c1 - c0), "cores": cores, "kind": "port",
                                      "sample": "frames 0..2 of the same RGB-D stream, oracle/loop_oracle.py, same iter_config, no meshing"}
+            try:                                                    # tracked poses of the two paths on the same frames (informational)
+                full_loop["cpu_port"]["max_translation_diff_gpu_vs_cpu_m"] = max(
+                    float(np.linalg.norm(cp[1] - gt_)) for cp, gt_ in zip(cpu_poses, gpu_t[:3]))
+            except NameError:
+                pass
         except Exception as e:
             full_loop["cpu_port"] = {"error": f"{type(e).__name__}: {e}"}
 
