@@ -8,13 +8,18 @@ encoder/decoder, a 200-frame yaw-sweep stream, integrate_interval = 1.  One STEP
     (a) point-to-implicit ICP linearisation of the frame against the map built so far
         (decoder forward + backward wrt xyz + 6x6 normal equations; reference tracker.py:174-218 compute_sdf_Hg)   [frame >= 1]
     (b) integrate_keyframe of the frame (voxelise/prune/allocate/gather/encoder/fuse; reference map.py:340-452).
-`value`  : frames/s with every frame's points already resident in HBM (device time, CUDA events per step).
-`e2e`    : the same steps through the reference-shaped Python API (DenseIndexedMap / SDFTracker) from PINNED HOST buffers:
-           H2D of the frame's points+normals inside the timed region, D2H of the 44-double ICP result and of the
-           integrate counters, host sync every frame (a tracking loop needs H,g on the host to update the pose).
-           One packed pinned block per frame -> ONE H2D copy per frame, issued one frame ahead on a copy stream.
-L2 is flushed (256 MiB write) between timed steps; per-step CUDA events exclude the flush.
-Extras in the same JSON line (rank 0, outside the timed region): `decoder_sweep` (BASELINE config 3, 2^14..2^22 samples) and
+Both arms run the step as ONE replayed CUDA graph of dif_frame (difusion_b200/system/frame.py): the per-frame point count and
+poses are read from a device block, so the host's share of a step is one copy + one graph launch.
+`value`  : frames/s with every frame's packed block already resident in HBM (device time: CUDA events around every step,
+           summed; a device-to-device copy of the frame into the graph's staging buffer is part of the pipeline, issued one
+           frame ahead on the copy stream).  The K-step pass is repeated on a map reset in place (>= 5 passes, more while the
+           timed total is short); `value` is the MEDIAN pass, `passes` holds min / max / all.
+`e2e`    : the same steps from PINNED HOST buffers: per step ONE H2D copy of the packed frame (header + points, issued one
+           frame ahead on the copy stream), the graph, and ONE 400-byte D2H of H, g, energy, valid count and the integrate
+           counters, with a host sync every frame (a tracking loop needs H, g on the host to update the pose).  Wall clock
+           around the K-step loop, device sync on both sides; median over the same number of passes.
+L2 is flushed (256 MiB write) between timed steps of the device-resident arm; the per-step CUDA events exclude the flush.
+Extras in the same JSON line (rank 0, outside the timed region): `decoder_sweep` (BASELINE config 3, 2^14..2^22 samples),
 `full_loop` (the whole reference loop through the mirror: track_camera on RGB-D images with the shipped iter_config + integrate +
 incremental meshing).
 --impl reference: the CPU restatement of the reference's own Python path (oracle/dif_oracle.py; the reference has no CPU
@@ -93,7 +98,7 @@ class ClockSampler(threading.Thread):
                 self.samples.append((mhz, reasons, util))
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(0.005)
 
     def summary(self):
         if not self.ok or not self.samples:
@@ -130,6 +135,131 @@ def run_cpu_port(frames, sc, n_steps, warmup, threads):
     return time.perf_counter() - t0
 
 
+def ncu_traffic(tag):
+    """dram read+write bytes per launch of the dominant kernel, from the newest committed `ncu --set full` summary of it
+    (profiles/r<round>_ncu_<tag>_metrics.csv).  It is context for the roofline line, not a live measurement: the file name is reported."""
+    best = None
+    for f in sorted((ROOT / "profiles").glob(f"r*_ncu_{tag}_metrics.csv")):
+        best = f
+    if best is None:
+        return None, None
+    tot = 0.0
+    for line in best.read_text().splitlines():
+        parts = line.split(",")
+        if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(parts[2]) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[parts[1]]
+    return tot, best.name
+
+
+# ------------------------------------------------------------------------------------------------- extras (outside the timed region)
+def extra_full_loop(torch, dev, model, sc, new_map, cores):
+    """The FULL reference loop (main.py:60-94) on RGB-D images: track_camera (pyramid, unproject, radius outlier, normals, box filter,
+    Gauss-Newton over the shipped 3-group iter_config with sdf + rgb terms) + integrate_keyframe every frame + one incremental mesh
+    extraction every 10 frames.  Images device-resident, wall clock.  Not the headline metric; it shows the rest of the loop runs on the GPU."""
+    from difusion_b200 import synthetic as S
+    from difusion_b200.system.tracker import SDFTracker
+    from difusion_b200.utils.motion_util import Isometry, Rotation
+    full_loop = {}
+    full_args = argparse.Namespace(
+        sdf=dict(robust_kernel="huber", robust_k=5.0, subsample=0.5),
+        rgb=dict(weight=500.0, robust_kernel=None, robust_k=0.01, min_grad_scale=0.0, max_depth_delta=0.2),
+        iter_config=[{"n": 10, "type": [["rgb", 2]]}, {"n": 10, "type": [["sdf"], ["rgb", 1]]}, {"n": 50, "type": [["sdf"], ["rgb", 0]]}])
+    gpu_t = []
+    try:
+        class _Calib:
+            fx, fy, cx, cy = S.ICL_FX, S.ICL_FY, S.ICL_CX, S.ICL_CY
+
+            def to_K(self):
+                return np.asarray([[self.fx, 0.0, self.cx], [0.0, self.fy, self.cy], [0.0, 0.0, 1.0]])
+        n_full = 24
+        imgs = []
+        for f in range(n_full):
+            R, t = S.orbit_pose(f, STREAM_LEN)
+            rgb, depth = S.render_rgbd(sc, R, t, step=1)
+            imgs.append((torch.from_numpy(rgb).to(dev), torch.from_numpy(depth).to(dev), Isometry(q=Rotation(matrix=R), t=t)))
+        for rep in range(2):                                   # rep 0 warms allocators / scratch
+            m4 = new_map()
+            trk4 = SDFTracker(m4, full_args)
+            n_iter = 0
+            orig = trk4.compute_sdf_Hg
+
+            def counted(*aa, **kk):
+                nonlocal n_iter
+                n_iter += 1
+                return orig(*aa, **kk)
+            trk4.compute_sdf_Hg = counted
+            torch.cuda.synchronize(dev)
+            w0 = time.perf_counter()
+            t_err, gpu_t = [], []
+            for f, (rgb_d, depth_d, gt) in enumerate(imgs):
+                pose = trk4.track_camera(rgb_d, depth_d, _Calib(), set_pose=gt if f == 0 else None)
+                pc_c, n_c = trk4.last_processed_pc
+                m4.integrate_keyframe(pose @ pc_c, pose.rotation @ n_c)
+                if f % 10 == 9:
+                    m4.extract_mesh(4, int(4e6), max_std=0.15)
+                t_err.append(float(np.linalg.norm(pose.t - gt.t)))
+                gpu_t.append(np.asarray(pose.t, float))
+            torch.cuda.synchronize(dev)
+            w1 = time.perf_counter()
+        full_loop = {"frames": n_full, "frames_per_s": n_full / (w1 - w0), "ms_per_frame": 1e3 * (w1 - w0) / n_full,
+                     "sdf_linearisations_per_frame": n_iter / max(n_full - 1, 1), "max_translation_error_m": max(t_err),
+                     "what": "track_camera(rgb, depth) with the shipped 3-group iter_config + integrate_keyframe per frame + incremental "
+                             "extract_mesh every 10 frames; 640x480 device-resident images; wall clock"}
+    except Exception as e:                                      # the extra must never take the bench line down
+        full_loop = {"error": f"{type(e).__name__}: {e}"}
+    # the same loop on the host cores: oracle/loop_oracle.py (the reference's tracker front end + Gauss-Newton driver sequenced
+    # over the pinned oracle pieces), bounded sample of 3 frames of the same stream, no meshing
+    try:
+        from oracle import dif_oracle as O, loop_oracle as Lp
+        torch.set_num_threads(cores)
+        Wc = O.load_weights_npz(ROOT / "tests" / "golden" / "weights.npz")
+        cpu_frames = []
+        for f in range(3):
+            R, t = S.orbit_pose(f, STREAM_LEN)
+            rgb, depth = S.render_rgbd(sc, R, t, step=1)
+            cpu_frames.append((rgb, depth, (R, t)))
+        c0 = time.perf_counter()
+        cpu_poses, _, _ = Lp.run_loop(Wc, sc.map_args(), cpu_frames, full_args.iter_config, S.ICL_FX, S.ICL_FY, S.ICL_CX, S.ICL_CY)
+        c1 = time.perf_counter()
+        full_loop["cpu_port"] = {"frames_per_s": 3 / (c1 - c0), "cores": cores, "kind": "port",
+                                 "sample": "frames 0..2 of the same RGB-D stream, oracle/loop_oracle.py, same iter_config, no meshing"}
+        if len(gpu_t) >= 3:                                     # tracked poses of the two paths on the same frames (informational)
+            full_loop["cpu_port"]["max_translation_diff_gpu_vs_cpu_m"] = max(
+                float(np.linalg.norm(cp[1] - gt_)) for cp, gt_ in zip(cpu_poses, gpu_t[:3]))
+    except Exception as e:
+        full_loop["cpu_port"] = {"error": f"{type(e).__name__}: {e}"}
+    return full_loop
+
+
+def extra_decoder_sweep(torch, dev, L, _lib, net_util, model, table, n_rows, flush, pk):
+    """BASELINE config 3: decoder batch sweep (samples/s), latent table = the map the timed passes built."""
+    sweep = {}
+    prep = net_util.prepared_for(model, dev)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    for p2 in (14, 16, 18, 20, 22):
+        n = 1 << p2
+        rows = torch.randint(0, max(n_rows, 1), (n,), generator=g, dtype=torch.int32).to(dev)
+        xyz = (torch.rand(n, 3, generator=g) * 2 - 1).to(dev)
+        sdf = torch.empty(n, device=dev); std = torch.empty(n, device=dev)
+
+        def run():
+            _lib.check(L.dif_decode(prep.decoder.data_ptr(), table.data_ptr(), rows.data_ptr(), xyz.data_ptr(), n, None, 1.0,
+                                    sdf.data_ptr(), std.data_ptr(), None, None, _lib.stream_ptr(dev)), "dif_decode")
+        for _ in range(3):
+            run()
+        ts = []
+        for _ in range(7):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); run(); e1.record(); torch.cuda.synchronize(dev)
+            ts.append(e0.elapsed_time(e1))
+        med = float(np.median(ts))
+        sps = n / (med * 1e-3)
+        sweep[f"2^{p2}"] = {"samples_per_s": sps, "ms_median": med, "ms_min": min(ts), "tflops_algorithmic": sps * DEC_FWD_FLOP / 1e12,
+                            "frac_of_bf16_burst_peak": sps * DEC_FWD_FLOP / 1e12 / pk["tf_burst"]}
+    return sweep
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -137,8 +267,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=24, help="frames of the stream timed for cpu_baseline")
+    ap.add_argument("--passes", type=int, default=0, help="timed passes over the K frames (0 = automatic: >= 5, more while the timed total is short)")
     ap.add_argument("--no-sweep", action="store_true", help="skip the decoder batch sweep (config 3) extras")
     ap.add_argument("--no-full-loop", action="store_true", help="skip the full track_camera + integrate + mesh loop extra")
+    ap.add_argument("--no-graph", action="store_true", help="launch the frame's kernels directly instead of replaying the captured CUDA graph")
     ap.add_argument("--sharded", action="store_true", help="N>1: ONE stream on a hash-sharded map (strong scaling) instead of N replicas")
     a = ap.parse_args()
     K, Wm = a.steps, max(a.warmup, 0)
@@ -156,7 +288,7 @@ def main():
         if rank != 0:
             return
         sc, frames = make_frames(max(K, Wm))
-        sec = run_cpu_port(frames, sc, K, min(Wm, 2), cores)
+        sec = run_cpu_port(frames, sc, K, Wm, cores)
         v = K / sec
         print(json.dumps({"impl": "reference", "metric": "frames/sec integrate+decode 640x480", "value": v, "unit": "frames/s", "n_gpus": a.gpus,
                           "steps": K, "warmup": Wm, "ms_per_step": 1e3 * sec / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -175,17 +307,14 @@ def main():
     torch.cuda.set_device(dev)
     from difusion_b200 import _lib
     from difusion_b200.network import utility as net_util
+    from difusion_b200.system.frame import HDR, ROW, pack_frame
     from difusion_b200.system.map import DenseIndexedMap
-    from difusion_b200.system.tracker import SDFTracker
-    from difusion_b200.utils.motion_util import Isometry, Rotation
     L = _lib.lib()                                          # raises if the CUDA library is missing: no fallback
     model, _ = net_util.load_model(str(ROOT / "tests" / "golden" / "weights.npz"))
 
     n_need = max(K, Wm)
     sc, frames = make_frames(n_need)
-    ident = Isometry()
-    poses = [Isometry(q=Rotation(matrix=fr["R"]), t=fr["t"]) for fr in frames]
-    trk_args = argparse.Namespace(sdf=dict(robust_kernel="huber", robust_k=5.0, subsample=0.5), rgb=None, iter_config=[{"n": 1, "type": [["sdf"]]}])
+    max_n = max(fr["pc"].shape[0] for fr in frames)
 
     def barrier():
         if world > 1:
@@ -193,121 +322,114 @@ def main():
         torch.cuda.synchronize(dev)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    # ------------------------------------------------------------------ device-resident arm (`value`)
-    d_frames = [dict(pc=torch.from_numpy(fr["pc"]).to(dev), xw=torch.from_numpy(fr["xw"]).to(dev), nw=torch.from_numpy(fr["nw"]).to(dev)) for fr in frames]
-
-    def dev_step(m, f, hooks=None):
-        fr, dfr = frames[f], d_frames[f]
-        if f >= 1:
-            if hooks:
-                L.dif_profile_hook(1, hooks[0].cuda_event, hooks[1].cuda_event)
-            m.icp_linearize(dfr["pc"], fr["R"], fr["t"], np.eye(3), np.zeros(3), huber_k=5.0, want_grad=True)
-        if hooks:
-            L.dif_profile_hook(0, hooks[2].cuda_event, hooks[3].cuda_event)
-        m.integrate_keyframe(dfr["xw"], dfr["nw"])
-
     sharded = a.sharded and world > 1
     if sharded:
-        from difusion_b200 import shard
-        sgroup = shard.ShardGroup()
+        return main_sharded_legacy(a, torch, dist, dev, model, sc, frames, config, rank, world, cores)
 
     def new_map():
-        if sharded:
-            return shard.make_sharded_map(model, sc.map_args(), 29, dev, sgroup, initial_capacity=1 << 19)
-        return DenseIndexedMap(model, sc.map_args(), 29, dev, initial_capacity=1 << 19)
+        return DenseIndexedMap(model, sc.map_args(), 29, dev, initial_capacity=1 << 21)
 
-    scratch_map = new_map()
-    for f in range(Wm):
-        dev_step(scratch_map, f)
-    torch.cuda.synchronize(dev)
-    del scratch_map
+    # packed frames ([header | interleaved point rows], system/frame.py): one pinned host copy and one device copy of each
+    h_packed, d_packed, n_pts = [], [], []
+    for f, fr in enumerate(frames):
+        buf = torch.zeros(HDR + ROW * fr["pc"].shape[0], dtype=torch.float32).pin_memory()
+        pack_frame(buf.numpy(), f, fr["pc"], fr["xw"], fr["nw"], fr["R"], fr["t"])
+        h_packed.append(buf); d_packed.append(buf.to(dev)); n_pts.append(fr["pc"].shape[0])
 
     m = new_map()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(K)]
-    for row in ev:                       # torch creates the CUDA event lazily: record once so .cuda_event is a live handle
+    pipe = m.frame_pipeline(max_n, huber_k=5.0, use_graph=not a.no_graph)
+    pipe_direct = m.frame_pipeline(max_n, huber_k=5.0, use_graph=False)          # per-kernel event hooks need direct launches
+
+    def run_pass(src, p, timed_events=None, sync_each=False, hooks=None, collect=None, do_reset=True):
+        """One pass over the K frames on the (reset) map.  src: packed frames (device or pinned host).  Frame 0 has nothing to
+        track against (empty map): integrate only, as in the reference loop (main.py:76-78 sets the first pose)."""
+        if do_reset:
+            m.reset()
+        main_s = torch.cuda.current_stream(dev)
+        k_next = p.upload(src[0], n_pts[0])
+        for f in range(K):
+            k = k_next
+            if f + 1 < K:                                              # the next frame's copy overlaps with this frame's kernels
+                k_next = p.upload(src[f + 1], n_pts[f + 1])
+            if timed_events is not None:
+                flush.zero_()
+                timed_events[f][0].record(main_s)
+            if hooks is not None:
+                if f >= 1:
+                    L.dif_profile_hook(1, hooks[f][0].cuda_event, hooks[f][1].cuda_event)
+                L.dif_profile_hook(0, hooks[f][2].cuda_event, hooks[f][3].cuda_event)
+            p.launch(k, track=f >= 1)
+            if timed_events is not None:
+                timed_events[f][1].record(main_s)
+            if sync_each or collect is not None:
+                icp, st = p.sync()
+                if collect is not None:
+                    collect.append((float(icp[43]) if f >= 1 else 0.0, st[_lib.STAT_N_SAMPLES]))
+        p.sync()
+
+    # ------------------------------------------------------------------ warm-up: W frames through both pipelines (captures the graphs)
+    Ksave = K
+    K = min(max(Wm, 2), Ksave)
+    run_pass(d_packed, pipe)
+    run_pass(d_packed, pipe_direct)
+    K = Ksave
+    torch.cuda.synchronize(dev)
+
+    # ------------------------------------------------------------------ kernel pass: direct launches with per-kernel CUDA-event hooks
+    hook_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    for row in hook_ev:                  # torch creates the CUDA event lazily: record once so .cuda_event is a live handle
         for e in row:
             e.record()
-    sampler = ClockSampler(dev.index or 0)
-    barrier()
-    sampler.start()
+    counts = []
     L.dif_launch_count(1)
-    for f in range(K):
-        flush.zero_()
-        ev[f][0].record()
-        dev_step(m, f, hooks=ev[f][2:6])
-        ev[f][1].record()
-    barrier()
-    launches = int(L.dif_launch_count(1))
-    step_ms = [ev[f][0].elapsed_time(ev[f][1]) for f in range(K)]
-    icp_ms = [ev[f][2].elapsed_time(ev[f][3]) for f in range(1, K)]
-    enc_ms = [ev[f][4].elapsed_time(ev[f][5]) for f in range(K)]
-    total_ms = float(sum(step_ms))
+    run_pass(d_packed, pipe_direct, hooks=hook_ev, collect=counts)
+    torch.cuda.synchronize(dev)
+    launches_per_pass = int(L.dif_launch_count(1))
+    icp_ms = [hook_ev[f][0].elapsed_time(hook_ev[f][1]) for f in range(1, K)]
+    enc_ms = [hook_ev[f][2].elapsed_time(hook_ev[f][3]) for f in range(K)]
+    icp_samples = [c[0] for c in counts[1:]]
+    enc_samples = [c[1] for c in counts]
     n_occ = m.n_occupied
     stats_dev = m.last_integrate_stats
 
-    # per-kernel algorithmic work (needs the per-frame sample counts: replay the counters cheaply through a second map)
-    m2 = new_map()
-    enc_samples, icp_samples = [], []
-    for f in range(K):
-        if f >= 1:
-            o = m2.icp_linearize(d_frames[f]["pc"], frames[f]["R"], frames[f]["t"], np.eye(3), np.zeros(3), 5.0, True)
-            icp_samples.append(float(o[43].item()))
-        m2.integrate_keyframe(d_frames[f]["xw"], d_frames[f]["nw"])
-        _ = m2.n_occupied
-        enc_samples.append(m2.last_integrate_stats["n_samples"])
-    del m2
-
-    # ------------------------------------------------------------------ end-to-end arm through the public API, host buffers
-    # Inputs live in pinned host memory.  Every step uploads its own frame (points cam, points world, normals world) and reads
-    # back the 44-double ICP result + the integrate counters, with a host sync (the pose update needs H, g on the host).
-    # The upload of frame f+1 is issued on a copy stream before frame f is computed (double-buffered device staging), the way a
-    # streaming SLAM front end would; it is inside the timed region.  Timed by wall clock around the whole loop (no L2 flush:
-    # every step's inputs are fresh host data) with a device sync on both sides.
-    # one pinned block per frame [3][n][3] = (points cam, points world, normals world) -> ONE H2D copy per frame
-    h_frames = [torch.from_numpy(np.stack([fr["pc"], fr["xw"], fr["nw"]])).pin_memory() for fr in frames]
-    max_n = max(fr["pc"].shape[0] for fr in frames)
-    stage = [torch.empty((3 * max_n, 3), device=dev) for _ in range(2)]
-    copy_stream = torch.cuda.Stream(device=dev)
-    copied = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
-    h2d = d2h = 0
-
-    def upload(f):
-        hf = h_frames[f]
-        n_f = hf.size(1)
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[f % 2])                  # the previous user of this staging buffer is done
-            stage[f % 2][:3 * n_f].copy_(hf.view(3 * n_f, 3), non_blocking=True)
-            copied[f % 2].record(copy_stream)
-        return 3 * n_f * 3 * 4
-
-    m3 = new_map()
-    trk = SDFTracker(m3, trk_args)
-    for e in consumed:
-        e.record()
+    # ------------------------------------------------------------------ device-resident arm (`value`): graph replay, events per step
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
+    sampler = ClockSampler(dev.index or 0)
     barrier()
-    wall0 = time.perf_counter()
-    h2d += upload(0)
-    main = torch.cuda.current_stream(dev)
-    for f in range(K):
-        if f + 1 < K:
-            h2d += upload(f + 1)                                     # overlaps with this frame's kernels
-        main.wait_event(copied[f % 2])
-        n_f = h_frames[f].size(1)
-        st_ = stage[f % 2]
-        pc, xw, nw = st_[:n_f], st_[n_f:2 * n_f], st_[2 * n_f:3 * n_f]
-        if f >= 1:
-            H, g, E = trk.compute_sdf_Hg(0, poses[f], ident, pc, no_grad=False)        # D2H of 44 doubles + sync inside
-        m3.integrate_keyframe(xw, nw)
-        _ = m3.n_occupied                                                               # D2H of the integrate counters + sync
-        consumed[f % 2].record(main)
-        d2h += (44 * 8 if f >= 1 else 0) + 8 * 4
+    sampler.start()
+    pass_ms, pass_steps = [], []
+    n_pass = a.passes if a.passes > 0 else 5
+    p_i = 0
+    while p_i < n_pass:
+        run_pass(d_packed, pipe, timed_events=ev)
+        torch.cuda.synchronize(dev)
+        step_ms = [ev[f][0].elapsed_time(ev[f][1]) for f in range(K)]
+        pass_ms.append(float(sum(step_ms))); pass_steps.append(step_ms)
+        p_i += 1
+        if a.passes == 0 and p_i == n_pass and n_pass < 25 and sum(pass_ms) < 250.0:
+            n_pass += 2                                               # short timed total: keep sampling (bounded)
+    barrier()
+    assert m.n_occupied == n_occ, "graph replay and direct launches diverged"
+    order = np.argsort(pass_ms)
+    med_i = int(order[len(order) // 2])
+    total_ms = pass_ms[med_i]
+    step_ms = pass_steps[med_i]
+
+    # ------------------------------------------------------------------ end-to-end arm: pinned host frames, sync every frame
+    e2e_pass_ms = []
+    h2d = sum(int(b.numel()) * 4 for b in h_packed[:K])
+    d2h = K * _lib.FRAME_RESULT_BYTES
+    for _ in range(len(pass_ms)):
+        m.reset()
+        barrier()
+        w0 = time.perf_counter()
+        run_pass(h_packed, pipe, sync_each=True, do_reset=False)
+        torch.cuda.synchronize(dev)
+        e2e_pass_ms.append(1e3 * (time.perf_counter() - w0))
     barrier()
     sampler.stop_flag = True
-    e2e_wall = time.perf_counter() - wall0
-    e2e_ms = 1e3 * e2e_wall
-    assert m3.n_occupied == n_occ, "e2e and device-resident arms diverged"
+    assert m.n_occupied == n_occ, "e2e and device-resident arms diverged"
+    e2e_ms = float(np.median(e2e_pass_ms))
 
     # max over ranks
     if world > 1:
@@ -323,133 +445,28 @@ def main():
     enc_flop = ENC_FLOP * float(sum(enc_samples))
     icp_flop = (DEC_FWD_FLOP + DEC_BWD_FLOP) * float(sum(icp_samples))
     enc_t, icp_t = sum(enc_ms) * 1e-3, sum(icp_ms) * 1e-3
-    dom = "enc::encode_tc_kernel" if enc_t >= icp_t else "tc::icp_tc_kernel"
-    dflop, dt, dn = (enc_flop, enc_t, len(enc_ms)) if enc_t >= icp_t else (icp_flop, icp_t, len(icp_ms))
+    dom_enc = enc_t >= icp_t
+    dom = "enc::encode_tc_kernel" if dom_enc else "tc::icp_tc_kernel"
+    dflop, dt, dn = (enc_flop, enc_t, len(enc_ms)) if dom_enc else (icp_flop, icp_t, len(icp_ms))
     achieved = dflop / dt / 1e12 if dt > 0 else 0.0
-
-    def ncu_traffic(tag):                                   # dram read+write bytes per launch from the committed ncu --set full capture
-        f = ROOT / "profiles" / f"r1_ncu_{tag}_metrics.csv"
-        if not f.exists():
-            return None
-        tot = 0.0
-        for line in f.read_text().splitlines():
-            k, u, v = line.split(",")[:3]
-            if k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                tot += float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
-        return tot
+    traffic, traffic_src = ncu_traffic("encode_tc" if dom_enc else "icp_tc")
     roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tf_sustained"], "traffic": ncu_traffic("encode_tc" if enc_t >= icp_t else "icp_tc"),
+                "frac": achieved / pk["tf_sustained"], "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": pk["src"] + ", bf16 sustained (kernel timed inside a long step)",
                 "avg_launch_ms": 1e3 * dt / max(dn, 1), "algorithmic_flop_per_launch": dflop / max(dn, 1),
                 "share_of_step": dt / (total_ms * 1e-3),
+                "kernel_ms_sum_per_step": (enc_t + icp_t) * 1e3 / K,
                 "note": "tcgen05 kernels, ALGORITHMIC FLOPs per SURVEY 8(d) (decoder fwd 98816 + bwd 91904, encoder 52096 per sample); the tensor pipe issues "
-                        "3x that (fp16 hi/lo split passes).  A frame is only ~250 tiles of 128 samples, so these launches are latency-bound; the large-batch "
-                        "figure for the same MMA pipeline is in decoder_sweep / profiles/",
-                "other": {"enc::encode_tc_kernel": {"ms_total": sum(enc_ms), "tflops": enc_flop / enc_t / 1e12 if enc_t else 0, "samples": int(sum(enc_samples))},
-                          "tc::icp_tc_kernel": {"ms_total": sum(icp_ms), "tflops": icp_flop / icp_t / 1e12 if icp_t else 0, "samples": int(sum(icp_samples))}}}
+                        "3x that (fp16 hi/lo split passes).  Kernel durations from CUDA events around the kernel in a direct-launch pass over the same "
+                        "frames (event hooks cannot sit inside a replayed graph).  A frame is only ~250 tiles of 128 samples, so these launches are "
+                        "latency-bound; the large-batch figure for the same MMA pipeline is in decoder_sweep / profiles/",
+                "other": {"enc::encode_tc_kernel": {"ms_total": sum(enc_ms), "tflops": enc_flop / enc_t / 1e12 if enc_t else 0, "samples": int(sum(enc_samples)),
+                                                    "frac": (enc_flop / enc_t / 1e12 / pk["tf_sustained"]) if enc_t else 0},
+                          "tc::icp_tc_kernel": {"ms_total": sum(icp_ms), "tflops": icp_flop / icp_t / 1e12 if icp_t else 0, "samples": int(sum(icp_samples)),
+                                                "frac": (icp_flop / icp_t / 1e12 / pk["tf_sustained"]) if icp_t else 0}}}
 
-    # ------------------------------------------------------------------ extra: the FULL reference loop (main.py:60-94) on RGB-D images
-    # track_camera (pyramid, unproject, radius outlier, normals, box filter, Gauss-Newton over the shipped 3-group iter_config with
-    # sdf + rgb terms) + integrate_keyframe every frame + one incremental mesh extraction every 10 frames.  Images device-resident,
-    # wall clock.  Not the headline metric (that is the integrate+decode step above); it shows the rest of the loop runs on the GPU.
-    full_loop = {}
-    if not a.no_full_loop:
-        try:
-            from difusion_b200 import synthetic as S
-
-            class _Calib:
-                fx, fy, cx, cy = S.ICL_FX, S.ICL_FY, S.ICL_CX, S.ICL_CY
-                def to_K(self):
-                    return np.asarray([[self.fx, 0.0, self.cx], [0.0, self.fy, self.cy], [0.0, 0.0, 1.0]])
-            n_full = 24
-            imgs = []
-            for f in range(n_full):
-                R, t = S.orbit_pose(f, STREAM_LEN)
-                rgb, depth = S.render_rgbd(sc, R, t, step=1)
-                imgs.append((torch.from_numpy(rgb).to(dev), torch.from_numpy(depth).to(dev), Isometry(q=Rotation(matrix=R), t=t)))
-            full_args = argparse.Namespace(
-                sdf=dict(robust_kernel="huber", robust_k=5.0, subsample=0.5),
-                rgb=dict(weight=500.0, robust_kernel=None, robust_k=0.01, min_grad_scale=0.0, max_depth_delta=0.2),
-                iter_config=[{"n": 10, "type": [["rgb", 2]]}, {"n": 10, "type": [["sdf"], ["rgb", 1]]}, {"n": 50, "type": [["sdf"], ["rgb", 0]]}])
-            for rep in range(2):                                   # rep 0 warms allocators / scratch
-                m4 = new_map() if not sharded else DenseIndexedMap(model, sc.map_args(), 29, dev, initial_capacity=1 << 19)
-                trk4 = SDFTracker(m4, full_args)
-                n_iter = 0
-                orig = trk4.compute_sdf_Hg
-                def counted(*aa, **kk):
-                    nonlocal n_iter
-                    n_iter += 1
-                    return orig(*aa, **kk)
-                trk4.compute_sdf_Hg = counted
-                torch.cuda.synchronize(dev)
-                w0 = time.perf_counter()
-                t_err = []
-                for f, (rgb_d, depth_d, gt) in enumerate(imgs):
-                    pose = trk4.track_camera(rgb_d, depth_d, _Calib(), set_pose=gt if f == 0 else None)
-                    pc_c, n_c = trk4.last_processed_pc
-                    m4.integrate_keyframe(pose @ pc_c, pose.rotation @ n_c)
-                    if f % 10 == 9:
-                        m4.extract_mesh(4, int(4e6), max_std=0.15)
-                    t_err.append(float(np.linalg.norm(pose.t - gt.t)))
-                    gpu_t = (gpu_t + [np.asarray(pose.t, float)]) if f else [np.asarray(pose.t, float)]
-                torch.cuda.synchronize(dev)
-                w1 = time.perf_counter()
-            full_loop = {"frames": n_full, "frames_per_s": n_full / (w1 - w0), "ms_per_frame": 1e3 * (w1 - w0) / n_full,
-                         "sdf_linearisations_per_frame": n_iter / max(n_full - 1, 1), "max_translation_error_m": max(t_err),
-                         "what": "track_camera(rgb, depth) with the shipped 3-group iter_config + integrate_keyframe per frame + incremental "
-                                 "extract_mesh every 10 frames; 640x480 device-resident images; wall clock"}
-        except Exception as e:                                      # the extra must never take the bench line down
-            full_loop = {"error": f"{type(e).__name__}: {e}"}
-        # the same loop on the host cores: oracle/loop_oracle.py (the reference's tracker front end + Gauss-Newton driver sequenced
-        # over the pinned oracle pieces), bounded sample of 3 frames of the same stream, no meshing
-        try:
-            from difusion_b200 import synthetic as S
-            from oracle import dif_oracle as O, loop_oracle as Lp
-            torch.set_num_threads(cores)
-            Wc = O.load_weights_npz(ROOT / "tests" / "golden" / "weights.npz")
-            cpu_frames = []
-            for f in range(3):
-                R, t = S.orbit_pose(f, STREAM_LEN)
-                rgb, depth = S.render_rgbd(sc, R, t, step=1)
-                cpu_frames.append((rgb, depth, (R, t)))
-            c0 = time.perf_counter()
-            cpu_poses, _, _ = Lp.run_loop(Wc, sc.map_args(), cpu_frames, full_args.iter_config, S.ICL_FX, S.ICL_FY, S.ICL_CX, S.ICL_CY)
-            c1 = time.perf_counter()
-            full_loop["cpu_port"] = {"frames_per_s": 3 / (c1 - c0), "cores": cores, "kind": "port",
-                                     "sample": "frames 0..2 of the same RGB-D stream, oracle/loop_oracle.py, same iter_config, no meshing"}
-            try:                                                    # tracked poses of the two paths on the same frames (informational)
-                full_loop["cpu_port"]["max_translation_diff_gpu_vs_cpu_m"] = max(
-                    float(np.linalg.norm(cp[1] - gt_)) for cp, gt_ in zip(cpu_poses, gpu_t[:3]))
-            except NameError:
-                pass
-        except Exception as e:
-            full_loop["cpu_port"] = {"error": f"{type(e).__name__}: {e}"}
-
-    # ------------------------------------------------------------------ config 3 extras: decoder batch sweep (samples/s)
-    sweep = {}
-    if not a.no_sweep:
-        prep = net_util.prepared_for(model, dev)
-        table = m._latent[:max(n_occ, 1)]
-        g = torch.Generator(device="cpu").manual_seed(0)
-        for p2 in (14, 16, 18, 20, 22):
-            n = 1 << p2
-            rows = torch.randint(0, max(n_occ, 1), (n,), generator=g, dtype=torch.int32).to(dev)
-            xyz = (torch.rand(n, 3, generator=g) * 2 - 1).to(dev)
-            sdf = torch.empty(n, device=dev); std = torch.empty(n, device=dev)
-            def run():
-                _lib.check(L.dif_decode(prep.decoder.data_ptr(), table.data_ptr(), rows.data_ptr(), xyz.data_ptr(), n, None, 1.0,
-                                        sdf.data_ptr(), std.data_ptr(), None, None, _lib.stream_ptr(dev)), "dif_decode")
-            for _ in range(3):
-                run()
-            best = 1e30
-            for _ in range(5):
-                flush.zero_()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(); run(); e1.record(); torch.cuda.synchronize(dev)
-                best = min(best, e0.elapsed_time(e1))
-            sps = n / (best * 1e-3)
-            sweep[f"2^{p2}"] = {"samples_per_s": sps, "tflops_algorithmic": sps * DEC_FWD_FLOP / 1e12,
-                                "frac_of_bf16_burst_peak": sps * DEC_FWD_FLOP / 1e12 / pk["tf_burst"]}
+    full_loop = {} if a.no_full_loop else extra_full_loop(torch, dev, model, sc, lambda: DenseIndexedMap(model, sc.map_args(), 29, dev, initial_capacity=1 << 19), cores)
+    sweep = {} if a.no_sweep else extra_decoder_sweep(torch, dev, L, _lib, net_util, model, m._latent[:max(n_occ, 1)], n_occ, flush, pk)
 
     # ------------------------------------------------------------------ cpu baseline: the oracle port on the host cores (bounded sample)
     ns = max(1, min(a.cpu_sample, K))
@@ -459,17 +476,69 @@ def main():
                      f"oracle/dif_oracle.py on torch CPU fp32 with {cores} threads"}
     gpu_prefix_ms = float(sum(step_ms[:ns]))
 
-    out = {"metric": "frames/sec integrate+decode 640x480", "value": (1 if sharded else world) * K / (total_ms * 1e-3), "unit": "frames/s", "n_gpus": world,
-           "steps": K, "warmup": Wm, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
+    out = {"metric": "frames/sec integrate+decode 640x480", "value": world * K / (total_ms * 1e-3), "unit": "frames/s", "n_gpus": world,
+           "steps": K, "warmup": Wm, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic", "config": config, "clocks": sampler.summary(),
-           "e2e": {"value": (1 if sharded else world) * K / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K,
-                   "ms_per_step": e2e_ms / K, "timing": "wall clock around the K-step loop, device sync on both sides; upload of frame f+1 overlaps frame f"},
-           "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+           "passes": {"n": len(pass_ms), "frames_per_s_median": K / (total_ms * 1e-3), "frames_per_s_min": K / (max(pass_ms) * 1e-3),
+                      "frames_per_s_max": K / (min(pass_ms) * 1e-3), "ms_per_pass": pass_ms, "timed_total_ms": sum(pass_ms),
+                      "what": "each pass = the K steps on the map reset in place; value = median pass (rank 0; ms_per_step = max over ranks of the median)"},
+           "e2e": {"value": world * K / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K,
+                   "ms_per_step": e2e_ms / K, "ms_per_pass": e2e_pass_ms,
+                   "timing": "wall clock around the K-step loop (median pass), device sync on both sides; upload of frame f+1 overlaps frame f; host sync + "
+                             "400-byte result read every frame"},
+           "gpu_launches": launches_per_pass, "launch_mode": "direct launches" if a.no_graph else
+           f"one CUDA-graph replay per step ({launches_per_pass} kernels per {K}-step pass inside the graphs, counted in the direct-launch pass)",
+           "roofline": roofline, "cpu_baseline": cpu,
            "same_prefix": {"frames": ns, "gpu_frames_per_s": ns / (gpu_prefix_ms * 1e-3), "cpu_frames_per_s": ns / cpu_sec},
            "map": {"n_occupied": n_occ, "last_integrate": stats_dev}, "decoder_sweep": sweep, "full_loop": full_loop}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def main_sharded_legacy(a, torch, dist, dev, model, sc, frames, config, rank, world, cores):
+    """ONE stream on the hash-sharded map (difusion_b200/shard.py), direct calls; prints its own JSON line on rank 0."""
+    from difusion_b200 import _lib, shard
+    K, Wm = a.steps, max(a.warmup, 0)
+    L = _lib.lib()
+    sgroup = shard.ShardGroup()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    d_frames = [dict(pc=torch.from_numpy(fr["pc"]).to(dev), xw=torch.from_numpy(fr["xw"]).to(dev), nw=torch.from_numpy(fr["nw"]).to(dev)) for fr in frames]
+
+    def new_map():
+        return shard.make_sharded_map(model, sc.map_args(), 29, dev, sgroup, initial_capacity=1 << 19)
+
+    def dev_step(m, f):
+        fr, dfr = frames[f], d_frames[f]
+        if f >= 1:
+            m.icp_linearize(dfr["pc"], fr["R"], fr["t"], np.eye(3), np.zeros(3), huber_k=5.0, want_grad=True)
+        m.integrate_keyframe(dfr["xw"], dfr["nw"])
+    scratch_map = new_map()
+    for f in range(Wm):
+        dev_step(scratch_map, f)
+    torch.cuda.synchronize(dev)
+    del scratch_map
+    m = new_map()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
+    dist.barrier(); torch.cuda.synchronize(dev)
+    L.dif_launch_count(1)
+    for f in range(K):
+        flush.zero_()
+        ev[f][0].record()
+        dev_step(m, f)
+        ev[f][1].record()
+    dist.barrier(); torch.cuda.synchronize(dev)
+    launches = int(L.dif_launch_count(1))
+    total_ms = float(sum(ev[f][0].elapsed_time(ev[f][1]) for f in range(K)))
+    tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms = float(tt.item())
+    n_occ = m.n_occupied
+    if rank == 0:
+        print(json.dumps({"metric": "frames/sec integrate+decode 640x480", "value": K / (total_ms * 1e-3), "unit": "frames/s", "n_gpus": world,
+                          "steps": K, "warmup": Wm, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                          "dtype": "f32", "data": "synthetic", "config": config, "gpu_launches": launches, "map": {"n_occupied": n_occ}}))
+    dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -11,8 +11,12 @@ from pathlib import Path
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ["DIF_LIB_PATH"]) if os.environ.get("DIF_LIB_PATH") else _HERE / "libdifusion_b200.so"   # override: kernel A/B builds (tools/)
 
-DIF_STAT_COUNT = 8
-STAT_N_KEPT, STAT_N_NEW, STAT_N_SAMPLES, STAT_N_UPDATED, STAT_N_OCCUPIED, STAT_FLAGS, STAT_N_FOCUSED, STAT_N_XCHG = range(8)
+ABI_VERSION = 2
+DIF_STAT_COUNT = 12
+STAT_N_KEPT, STAT_N_NEW, STAT_N_SAMPLES, STAT_N_UPDATED, STAT_N_OCCUPIED, STAT_FLAGS, STAT_N_FOCUSED, STAT_N_XCHG, STAT_SEQ = range(9)
+FRAME_HEADER_FLOATS, FRAME_POINT_FLOATS = 32, 9           # DIF_FRAME_HEADER_FLOATS / DIF_FRAME_POINT_FLOATS
+FRAME_TRACK, FRAME_INTEGRATE = 1, 2
+FRAME_RESULT_BYTES = 44 * 8 + DIF_STAT_COUNT * 4
 
 
 class MapView(C.Structure):
@@ -23,6 +27,11 @@ class MapView(C.Structure):
                 ("bound_min", C.c_float * 3), ("voxel_size", C.c_float), ("prune_min_vox_obs", C.c_int32),
                 ("ignore_count_th", C.c_float), ("encoder_count_th", C.c_float),
                 ("shard_rank", C.c_int32), ("shard_world", C.c_int32), ("xchg_slots", C.c_void_p)]
+
+
+class FrameParams(C.Structure):
+    """struct dif_frame_params (the per-frame block the kernels read from DEVICE memory)"""
+    _fields_ = [("n_points", C.c_int32), ("seq", C.c_int32), ("reserved", C.c_int32 * 2), ("pose", C.c_float * 24)]
 
 
 _P, _I64, _I32, _F, _SZ = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_size_t
@@ -46,12 +55,13 @@ SIGNATURES = {
     "dif_prepare_encoder": (C.c_int, [_P, _P, _P]),
     "dif_integrate_persist_bytes": (_SZ, [_I64, _I64]),
     "dif_integrate_scratch_bytes": (_SZ, [_I64]),
-    "dif_integrate": (C.c_int, [_MV, _P, _P, _P, _I64, _P, _P, _SZ, _P, _SZ, _P, _P]),
+    "dif_integrate": (C.c_int, [_MV, _P, _P, _P, _I64, _P, _P, _P, _SZ, _P, _SZ, _P, _P]),
     "dif_decode": (C.c_int, [_P, _P, _P, _P, _I64, _P, _F, _P, _P, _P, _P, _P]),
     "dif_encode": (C.c_int, [_P, _P, _I64, _P, _P]),
     "dif_map_query": (C.c_int, [_MV, _P, _I64, _P, _P, _P, _P]),
     "dif_icp_scratch_bytes": (_SZ, [_I64]),
-    "dif_icp_linearize": (C.c_int, [_MV, _P, _P, _I64, _P, _F, C.c_int, _P, _SZ, _P, _P]),
+    "dif_icp_linearize": (C.c_int, [_MV, _P, _P, _I64, _P, _P, _F, C.c_int, _P, _SZ, _P, _P]),
+    "dif_frame": (C.c_int, [_MV, _P, _P, _P, _I64, _P, _F, C.c_int, _P, _P, _SZ, _P, _SZ, _P, _SZ, _P, _P]),
     "dif_mesh_select_scratch_bytes": (_SZ, [_I64, _I64]),
     "dif_mesh_select": (C.c_int, [_MV, _P, _I64, _P, _P, _P, _P, _P, _SZ, _P]),
     "dif_mesh_decode_scratch_bytes": (_SZ, [_I64, C.c_int]),
@@ -94,7 +104,7 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             f = getattr(h, name)
             f.restype, f.argtypes = res, args
-        if h.dif_abi_version() != 1:
+        if h.dif_abi_version() != ABI_VERSION:
             raise DifusionLibraryError("ABI version mismatch")
         _lib = h
     return _lib

@@ -364,7 +364,8 @@ int launch_decode_tc(const void* prepared, DecodeArgs a, int64_t n_max, cudaStre
     const unsigned char* image = (const unsigned char*)prepared + (size_t)DecW::FP32_END * sizeof(float);
     const int64_t n_tiles = (n_max + tc::TILE - 1) / tc::TILE;
     const int grid = (int)(n_tiles < DIF_NUM_SMS ? n_tiles : DIF_NUM_SMS);
-    cudaFuncSetAttribute(tc::decode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_B);
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(tc::decode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_B); attr_set = true; }
     prof_begin(DIF_PROF_DECODE, st);
     tc::decode_tc_kernel<<<grid, tc::THREADS, tc::SMEM_B, st>>>(image, P, a);
     prof_end(DIF_PROF_DECODE, st);

@@ -40,7 +40,7 @@ struct EncodeArgs {
     // mode 0: samples come from the integrate sample list (point index, offset index, target slot); results are accumulated
     //         into slot_sum.  mode 1: explicit (n, 6) inputs, results stored to out (n, 29)  (dif_encode).
     int mode;
-    Grid g; const float* p_hat; const float* normal; const int32_t* s_pt; const int32_t* s_slot; const uint8_t* s_off;
+    Grid g; const float* p_hat; const float* normal; int normal_stride; const int32_t* s_pt; const int32_t* s_slot; const uint8_t* s_off;
     const int32_t* n_dev; float* slot_sum;
     const float* xyzn; int64_t n; float* out;
 };
@@ -183,7 +183,8 @@ __global__ void __launch_bounds__(THREADS, 1) encode_tc_kernel(const unsigned ch
                             const float cz = (float)clampi((int)ceilf(__fadd_rn(pz, oz)) - 1, 0, a.g.nz - 1);
                             // rel = p - cell - 0.5, two separately rounded subtractions as in map.py:425
                             in[0] = __fsub_rn(__fsub_rn(px, cx), 0.5f); in[1] = __fsub_rn(__fsub_rn(py, cy), 0.5f); in[2] = __fsub_rn(__fsub_rn(pz, cz), 0.5f);
-                            in[3] = a.normal[3 * i]; in[4] = a.normal[3 * i + 1]; in[5] = a.normal[3 * i + 2];
+                            const float* np_ = a.normal + (int64_t)a.normal_stride * i;
+                            in[3] = np_[0]; in[4] = np_[1]; in[5] = np_[2];
                         } else {
                             slot = 0;
 #pragma unroll
@@ -333,7 +334,8 @@ int prepare_encoder_tc(const float* P, unsigned char* image, cudaStream_t st) {
 static int launch(const unsigned char* image, const enc::EncodeArgs& a, int64_t max_samples, cudaStream_t st) {
     const int64_t max_tiles = (max_samples + tc::TILE - 1) / tc::TILE;
     const int grid = (int)(max_tiles < DIF_NUM_SMS ? (max_tiles > 0 ? max_tiles : 1) : DIF_NUM_SMS);
-    cudaFuncSetAttribute(enc::encode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc::ESMEM_B);
+    static bool attr_set = false;        // once per process: keeps the launch path free of non-stream API calls (CUDA-graph capture)
+    if (!attr_set) { cudaFuncSetAttribute(enc::encode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc::ESMEM_B); attr_set = true; }
     prof_begin(DIF_PROF_ENCODE, st);
     launch_pdl(enc::encode_tc_kernel, grid, tc::THREADS, enc::ESMEM_B, st, image, a);
     prof_end(DIF_PROF_ENCODE, st);
@@ -342,18 +344,18 @@ static int launch(const unsigned char* image, const enc::EncodeArgs& a, int64_t 
 }
 
 // integrate path: samples from the gather list (device-side count), accumulate into slot_sum
-int launch_encode_accumulate_tc(const void* encoder_prepared, Grid g, const float* p_hat, const float* normal, const int32_t* s_pt,
+int launch_encode_accumulate_tc(const void* encoder_prepared, Grid g, const float* p_hat, const float* normal, int normal_stride, const int32_t* s_pt,
                                 const int32_t* s_slot, const uint8_t* s_off, const int32_t* n_dev, int64_t max_samples, float* slot_sum,
                                 cudaStream_t st) {
     const unsigned char* image = (const unsigned char*)encoder_prepared + (size_t)EncW::FP32_END * sizeof(float);
-    enc::EncodeArgs a{0, g, p_hat, normal, s_pt, s_slot, s_off, n_dev, slot_sum, nullptr, 0, nullptr};
+    enc::EncodeArgs a{0, g, p_hat, normal, normal_stride, s_pt, s_slot, s_off, n_dev, slot_sum, nullptr, 0, nullptr};
     return launch(image, a, max_samples, st);
 }
 
 // dif_encode path: explicit (n, 6) inputs -> (n, 29) outputs
 int launch_encode_tc(const void* encoder_prepared, const float* xyzn, int64_t n, float* out, cudaStream_t st) {
     const unsigned char* image = (const unsigned char*)encoder_prepared + (size_t)EncW::FP32_END * sizeof(float);
-    enc::EncodeArgs a{1, Grid{}, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, xyzn, n, out};
+    enc::EncodeArgs a{1, Grid{}, nullptr, nullptr, 3, nullptr, nullptr, nullptr, nullptr, nullptr, xyzn, n, out};
     return launch(image, a, n, st);
 }
 

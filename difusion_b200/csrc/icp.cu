@@ -14,14 +14,20 @@ namespace dif {
 constexpr int ICP_VALS = 32;     // 21 upper-tri H + 6 g + E + M, padded
 
 __global__ void __launch_bounds__(MLP_THREADS) icp_linearize_kernel(
-        MapRO m, const float* __restrict__ P, const float* __restrict__ obs, int n, Pose pose, float huber_k, int want_grad,
-        float* __restrict__ partials, unsigned int* __restrict__ done_counter, double* __restrict__ out) {
+        MapRO m, const float* __restrict__ P, const float* __restrict__ obs, int obs_stride, int n_host, const dif_frame_params* __restrict__ frame,
+        Pose pose_host, float huber_k, int want_grad, float* __restrict__ partials, unsigned int* __restrict__ done_counter,
+        double* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DecoderSmem& s = *reinterpret_cast<DecoderSmem*>(smem_raw);
     __shared__ float q_s[3 * MLP_T];
     __shared__ float r_s[MLP_T];
     __shared__ int slot_s[MLP_T];
     __shared__ bool is_last;
+    __shared__ IcpFrame fr_s;
+    if (threadIdx.x == 0) icp_resolve_frame(frame, pose_host, n_host, fr_s);
+    __syncthreads();
+    const Pose& pose = fr_s.pose;
+    const int n = fr_s.n;
     float acc[29];                               // meaningful on lane 0 of warp 0 only
 #pragma unroll
     for (int j = 0; j < 29; ++j) acc[j] = 0.f;
@@ -33,7 +39,8 @@ __global__ void __launch_bounds__(MLP_THREADS) icp_linearize_kernel(
             const int t = threadIdx.x, i = base + t;
             int slot = -1; float rx = 0.f, ry = 0.f, rz = 0.f;
             if (i < n) {
-                const float x = obs[3 * i], y = obs[3 * i + 1], z = obs[3 * i + 2];
+                const float* op = obs + (int64_t)obs_stride * i;
+                const float x = op[0], y = op[1], z = op[2];
                 // cur = (last . delta) @ obs  (tracker.py:181, motion_util.py:322-327)
                 const float wx = fmaf(z, pose.Rc[2], fmaf(y, pose.Rc[1], x * pose.Rc[0])) + pose.tc[0];
                 const float wy = fmaf(z, pose.Rc[5], fmaf(y, pose.Rc[4], x * pose.Rc[3])) + pose.tc[1];
@@ -135,35 +142,17 @@ __global__ void __launch_bounds__(MLP_THREADS) icp_linearize_kernel(
 
 }  // namespace dif
 
-using namespace dif;
+extern "C" size_t dif_icp_scratch_bytes(int64_t n);
 
-extern "C" {
-
-size_t dif_icp_scratch_bytes(int64_t n) {
-    (void)n;
-    return align_up((size_t)DIF_NUM_SMS * 3 * ICP_VALS * sizeof(float)) + 256;
-}
-
-int dif_icp_linearize(const dif_map_view* map, const void* decoder_prepared, const float* obs_xyz, int64_t n, const float* pose_host,
-                      float huber_k, int want_grad, void* scratch, size_t scratch_sz, double* out_dev, void* stream) {
-    if (!map || !decoder_prepared || !pose_host || !scratch || !out_dev || n < 0 || n >= (int64_t(1) << 31) || (n > 0 && !obs_xyz)) return DIF_E_INVALID;
+namespace dif {
+int icp_launch(const dif_map_view* map, const void* decoder_prepared, const float* obs_xyz, int obs_stride, int64_t n, const float* pose_host,
+               const dif_frame_params* frame_dev, float huber_k, int want_grad, void* scratch, size_t scratch_sz, double* out_dev, cudaStream_t st) {
+    if (!map || !decoder_prepared || (!pose_host && !frame_dev) || !scratch || !out_dev || n < 0 || n >= (int64_t(1) << 31) || (n > 0 && !obs_xyz))
+        return DIF_E_INVALID;
     if (scratch_sz < dif_icp_scratch_bytes(n)) return DIF_E_WORKSPACE;
-    cudaStream_t st = (cudaStream_t)stream;
     MapRO m{map->indexer, map->latent_vecs, map->voxel_obs_count, make_grid(map), map->ignore_count_th};
-    const float *Rl = pose_host, *tl = pose_host + 9, *Rd = pose_host + 12, *td = pose_host + 21;
-    Pose p;
-    for (int i = 0; i < 3; ++i) {
-        double t = tl[i];
-        for (int j = 0; j < 3; ++j) {
-            double a = 0;
-            for (int k = 0; k < 3; ++k) a += (double)Rl[3 * i + k] * Rd[3 * k + j];
-            p.Rc[3 * i + j] = (float)a;
-            t += (double)Rl[3 * i + j] * td[j];
-        }
-        p.tc[i] = (float)t;
-    }
-    for (int i = 0; i < 9; ++i) { p.Rd[i] = Rd[i]; p.Rl[i] = Rl[i]; }
-    for (int i = 0; i < 3; ++i) p.td[i] = td[i];
+    Pose p = {};
+    if (pose_host) compose_pose(pose_host, p);
     Carver c(scratch);
     float* partials = c.take<float>((size_t)DIF_NUM_SMS * 3 * ICP_VALS);
     unsigned int* counter = c.take<unsigned int>(1);
@@ -174,20 +163,36 @@ int dif_icp_linearize(const dif_map_view* map, const void* decoder_prepared, con
     const bool force_simt = path_env && path_env[0] == 's';
     if (!force_simt && n >= 2048) {
         static_assert((size_t)DIF_NUM_SMS * 32 * sizeof(double) <= (size_t)DIF_NUM_SMS * 3 * ICP_VALS * sizeof(float), "partials region");
-        IcpTcArgs a{m, obs_xyz, (int)n, p, huber_k, want_grad, reinterpret_cast<double*>(partials), counter, out_dev};
+        IcpTcArgs a{m, obs_xyz, obs_stride, (int)n, frame_dev, p, huber_k, want_grad, reinterpret_cast<double*>(partials), counter, out_dev};
         return launch_icp_tc(decoder_prepared, a, st);
     }
     const int64_t n_tiles = (n + MLP_T - 1) / MLP_T;
     int grid = (int)(n_tiles < DIF_NUM_SMS * 3 ? n_tiles : DIF_NUM_SMS * 3);
     if (grid < 1) grid = 1;
     const size_t smem = sizeof(DecoderSmem);
-    cudaFuncSetAttribute(icp_linearize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(icp_linearize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
     prof_begin(DIF_PROF_ICP, st);
-    icp_linearize_kernel<<<grid, MLP_THREADS, smem, st>>>(m, (const float*)decoder_prepared, obs_xyz, (int)n, p, huber_k, want_grad,
-                                                          partials, counter, out_dev);
+    icp_linearize_kernel<<<grid, MLP_THREADS, smem, st>>>(m, (const float*)decoder_prepared, obs_xyz, obs_stride, (int)n, frame_dev, p, huber_k,
+                                                          want_grad, partials, counter, out_dev);
     prof_end(DIF_PROF_ICP, st);
     DIF_COUNT_LAUNCH(1);
     return check_launch("icp_linearize_kernel");
+}
+}  // namespace dif
+
+using namespace dif;
+
+extern "C" {
+
+size_t dif_icp_scratch_bytes(int64_t n) {
+    (void)n;
+    return align_up((size_t)DIF_NUM_SMS * 3 * ICP_VALS * sizeof(float)) + 256;
+}
+
+int dif_icp_linearize(const dif_map_view* map, const void* decoder_prepared, const float* obs_xyz, int64_t n, const float* pose_host,
+                      const dif_frame_params* frame_dev, float huber_k, int want_grad, void* scratch, size_t scratch_sz, double* out_dev, void* stream) {
+    return icp_launch(map, decoder_prepared, obs_xyz, 3, n, pose_host, frame_dev, huber_k, want_grad, scratch, scratch_sz, out_dev, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -21,7 +21,9 @@ namespace dif {
 namespace tc {
 
 constexpr uint32_t OFF_AUX = OFF_BAR + 96 + 16;          // per slot: validity byte of the tile's 128 samples
-constexpr uint32_t ICP_SMEM_B = OFF_AUX + 2 * TILE;
+constexpr uint32_t OFF_FRAME = OFF_AUX + 2 * TILE;         // IcpFrame: pose + point count of the launch (host values or the device block)
+constexpr uint32_t ICP_SMEM_B = OFF_FRAME + 144;
+static_assert(sizeof(IcpFrame) <= 144, "frame block");
 static_assert(ICP_SMEM_B <= 232448, "shared memory budget");
 
 __device__ __forceinline__ constexpr uint32_t idesc_f16_bt(int N) { return idesc_f16(N) | (1u << 16); }      // B operand MN-major
@@ -63,16 +65,17 @@ __device__ __forceinline__ void convert_bwd16(const uint32_t* v, uint32_t mask, 
 }
 
 // producer: one observation per lane -> world point -> PLIVox lookup (map.py:565-575) -> latent row + rel xyz
-__device__ __forceinline__ void icp_gather_row(const IcpTcArgs& a, int64_t i, float (&x)[32], bool& valid) {
+__device__ __forceinline__ void icp_gather_row(const IcpTcArgs& a, const IcpFrame& fr, int64_t i, float (&x)[32], bool& valid) {
     valid = false;
     int64_t slot = 0;
     float rx = 0.f, ry = 0.f, rz = 0.f;
-    if (i < a.n) {
-        const float ox = __ldg(a.obs + 3 * i), oy = __ldg(a.obs + 3 * i + 1), oz = __ldg(a.obs + 3 * i + 2);
+    if (i < fr.n) {
+        const float* op = a.obs + (int64_t)a.obs_stride * i;
+        const float ox = __ldg(op), oy = __ldg(op + 1), oz = __ldg(op + 2);
         // cur = (last . delta) @ obs  (tracker.py:181, motion_util.py:322-327) -- same arithmetic as icp_linearize_kernel
-        const float wx = fmaf(oz, a.pose.Rc[2], fmaf(oy, a.pose.Rc[1], ox * a.pose.Rc[0])) + a.pose.tc[0];
-        const float wy = fmaf(oz, a.pose.Rc[5], fmaf(oy, a.pose.Rc[4], ox * a.pose.Rc[3])) + a.pose.tc[1];
-        const float wz = fmaf(oz, a.pose.Rc[8], fmaf(oy, a.pose.Rc[7], ox * a.pose.Rc[6])) + a.pose.tc[2];
+        const float wx = fmaf(oz, fr.pose.Rc[2], fmaf(oy, fr.pose.Rc[1], ox * fr.pose.Rc[0])) + fr.pose.tc[0];
+        const float wy = fmaf(oz, fr.pose.Rc[5], fmaf(oy, fr.pose.Rc[4], ox * fr.pose.Rc[3])) + fr.pose.tc[1];
+        const float wz = fmaf(oz, fr.pose.Rc[8], fmaf(oy, fr.pose.Rc[7], ox * fr.pose.Rc[6])) + fr.pose.tc[2];
         const float3 p = normalize_point(a.m.g, wx, wy, wz);
         const int ix = (int)ceilf(p.x) - 1, iy = (int)ceilf(p.y) - 1, iz = (int)ceilf(p.z) - 1;
         if (p.x == p.x && p.y == p.y && p.z == p.z && in_grid(a.m.g, ix, iy, iz)) {
@@ -93,8 +96,8 @@ __global__ void __launch_bounds__(THREADS, 1) icp_tc_kernel(const unsigned char*
     const uint32_t bar0 = sbase + OFF_BAR;
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 96);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t n_tiles = ((int64_t)a.n + TILE - 1) / TILE;
     const int n_stages = a.want_grad ? 8 : 4;
+    IcpFrame& fr = *reinterpret_cast<IcpFrame*>(smem + OFF_FRAME);
 
     if (threadIdx.x == 0) {
         mbar_init(bar0 + 8 * BAR_W, 1);
@@ -122,6 +125,9 @@ __global__ void __launch_bounds__(THREADS, 1) icp_tc_kernel(const unsigned char*
         for (uint32_t off = 0; off < IMAGE_B; off += CH) bulk_g2s(sbase + off, image + off, (IMAGE_B - off) < CH ? (IMAGE_B - off) : CH, bar0 + 8 * BAR_W);
     }
     pdl_wait(); pdl_launch_dependents();
+    if (threadIdx.x == 0) icp_resolve_frame(a.frame, a.pose, a.n, fr);     // (a device-side frame block is only read after the dependency wait)
+    __syncthreads();
+    const int64_t n_tiles = ((int64_t)fr.n + TILE - 1) / TILE;
 
     if (warp == MMA_WARP) {
         // ===================================================== MMA issuer (warp-uniform, instructions elected)
@@ -183,17 +189,17 @@ __global__ void __launch_bounds__(THREADS, 1) icp_tc_kernel(const unsigned char*
             bool va = false, vb = false;
             uint32_t ph_xf = 0;
             int64_t tile = blockIdx.x + (int64_t)gridDim.x * s;
-            if (tile < n_tiles) icp_gather_row(a, tile * TILE + lane, xa, va);
+            if (tile < n_tiles) icp_gather_row(a, fr, tile * TILE + lane, xa, va);
             for (int64_t it = 0; tile < n_tiles; ++it) {
                 if (it > 0) { mbar_wait(bar0 + 8 * (BAR_XF0 + s), ph_xf); ph_xf ^= 1; }
-                icp_gather_row(a, tile * TILE + 32 + lane, xb, vb);
+                icp_gather_row(a, fr, tile * TILE + 32 + lane, xb, vb);
                 gather_store_row(xa, va, lane, x_hi_p); aux[lane] = va;
-                icp_gather_row(a, tile * TILE + 64 + lane, xa, va);
+                icp_gather_row(a, fr, tile * TILE + 64 + lane, xa, va);
                 gather_store_row(xb, vb, 32 + lane, x_hi_p); aux[32 + lane] = vb;
-                icp_gather_row(a, tile * TILE + 96 + lane, xb, vb);
+                icp_gather_row(a, fr, tile * TILE + 96 + lane, xb, vb);
                 gather_store_row(xa, va, 64 + lane, x_hi_p); aux[64 + lane] = va;
                 const int64_t next = tile + 2 * (int64_t)gridDim.x;
-                if (next < n_tiles) icp_gather_row(a, next * TILE + lane, xa, va);
+                if (next < n_tiles) icp_gather_row(a, fr, next * TILE + lane, xa, va);
                 gather_store_row(xb, vb, 96 + lane, x_hi_p); aux[96 + lane] = vb;
                 fence_async_smem();
                 __syncwarp();
@@ -362,15 +368,17 @@ __global__ void __launch_bounds__(THREADS, 1) icp_tc_kernel(const unsigned char*
                     v[28] = 1.f;
                     if (a.want_grad) {
                         const int64_t i = tile * TILE + row;
-                        const float ox = __ldg(a.obs + 3 * i), oy = __ldg(a.obs + 3 * i + 1), oz = __ldg(a.obs + 3 * i + 2);
-                        const float qx = fmaf(oz, a.pose.Rd[2], fmaf(oy, a.pose.Rd[1], ox * a.pose.Rd[0])) + a.pose.td[0];
-                        const float qy = fmaf(oz, a.pose.Rd[5], fmaf(oy, a.pose.Rd[4], ox * a.pose.Rd[3])) + a.pose.td[1];
-                        const float qz = fmaf(oz, a.pose.Rd[8], fmaf(oy, a.pose.Rd[7], ox * a.pose.Rd[6])) + a.pose.td[2];
+                        const float* op = a.obs + (int64_t)a.obs_stride * i;
+                        const float ox = __ldg(op), oy = __ldg(op + 1), oz = __ldg(op + 2);
+                        const Pose& ps = fr.pose;
+                        const float qx = fmaf(oz, ps.Rd[2], fmaf(oy, ps.Rd[1], ox * ps.Rd[0])) + ps.td[0];
+                        const float qy = fmaf(oz, ps.Rd[5], fmaf(oy, ps.Rd[4], ox * ps.Rd[3])) + ps.td[1];
+                        const float qz = fmaf(oz, ps.Rd[8], fmaf(oy, ps.Rd[7], ox * ps.Rd[6])) + ps.td[2];
                         const float gx = gxs0 / a.m.g.vs, gy = gxs1 / a.m.g.vs, gz = gxs2 / a.m.g.vs;
                         float J[6];
-                        J[0] = gx * a.pose.Rl[0] + gy * a.pose.Rl[1] + gz * a.pose.Rl[2];
-                        J[1] = gx * a.pose.Rl[3] + gy * a.pose.Rl[4] + gz * a.pose.Rl[5];
-                        J[2] = gx * a.pose.Rl[6] + gy * a.pose.Rl[7] + gz * a.pose.Rl[8];
+                        J[0] = gx * ps.Rl[0] + gy * ps.Rl[1] + gz * ps.Rl[2];
+                        J[1] = gx * ps.Rl[3] + gy * ps.Rl[4] + gz * ps.Rl[5];
+                        J[2] = gx * ps.Rl[6] + gy * ps.Rl[7] + gz * ps.Rl[8];
                         J[3] = qy * J[2] - qz * J[1];
                         J[4] = qz * J[0] - qx * J[2];
                         J[5] = qx * J[1] - qy * J[0];
@@ -443,7 +451,8 @@ int launch_icp_tc(const void* decoder_prepared, const IcpTcArgs& a, cudaStream_t
     const unsigned char* image = (const unsigned char*)decoder_prepared + (size_t)DecW::FP32_END * sizeof(float);
     const int64_t n_tiles = ((int64_t)a.n + tc::TILE - 1) / tc::TILE;
     const int grid = (int)(n_tiles < DIF_NUM_SMS ? (n_tiles > 0 ? n_tiles : 1) : DIF_NUM_SMS);
-    cudaFuncSetAttribute(tc::icp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::ICP_SMEM_B);
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(tc::icp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::ICP_SMEM_B); attr_set = true; }
     prof_begin(DIF_PROF_ICP, st);
     launch_pdl(tc::icp_tc_kernel, grid, tc::THREADS, tc::ICP_SMEM_B, st, image, P, a);
     prof_end(DIF_PROF_ICP, st);

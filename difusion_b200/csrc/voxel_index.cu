@@ -13,7 +13,7 @@
 
 namespace dif {
 
-int launch_encode_accumulate_tc(const void* encoder_prepared, Grid g, const float* p_hat, const float* normal, const int32_t* s_pt,
+int launch_encode_accumulate_tc(const void* encoder_prepared, Grid g, const float* p_hat, const float* normal, int normal_stride, const int32_t* s_pt,
                                 const int32_t* s_slot, const uint8_t* s_off, const int32_t* n_dev, int64_t max_samples, float* slot_sum,
                                 cudaStream_t st);
 
@@ -66,14 +66,24 @@ static Scratch carve_scratch(void* p, int64_t n, int64_t n_chunks_max) {
 constexpr int64_t MAX_CHUNKS = (int64_t(1) << 31) / 32 / CHUNK_WORDS;
 
 // ------------------------------------------------------------------------------------------------ K1 voxelise + histogram
-__global__ void voxelize_kernel(MapDev m, const float* __restrict__ xyz, int n, float* __restrict__ p_hat,
-                                int32_t* __restrict__ cell, uint32_t* __restrict__ cell_count, int32_t* __restrict__ stats,
-                                int32_t* __restrict__ ctr) {
+// Frame mode (frame != NULL): `n` only bounds the grid, the actual count lives in the device block (dif_frame_params).
+__device__ __forceinline__ int frame_count(const dif_frame_params* frame, int n) {
+    if (!frame) return n;
+    const int f = frame->n_points;
+    return f < 0 ? 0 : (f < n ? f : n);
+}
+
+__global__ void voxelize_kernel(MapDev m, const float* __restrict__ xyz, int stride, int n, const dif_frame_params* __restrict__ frame,
+                                float* __restrict__ p_hat, int32_t* __restrict__ cell, uint32_t* __restrict__ cell_count,
+                                int32_t* __restrict__ stats, int32_t* __restrict__ ctr) {
     pdl_wait(); pdl_launch_dependents();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < CTR_COUNT) ctr[i] = 0;                  // per-call counters (first read by a later kernel of the same call)
+    if (i == 0 && frame) stats[DIF_STAT_SEQ] = frame->seq;
+    n = frame_count(frame, n);
     if (i >= n) return;
-    const float3 p = normalize_point(m.g, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    const float* xp = xyz + (int64_t)stride * i;
+    const float3 p = normalize_point(m.g, xp[0], xp[1], xp[2]);
     p_hat[3 * i] = p.x; p_hat[3 * i + 1] = p.y; p_hat[3 * i + 2] = p.z;
     // cell = ceil(p) - 1: a point exactly on a face belongs to the lower cell (map.py:368)
     const int ix = (int)ceilf(p.x) - 1, iy = (int)ceilf(p.y) - 1, iz = (int)ceilf(p.z) - 1;
@@ -88,11 +98,12 @@ __global__ void voxelize_kernel(MapDev m, const float* __restrict__ xyz, int n, 
 }
 
 // ------------------------------------------------------------------------------------------------ K2 prune + mark new cells
-__global__ void prune_mark_kernel(MapDev m, int n, const int32_t* __restrict__ cell, const uint32_t* __restrict__ cell_count,
-                                  uint8_t* __restrict__ kept, uint8_t* __restrict__ unq_mask, uint32_t* __restrict__ bitmap,
-                                  int32_t* __restrict__ stats) {
+__global__ void prune_mark_kernel(MapDev m, int n, const dif_frame_params* __restrict__ frame, const int32_t* __restrict__ cell,
+                                  const uint32_t* __restrict__ cell_count, uint8_t* __restrict__ kept, uint8_t* __restrict__ unq_mask,
+                                  uint32_t* __restrict__ bitmap, int32_t* __restrict__ stats) {
     pdl_wait(); pdl_launch_dependents();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    n = frame_count(frame, n);
     bool k = false;
     if (i < n) {
         const int c = cell[i];
@@ -304,12 +315,14 @@ __device__ __forceinline__ int target_slot(const MapDev& m, int lin) {
     return (s >= 0 && m.obs[s] < m.enc_th) ? (int)s : -1;
 }
 
-__global__ void gather_kernel(MapDev m, int n, const float* __restrict__ p_hat, const int32_t* __restrict__ cell,
-                              const uint8_t* __restrict__ kept, uint32_t* __restrict__ cell_count, uint32_t* __restrict__ slot_cnt,
-                              int32_t* __restrict__ s_pt, int32_t* __restrict__ s_slot, uint8_t* __restrict__ s_off,
-                              int32_t* __restrict__ touched, int32_t* __restrict__ ctr, int32_t* __restrict__ stats) {
+__global__ void gather_kernel(MapDev m, int n, const dif_frame_params* __restrict__ frame, const float* __restrict__ p_hat,
+                              const int32_t* __restrict__ cell, const uint8_t* __restrict__ kept, uint32_t* __restrict__ cell_count,
+                              uint32_t* __restrict__ slot_cnt, int32_t* __restrict__ s_pt, int32_t* __restrict__ s_slot,
+                              uint8_t* __restrict__ s_off, int32_t* __restrict__ touched, int32_t* __restrict__ ctr,
+                              int32_t* __restrict__ stats) {
     pdl_wait(); pdl_launch_dependents();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    n = frame_count(frame, n);
     const int lane = threadIdx.x & 31;
     int slots[8]; bool mine[8]; int cnt = 0; bool focused = false;
 #pragma unroll
@@ -390,7 +403,7 @@ __global__ void gather_kernel(MapDev m, int n, const float* __restrict__ p_hat, 
 
 // ------------------------------------------------------------------------------------------------ K5 encoder + per-PLIVox sum
 __global__ void __launch_bounds__(MLP_THREADS) encode_accumulate_kernel(
-        MapDev m, const float* __restrict__ encP, const float* __restrict__ p_hat, const float* __restrict__ normal,
+        MapDev m, const float* __restrict__ encP, const float* __restrict__ p_hat, const float* __restrict__ normal, int stride,
         const int32_t* __restrict__ s_pt, const int32_t* __restrict__ s_slot, const uint8_t* __restrict__ s_off,
         const int32_t* __restrict__ ctr, float* __restrict__ slot_sum) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -415,7 +428,8 @@ __global__ void __launch_bounds__(MLP_THREADS) encode_accumulate_kernel(
                 const float cz = (float)clampi((int)ceilf(__fadd_rn(pz, oz)) - 1, 0, g.nz - 1);
                 // rel = p - cell - 0.5, two separately rounded subtractions as in map.py:425
                 in[0] = __fsub_rn(__fsub_rn(px, cx), 0.5f); in[1] = __fsub_rn(__fsub_rn(py, cy), 0.5f); in[2] = __fsub_rn(__fsub_rn(pz, cz), 0.5f);
-                in[3] = normal[3 * i]; in[4] = normal[3 * i + 1]; in[5] = normal[3 * i + 2];
+                const float* np_ = normal + (int64_t)stride * i;
+                in[3] = np_[0]; in[4] = np_[1]; in[5] = np_[2];
             }
             tile_slot[t] = slot;
 #pragma unroll
@@ -540,19 +554,16 @@ __global__ void mesh_assign_kernel(MapDev m, uint32_t* __restrict__ bitmap, int6
 
 using namespace dif;
 
-extern "C" {
-
-size_t dif_integrate_persist_bytes(int64_t n_cells, int64_t capacity) { return persist_bytes(n_cells, capacity); }
-size_t dif_integrate_scratch_bytes(int64_t max_points) { return scratch_bytes(max_points > 0 ? max_points : 1, MAX_CHUNKS); }
-
-int dif_integrate(const dif_map_view* map, const void* encoder_prepared, const float* xyz, const float* normal, int64_t n,
-                  uint8_t* unq_mask, void* persist, size_t persist_sz, void* scratch, size_t scratch_sz, int32_t* stats_dev, void* stream) {
+namespace dif {
+// integrate chain with strided point rows and an optional device-side frame block (dif_integrate: stride 3; dif_frame: stride 9)
+int integrate_launch(const dif_map_view* map, const void* encoder_prepared, const float* xyz, const float* normal, int stride, int64_t n,
+                     const dif_frame_params* frame, uint8_t* unq_mask, void* persist, size_t persist_sz, void* scratch, size_t scratch_sz,
+                     int32_t* stats_dev, cudaStream_t st) {
     if (!map || !encoder_prepared || !persist || !scratch || !stats_dev || n < 0 || n >= (int64_t(1) << 27)) return DIF_E_INVALID;
     const MapDev m = to_dev(map);
     const int64_t n_cells = m.g.cells();
     if (n_cells <= 0 || n_cells >= (int64_t(1) << 31)) return DIF_E_INVALID;
     if (persist_sz < persist_bytes(n_cells, m.capacity) || scratch_sz < scratch_bytes(n > 0 ? n : 1, MAX_CHUNKS)) return DIF_E_WORKSPACE;
-    cudaStream_t st = (cudaStream_t)stream;
     const Persist P = carve_persist(persist, n_cells, m.capacity);
     const Scratch S = carve_scratch(scratch, n > 0 ? n : 1, MAX_CHUNKS);
     const int64_t n_words = (n_cells + 31) / 32;
@@ -562,8 +573,8 @@ int dif_integrate(const dif_map_view* map, const void* encoder_prepared, const f
     const int PT = 64;                                             // small blocks: a 30k-point frame must still fill 148 SMs
     const int nb = (int)((n + PT - 1) / PT);
     if (n > 0) {
-        launch_pdl(voxelize_kernel, nb, PT, 0, st, m, xyz, (int)n, S.p_hat, S.cell, P.cell_count, stats_dev, S.ctr);
-        launch_pdl(prune_mark_kernel, nb, PT, 0, st, m, (int)n, S.cell, P.cell_count, S.kept, unq_mask, P.bitmap, stats_dev);
+        launch_pdl(voxelize_kernel, nb, PT, 0, st, m, xyz, stride, (int)n, frame, S.p_hat, S.cell, P.cell_count, stats_dev, S.ctr);
+        launch_pdl(prune_mark_kernel, nb, PT, 0, st, m, (int)n, frame, S.cell, P.cell_count, S.kept, unq_mask, P.bitmap, stats_dev);
         DIF_COUNT_LAUNCH(2);
     }
     DIF_COUNT_LAUNCH(1);
@@ -573,21 +584,22 @@ int dif_integrate(const dif_map_view* map, const void* encoder_prepared, const f
         launch_pdl(alloc_kernel, (n_chunks + per - 1) / per, SCAN_THREADS, 0, st, m, P.bitmap, n_words, n_chunks, per, P.alloc_sync, S.ctr, stats_dev);
     }
     if (n > 0) {
-        launch_pdl(gather_kernel, nb, PT, 0, st, m, (int)n, S.p_hat, S.cell, S.kept, P.cell_count, P.slot_cnt, S.s_pt, S.s_slot, S.s_off,
+        launch_pdl(gather_kernel, nb, PT, 0, st, m, (int)n, frame, S.p_hat, S.cell, S.kept, P.cell_count, P.slot_cnt, S.s_pt, S.s_slot, S.s_off,
                    S.touched, S.ctr, stats_dev);
         const char* enc_env = getenv("DIF_ENCODE_PATH");                 // "simt" forces the exact-fp32 kernel (tests compare both)
         if (!(enc_env && enc_env[0] == 's') && n >= 256) {
-            const int rc = launch_encode_accumulate_tc(encoder_prepared, m.g, S.p_hat, normal, S.s_pt, S.s_slot, S.s_off, S.ctr + CTR_N_SAMPLES,
+            const int rc = launch_encode_accumulate_tc(encoder_prepared, m.g, S.p_hat, normal, stride, S.s_pt, S.s_slot, S.s_off, S.ctr + CTR_N_SAMPLES,
                                                        8 * n, P.slot_sum, st);
             if (rc) return rc;
             DIF_COUNT_LAUNCH(2);
         } else {
             const size_t smem = sizeof(EncoderSmem);
-            cudaFuncSetAttribute(encode_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            static bool attr_set = false;
+            if (!attr_set) { cudaFuncSetAttribute(encode_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
             const int64_t max_tiles = (8 * n + MLP_T - 1) / MLP_T;
             const int grid = (int)(max_tiles < DIF_NUM_SMS * 4 ? max_tiles : DIF_NUM_SMS * 4);
             prof_begin(DIF_PROF_ENCODE, st);
-            encode_accumulate_kernel<<<grid, MLP_THREADS, smem, st>>>(m, (const float*)encoder_prepared, S.p_hat, normal, S.s_pt, S.s_slot,
+            encode_accumulate_kernel<<<grid, MLP_THREADS, smem, st>>>(m, (const float*)encoder_prepared, S.p_hat, normal, stride, S.s_pt, S.s_slot,
                                                                       S.s_off, S.ctr, P.slot_sum);
             prof_end(DIF_PROF_ENCODE, st);
             DIF_COUNT_LAUNCH(3);
@@ -595,6 +607,19 @@ int dif_integrate(const dif_map_view* map, const void* encoder_prepared, const f
         launch_pdl(fuse_kernel, DIF_NUM_SMS * 8, 256, 0, st, m, S.touched, S.ctr, P.slot_cnt, P.slot_sum, stats_dev);
     }
     return check_launch("dif_integrate");
+}
+}  // namespace dif
+
+extern "C" {
+
+size_t dif_integrate_persist_bytes(int64_t n_cells, int64_t capacity) { return persist_bytes(n_cells, capacity); }
+size_t dif_integrate_scratch_bytes(int64_t max_points) { return scratch_bytes(max_points > 0 ? max_points : 1, MAX_CHUNKS); }
+
+int dif_integrate(const dif_map_view* map, const void* encoder_prepared, const float* xyz, const float* normal, int64_t n,
+                  const dif_frame_params* frame_dev, uint8_t* unq_mask, void* persist, size_t persist_sz, void* scratch, size_t scratch_sz,
+                  int32_t* stats_dev, void* stream) {
+    return integrate_launch(map, encoder_prepared, xyz, normal, 3, n, frame_dev, unq_mask, persist, persist_sz, scratch, scratch_sz, stats_dev,
+                            (cudaStream_t)stream);
 }
 
 int dif_map_query(const dif_map_view* map, const float* xyz, int64_t n, int32_t* slot_out, float* rel_out, int32_t* n_valid_dev, void* stream) {

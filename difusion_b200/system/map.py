@@ -9,8 +9,8 @@ Deliberate differences (documented in DESIGN.md):
     ``latent_vecs_pos`` / ``voxel_obs_count`` / ``voxel_optimized`` views keep the reference's capacity rule
     (smallest power of two >= n_occupied, map.py:263-281) so shapes match the reference exactly;
   * ``n_occupied`` lives on the device; the host value is fetched lazily (the reference syncs ~25 times per integrate);
-  * points outside the grid are dropped and reported (IndexError at the next host sync) instead of indexing out of
-    range (map.py:313 "will not check index overflow");
+  * points outside the grid are dropped, counted (``n_frames_with_dropped_points``, ``last_integrate_stats["flags"] & 1``) and
+    logged instead of indexing out of range (map.py:313 "will not check index overflow");
   * the disabled latent-optimisation branch (do_optimize, map.py:456-516, never enabled by main.py:85-86) is not built.
 """
 from __future__ import annotations
@@ -155,6 +155,9 @@ class DenseIndexedMap:
         self._stats_next = 0
         self._stats_last = [0] * _lib.DIF_STAT_COUNT
         self._n_occ_host = 0
+        self._pending_error = None
+        self._reset_epoch = 0
+        self.n_frames_with_dropped_points = 0
         self._shard_rank, self._shard_world, self._xchg = 0, 1, None       # see difusion_b200/shard.py
         self._cap_phys = 0
         self._latent = self._pos = self._obs = self._optimized = self._dirty = None
@@ -162,6 +165,7 @@ class DenseIndexedMap:
         self._scratch = None
         self._scratch_points = 0
         self._mesh_persist = None
+        self._mesh_persist_cap = 0
         self._cache_persist = None
         self._icp_scratch = None
         self._view_key, self._view_obj = None, None
@@ -192,8 +196,10 @@ class DenseIndexedMap:
             self._persist = torch.zeros(self._L.dif_integrate_persist_bytes(self._n_cells, new_cap), dtype=torch.uint8, device=dev)
 
     def _retire_stats(self, block: bool):
-        """Consume finished integrate results (all of them when block=True)."""
-        err = None
+        """Consume finished integrate results (all of them when block=True).  Nothing is ever raised from the non-blocking path:
+        which later call would see a finished event depends on timing, and a rank of a sharded map that raised alone would
+        leave the others inside a collective.  Out-of-grid points are dropped, counted and logged (the reference indexes out of
+        range there, map.py:313); an exhausted capacity (internal sizing error) is raised at the next BLOCKING point."""
         while self._stats_inflight:
             buf, ev = self._stats_ring[self._stats_inflight[0][0]]
             if block:
@@ -201,18 +207,43 @@ class DenseIndexedMap:
             elif not ev.query():
                 break
             self._stats_inflight.pop(0)
-            st = buf.tolist()
-            self._stats_last = st
-            self._n_occ_host = st[_lib.STAT_N_OCCUPIED]
-            self.last_integrate_stats = dict(n_kept=st[0], n_new=st[1], n_samples=st[2], n_updated=st[3], n_occupied=st[4],
-                                             flags=st[5], n_focused=st[6])
-            if st[_lib.STAT_FLAGS] & 2:
-                err = RuntimeError("PLIVox capacity exhausted inside dif_integrate (internal sizing error)")
-            elif st[_lib.STAT_FLAGS] & 1:
-                err = IndexError("integrate_keyframe: surface points outside the map bounds were dropped "
-                                 "(the reference indexes out of range here, map.py:313)")
-        if err is not None:
+            self._consume_stats(buf.tolist())
+        if block and self._pending_error is not None:
+            err, self._pending_error = self._pending_error, None
             raise err
+
+    def _consume_stats(self, st):
+        self._stats_last = st
+        self._n_occ_host = st[_lib.STAT_N_OCCUPIED]
+        self.last_integrate_stats = dict(n_kept=st[0], n_new=st[1], n_samples=st[2], n_updated=st[3], n_occupied=st[4],
+                                         flags=st[5], n_focused=st[6])
+        if st[_lib.STAT_FLAGS] & 2:
+            self._pending_error = RuntimeError("PLIVox capacity exhausted inside dif_integrate (internal sizing error)")
+        if st[_lib.STAT_FLAGS] & 1:
+            self.n_frames_with_dropped_points += 1
+            if self.n_frames_with_dropped_points in (1, 10, 100) or self.n_frames_with_dropped_points % 1000 == 0:
+                logging.warning("integrate_keyframe: surface points outside the map bounds were dropped (%d frames so far; the "
+                                "reference indexes out of range here, map.py:313)", self.n_frames_with_dropped_points)
+
+    def reset(self):
+        """Back to the empty map IN PLACE: every buffer keeps its address, so captured launch sequences (FramePipeline) stay
+        valid.  The per-frame scratch is self-cleaning and therefore already zero."""
+        torch.cuda.synchronize(self.device)
+        self._stats_inflight.clear()
+        self._indexer.fill_(-1)
+        self._latent.zero_(); self._pos.fill_(-1); self._obs.zero_(); self._optimized.zero_(); self._dirty.zero_()
+        self._n_occ_dev.zero_()
+        self._n_occ_host = 0
+        self._pending_error = None
+        self._reset_epoch += 1
+        self.last_integrate_stats = None
+        self.mesh_cache.clear_all()
+        torch.cuda.synchronize(self.device)
+
+    def frame_pipeline(self, max_points: int, **kw):
+        """One-launch-per-frame path (tracker linearisation + integrate as a replayable CUDA graph), see system/frame.py."""
+        from .frame import FramePipeline
+        return FramePipeline(self, max_points, **kw)
 
     def _sync_stats(self):
         self._retire_stats(block=True)
@@ -328,7 +359,7 @@ class DenseIndexedMap:
             unq = torch.empty(n, dtype=torch.uint8, device=self.device) if prune else None
             view = self._view()
             st = _lib.stream_ptr(self.device)
-            _lib.check(self._L.dif_integrate(ctypes.byref(view), self._prep.encoder.data_ptr(), xyz.data_ptr(), nrm.data_ptr(), n,
+            _lib.check(self._L.dif_integrate(ctypes.byref(view), self._prep.encoder.data_ptr(), xyz.data_ptr(), nrm.data_ptr(), n, None,
                                              _lib.ptr(unq), self._persist.data_ptr(), self._persist.numel(), self._scratch.data_ptr(),
                                              self._scratch.numel(), self._stats_dev.data_ptr(), st), "dif_integrate")
             buf, ev = self._stats_ring[self._stats_next]
@@ -369,7 +400,7 @@ class DenseIndexedMap:
         pose = np.empty(24, np.float32)
         pose[0:9], pose[9:12], pose[12:21], pose[21:24] = np.ravel(R_last), np.ravel(t_last), np.ravel(R_delta), np.ravel(t_delta)
         view = self._view()
-        _lib.check(self._L.dif_icp_linearize(ctypes.byref(view), self._prep.decoder.data_ptr(), x.data_ptr(), n, pose.ctypes.data,
+        _lib.check(self._L.dif_icp_linearize(ctypes.byref(view), self._prep.decoder.data_ptr(), x.data_ptr(), n, pose.ctypes.data, None,
                                              float(huber_k) if huber_k else 0.0, int(want_grad), self._icp_scratch.data_ptr(),
                                              self._icp_scratch.numel(), out.data_ptr(), _lib.stream_ptr(self.device)), "dif_icp_linearize")
         return out
@@ -401,19 +432,31 @@ class DenseIndexedMap:
         total = int(totals[1].item())                        # host sync: the merged cache is sliced to its size
         c._set(o_tri[:total], o_id[:total], o_std[:total])
 
-    def mesh_cubes(self, voxel_resolution: int, fast: bool = True, updated_vec_id: torch.Tensor = None):
+    def _snapshot(self):
+        """What the reference's backup_vars are for (map.py:620-622): the tensors a mesh extraction reads, pinned by reference so
+        that a concurrent capacity growth (which rebinds the attributes) cannot hand their memory back to the allocator, plus a
+        COPY of the device view built from exactly these tensors."""
+        v = _lib.MapView()
+        ctypes.memmove(ctypes.byref(v), ctypes.byref(self._view()), ctypes.sizeof(v))
+        return dict(view=v, cap=self._cap_phys, tensors=(self._indexer, self._latent, self._pos, self._obs, self._dirty, self._n_occ_dev),
+                    indexer=self._indexer, pos=self._pos)
+
+    def mesh_cubes(self, voxel_resolution: int, fast: bool = True, updated_vec_id: torch.Tensor = None, snap: dict = None):
         """Stages map.py:627-687 on the device: returns (focused_flatten_id (K,), vec_id_batch_mapping (cap,), high_sdf, high_std
-        (B,2r,2r,2r) [sdf already negated], block_slots (B,), counts dict).  updated_vec_id None == all occupied PLIVoxes."""
+        (B,2r,2r,2r) [sdf already negated], block_slots (B,), counts dict).  updated_vec_id None == all occupied PLIVoxes.
+        snap: a _snapshot() taken under modifying_lock (asynchronous extraction); default = the live map."""
         dev, L = self.device, self._L
         st = _lib.stream_ptr(dev)
-        view = self._view()
-        if self._mesh_persist is None:
-            self._mesh_persist = torch.zeros(L.dif_mesh_select_scratch_bytes(self._n_cells, self._cap_phys), dtype=torch.uint8, device=dev)
-        k_max = self._cap_phys if updated_vec_id is None else int(updated_vec_id.numel())
+        snap = snap or self._snapshot()
+        view, cap = snap["view"], snap["cap"]
+        if self._mesh_persist is None or self._mesh_persist_cap != cap:
+            self._mesh_persist = torch.zeros(L.dif_mesh_select_scratch_bytes(self._n_cells, cap), dtype=torch.uint8, device=dev)
+            self._mesh_persist_cap = cap
+        k_max = cap if updated_vec_id is None else int(updated_vec_id.numel())
         upd = None if updated_vec_id is None else updated_vec_id.to(torch.int32).contiguous()
         focused = torch.empty(max(k_max, 1), dtype=torch.long, device=dev)
-        block_slots = torch.empty(min(self._cap_phys, 7 * max(k_max, 1)), dtype=torch.int32, device=dev)
-        mapping = torch.empty(self._cap_phys, dtype=torch.int32, device=dev)
+        block_slots = torch.empty(min(cap, 7 * max(k_max, 1)), dtype=torch.int32, device=dev)
+        mapping = torch.empty(cap, dtype=torch.int32, device=dev)
         counts = torch.zeros(2, dtype=torch.int32, device=dev)
         _lib.check(L.dif_mesh_select(ctypes.byref(view), _lib.ptr(upd), 0 if upd is None else upd.numel(), focused.data_ptr(),
                                      block_slots.data_ptr(), mapping.data_ptr(), counts.data_ptr(), self._mesh_persist.data_ptr(),
@@ -463,17 +506,22 @@ class DenseIndexedMap:
                 updated = self.decode_set(owned)            # owned + their 26 neighbours: same decode batch as a full extraction sees
             else:
                 owned = None
+            # the mesher reads THIS state even if integrate_keyframe grows (rebinds) the map meanwhile (map.py:620-622 backup_vars)
+            snap = self._snapshot()
+            if extract_async:
+                for t in snap["tensors"]:
+                    t.record_stream(self.meshing_stream)
 
         def do_meshing(res):
             torch.cuda.synchronize(self.device)
             with torch.cuda.stream(self.meshing_stream):
-                focused, mapping, cube_sdf, cube_std, _, _ = self.mesh_cubes(res, fast, updated)
+                focused, mapping, cube_sdf, cube_std, _, _ = self.mesh_cubes(res, fast, updated, snap)
                 if owned is not None:                       # sharded map: triangles only for the PLIVoxes this rank owns
-                    focused = self._pos[owned].contiguous()
+                    focused = snap["pos"][owned].contiguous()
                 if cube_sdf.size(0) == 0 or focused.numel() == 0:
                     return
                 vertices, vertices_flatten_id, vertices_std = _ext.marching_cubes_interp(
-                    self.indexer.view(self.n_xyz), focused, mapping, cube_sdf, cube_std, max_n_triangles, self.n_xyz, max_std)
+                    snap["indexer"].view(self.n_xyz), focused, mapping, cube_sdf, cube_std, max_n_triangles, self.n_xyz, max_std)
                 self._merge_into_cache(vertices.contiguous(), vertices_flatten_id.contiguous(), vertices_std.contiguous())
 
         if extract_async:

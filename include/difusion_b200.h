@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DIF_ABI_VERSION 1
+#define DIF_ABI_VERSION 2
 #define DIF_LATENT_DIM 29                 /* ckpt/default/hyper.json:34 "code_length" */
 
 enum {
@@ -96,12 +96,28 @@ enum {
     DIF_STAT_FLAGS = 5,          /* bit0: a point fell outside the grid (dropped); bit1: capacity exhausted */
     DIF_STAT_N_FOCUSED = 6,      /* points passing the focus mask (map.py:389-397)                */
     DIF_STAT_N_XCHG = 7,         /* sharded map: owned PLIVoxes fused by this call (length of xchg_slots) */
-    DIF_STAT_COUNT = 8
+    DIF_STAT_SEQ = 8,            /* frame->seq echoed back (0 without a frame block): tells a lagging reader which frame the counters belong to */
+    DIF_STAT_COUNT = 12
 };
+
+/* ---- per-frame parameter block in DEVICE memory (new: SURVEY 7 step 7, "CUDA-graph the per-frame pipeline") -----------
+ * The reference passes the point count and the poses as host values (tensor shapes, Isometry objects), which bakes them into
+ * every launch.  With this block the SAME launch sequence serves every frame, so it can be captured once into a CUDA graph and
+ * replayed: the caller writes the block (it may sit in front of the frame's points so that ONE H2D copy moves both) and the
+ * kernels read the actual point count and the poses from it.  `n` / `max_points` arguments then only bound the launch grids. */
+typedef struct dif_frame_params {
+    int32_t n_points;            /* valid rows this frame (clamped to the n / max_points argument of the call) */
+    int32_t seq;                 /* caller's frame number, echoed to stats[DIF_STAT_SEQ] */
+    int32_t reserved[2];
+    float   pose[24];            /* R_last[9], t_last[3], R_delta[9], t_delta[3], row-major (the pose_host layout of dif_icp_linearize) */
+} dif_frame_params;              /* 112 bytes; callers that pack it in front of the points pad it to DIF_FRAME_HEADER_FLOATS floats */
+#define DIF_FRAME_HEADER_FLOATS 32
+#define DIF_FRAME_POINT_FLOATS 9          /* dif_frame point row: camera xyz, world xyz, world normal */
 size_t dif_integrate_persist_bytes(int64_t n_cells, int64_t capacity);
 size_t dif_integrate_scratch_bytes(int64_t max_points);
 int dif_integrate(const dif_map_view* map, const void* encoder_prepared,
                   const float* xyz /*[n][3] world*/, const float* normal /*[n][3] world*/, int64_t n,
+                  const dif_frame_params* frame_dev /* NULL: n is exact; else n bounds frame_dev->n_points (device) */,
                   uint8_t* unq_mask /*[n] or NULL*/, void* persist, size_t persist_bytes,
                   void* scratch, size_t scratch_bytes, int32_t* stats_dev, void* stream);
 
@@ -125,11 +141,27 @@ int dif_map_query(const dif_map_view* map, const float* xyz, int64_t n, int32_t*
  * Huber(k) (huber_k <= 0: no robust kernel), normal equations.  pose = {R_last[9], t_last[3], R_delta[9], t_delta[3]}
  * row-major fp32 (host memory, copied at call time).  out_dev[44] (fp64): H[36] row-major, g[6], energy, M (valid count);
  * already divided by M as the reference does.  want_grad = 0 reproduces no_grad=True (only energy and M are written).
- * `scratch` must be zero-filled ONCE by the caller; every call leaves it zero-filled again. */
+ * `scratch` must be zero-filled ONCE by the caller; every call leaves it zero-filled again.
+ * frame_dev != NULL: the point count (bounded by n) and the poses are read from the device block instead of n / pose_host
+ * (pose_host may then be NULL); the composite pose last*delta is formed on the device with the same fp64 arithmetic. */
 size_t dif_icp_scratch_bytes(int64_t n);
 int dif_icp_linearize(const dif_map_view* map, const void* decoder_prepared, const float* obs_xyz /*[n][3] camera frame*/,
-                      int64_t n, const float* pose_host /*[24]*/, float huber_k, int want_grad,
+                      int64_t n, const float* pose_host /*[24]*/, const dif_frame_params* frame_dev, float huber_k, int want_grad,
                       void* scratch, size_t scratch_bytes, double* out_dev /*[44]*/, void* stream);
+
+/* ---- one frame, one call  (main.py:71-94: tracker linearisation against the map so far, then integrate_keyframe) -----------
+ * points: [max_points][DIF_FRAME_POINT_FLOATS] rows = camera-frame xyz (tracker.last_processed_pc), world xyz and world normal
+ * (what main.py:88 passes to integrate_keyframe); frame_dev->n_points of them are valid.  Equivalent to dif_icp_linearize (if
+ * flags & DIF_FRAME_TRACK) followed by dif_integrate (if flags & DIF_FRAME_INTEGRATE) on the same stream, with every per-frame
+ * value read from device memory - the whole call is CUDA-graph capturable and replayable for any frame that fits max_points.
+ * result_dev: [44] doubles (H, g, energy, M as dif_icp_linearize) followed by DIF_STAT_COUNT int32 counters (as dif_integrate),
+ * DIF_FRAME_RESULT_BYTES in all, so that one D2H copy returns everything the host loop reads. */
+enum { DIF_FRAME_TRACK = 1, DIF_FRAME_INTEGRATE = 2 };
+#define DIF_FRAME_RESULT_BYTES (44 * 8 + DIF_STAT_COUNT * 4)
+int dif_frame(const dif_map_view* map, const void* encoder_prepared, const void* decoder_prepared,
+              const float* points, int64_t max_points, const dif_frame_params* frame_dev, float huber_k, int flags,
+              uint8_t* unq_mask /*[max_points] or NULL*/, void* persist, size_t persist_bytes, void* scratch, size_t scratch_bytes,
+              void* icp_scratch, size_t icp_scratch_bytes, void* result_dev, void* stream);
 
 /* ---- mesh extraction  (system/map.py:624-691; SURVEY a-10, a-11) ---------------------------------------
  * dif_mesh_select: which PLIVoxes to decode.  updated_slots == NULL means "all occupied" (no_cache=True, map.py:615).

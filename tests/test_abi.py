@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, n), f"{n} declared in the header but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
     assert set(_lib.SIGNATURES) == set(names)
-    assert L.dif_abi_version() == 1
+    assert L.dif_abi_version() == _lib.ABI_VERSION
 
 
 def test_workspace_queries_need_no_gpu():

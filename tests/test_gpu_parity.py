@@ -31,7 +31,7 @@ def _t(a, dev):
 
 def test_native_library_is_loaded():
     from difusion_b200 import _lib
-    assert _lib.lib().dif_abi_version() == 1
+    assert _lib.lib().dif_abi_version() == _lib.ABI_VERSION
     assert "libdifusion_b200.so" in open("/proc/self/maps").read()
 
 
@@ -239,8 +239,7 @@ def test_edge_cases(model, dev):
     # (4) out-of-bounds points are dropped and reported
     far = _t(np.array([[100.0, 0, 0]], np.float32), dev)
     m2.integrate_keyframe(far, far)
-    with pytest.raises(IndexError):
-        _ = m2.n_occupied
+    assert m2.n_occupied == 0 and m2.last_integrate_stats["flags"] & 1 and m2.n_frames_with_dropped_points == 1
     # (5) get_sdf on an empty map asserts like the reference (utility.py:84-85)
     with pytest.raises(AssertionError):
         m2.get_sdf(_t(pts, dev))

@@ -59,7 +59,7 @@ for rep in range(3):
             m._scratch = torch.empty(m._L.dif_integrate_scratch_bytes(m._scratch_points), dtype=torch.uint8, device=dev)
         view = m._view(); st = _lib.stream_ptr(dev)
         t3 = time.perf_counter()
-        _lib.check(m._L.dif_integrate(ctypes.byref(view), m._prep.encoder.data_ptr(), xyz.data_ptr(), nrm.data_ptr(), n, _lib.ptr(unq), m._persist.data_ptr(),
+        _lib.check(m._L.dif_integrate(ctypes.byref(view), m._prep.encoder.data_ptr(), xyz.data_ptr(), nrm.data_ptr(), n, None, _lib.ptr(unq), m._persist.data_ptr(),
                                       m._persist.numel(), m._scratch.data_ptr(), m._scratch.numel(), m._stats_dev.data_ptr(), st), "dif_integrate")
         t4 = time.perf_counter()
         buf, ev = m._stats_ring[m._stats_next]
