@@ -243,7 +243,7 @@ def extra_decoder_sweep(torch, dev, L, _lib, net_util, model, table, n_rows, flu
         sdf = torch.empty(n, device=dev); std = torch.empty(n, device=dev)
 
         def run():
-            _lib.check(L.dif_decode(prep.decoder.data_ptr(), table.data_ptr(), rows.data_ptr(), xyz.data_ptr(), n, None, 1.0,
+            _lib.check(L.dif_decode(prep.decoder.data_ptr(), table.data_ptr(), table.stride(0), rows.data_ptr(), xyz.data_ptr(), n, None, 1.0,
                                     sdf.data_ptr(), std.data_ptr(), None, None, _lib.stream_ptr(dev)), "dif_decode")
         for _ in range(3):
             run()

@@ -16,6 +16,7 @@ DIF_STAT_COUNT = 12
 STAT_N_KEPT, STAT_N_NEW, STAT_N_SAMPLES, STAT_N_UPDATED, STAT_N_OCCUPIED, STAT_FLAGS, STAT_N_FOCUSED, STAT_N_XCHG, STAT_SEQ = range(9)
 FRAME_HEADER_FLOATS, FRAME_POINT_FLOATS = 32, 9           # DIF_FRAME_HEADER_FLOATS / DIF_FRAME_POINT_FLOATS
 FRAME_TRACK, FRAME_INTEGRATE = 1, 2
+LATENT_ROW_FLOATS = 32       # the map stores 128-byte latent rows (dif_map_view.latent_stride); columns 29..31 are padding
 FRAME_RESULT_BYTES = 44 * 8 + DIF_STAT_COUNT * 4
 
 
@@ -26,7 +27,7 @@ class MapView(C.Structure):
                 ("capacity", C.c_int64), ("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32),
                 ("bound_min", C.c_float * 3), ("voxel_size", C.c_float), ("prune_min_vox_obs", C.c_int32),
                 ("ignore_count_th", C.c_float), ("encoder_count_th", C.c_float),
-                ("shard_rank", C.c_int32), ("shard_world", C.c_int32), ("xchg_slots", C.c_void_p)]
+                ("shard_rank", C.c_int32), ("shard_world", C.c_int32), ("xchg_slots", C.c_void_p), ("latent_stride", C.c_int32)]
 
 
 class FrameParams(C.Structure):
@@ -56,7 +57,7 @@ SIGNATURES = {
     "dif_integrate_persist_bytes": (_SZ, [_I64, _I64]),
     "dif_integrate_scratch_bytes": (_SZ, [_I64]),
     "dif_integrate": (C.c_int, [_MV, _P, _P, _P, _I64, _P, _P, _P, _SZ, _P, _SZ, _P, _P]),
-    "dif_decode": (C.c_int, [_P, _P, _P, _P, _I64, _P, _F, _P, _P, _P, _P, _P]),
+    "dif_decode": (C.c_int, [_P, _P, C.c_int, _P, _P, _I64, _P, _F, _P, _P, _P, _P, _P]),
     "dif_encode": (C.c_int, [_P, _P, _I64, _P, _P]),
     "dif_map_query": (C.c_int, [_MV, _P, _I64, _P, _P, _P, _P]),
     "dif_icp_scratch_bytes": (_SZ, [_I64]),

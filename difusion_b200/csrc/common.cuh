@@ -98,6 +98,20 @@ __host__ __device__ __forceinline__ int shard_owner(int64_t lin, int world) {
     return (int)(z % (uint64_t)world);
 }
 
+// One latent row (29 floats) into x[0..28] (x[29..31] are left for the caller).  Rows padded to 32 floats are 16-byte aligned:
+// 8 vector loads; a lane gathering its own row touches one 128-byte line instead of issuing 29 scalar requests.
+__device__ __forceinline__ void load_latent_row(const float* __restrict__ table, int64_t row, int stride, float (&x)[32]) {
+    const float* lp = table + row * stride;
+    if (stride == 32) {
+        const float4* q = reinterpret_cast<const float4*>(lp);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float4 v = __ldg(q + j); x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w; }
+    } else {
+#pragma unroll
+        for (int j = 0; j < DIF_L; ++j) x[j] = __ldg(lp + j);
+    }
+}
+
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 __device__ __forceinline__ float warp_sum(float v) {

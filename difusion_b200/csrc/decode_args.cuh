@@ -8,7 +8,7 @@ namespace dif {
 // s -> PLIVox s / n3, lattice point s % n3 (map.py:644-653: the reference materialises B*l^3 x 32 inputs).  mode 2: the same
 // lattice addressed through a compacted list of global lattice indices whose length lives on the device (map.py:667-679).
 struct DecodeArgs {
-    const float* P; const float* latent; const int32_t* rows; const float* xyz; int64_t n;
+    const float* P; const float* latent; int lat_stride; const int32_t* rows; const float* xyz; int64_t n;
     const int32_t* out_index; float sdf_sign; float* sdf; float* std; float* grad; int grad_head;
     int mode; int lat_n; float lat_step, lat_a; const uint32_t* list; const int32_t* n_dev;
 };

@@ -25,6 +25,7 @@
 // coalesced loads (one sample's 29 latent floats + xyz per load instruction, lane = input column), three 16-row
 // batches in flight, and runs one tile ahead of the tensor pipe.
 #include <atomic>
+#include <stdlib.h>
 
 #include "tc_common.cuh"
 
@@ -40,9 +41,7 @@ __device__ __forceinline__ void gather_load_row(const DecodeArgs& a, int64_t sid
     int64_t row, out; int li;
     decode_sample_source(a, sidx, n_total, n3, row, out, li);
     valid = row >= 0;
-    const float* lp = a.latent + (valid ? row : 0) * DIF_L;
-#pragma unroll
-    for (int j = 0; j < DIF_L; ++j) x[j] = __ldg(lp + j);
+    load_latent_row(a.latent, valid ? row : 0, a.lat_stride, x);
     if (a.mode == 0) {
         const float* xp = a.xyz + (valid ? sidx : 0) * 3;
         x[29] = __ldg(xp); x[30] = __ldg(xp + 1); x[31] = __ldg(xp + 2);
@@ -335,6 +334,7 @@ __global__ void prepare_tc_kernel(const float* __restrict__ P, unsigned char* __
 }  // namespace tc
 }  // namespace dif
 
+#include "decode_tc2.cuh"
 #include "icp_args.cuh"
 #include "icp_tc.cuh"
 
@@ -365,9 +365,15 @@ int launch_decode_tc(const void* prepared, DecodeArgs a, int64_t n_max, cudaStre
     const int64_t n_tiles = (n_max + tc::TILE - 1) / tc::TILE;
     const int grid = (int)(n_tiles < DIF_NUM_SMS ? n_tiles : DIF_NUM_SMS);
     static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(tc::decode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_B); attr_set = true; }
+    if (!attr_set) {
+        cudaFuncSetAttribute(tc::decode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_B);
+        cudaFuncSetAttribute(tc::decode_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::D2_SMEM_B);
+        attr_set = true;
+    }
+    const char* v = getenv("DIF_DECODE_V");                  // "1": the first pipeline (separate accumulator / operand regions), kept for A/B timing
     prof_begin(DIF_PROF_DECODE, st);
-    tc::decode_tc_kernel<<<grid, tc::THREADS, tc::SMEM_B, st>>>(image, P, a);
+    if (v && v[0] == '1') tc::decode_tc_kernel<<<grid, tc::THREADS, tc::SMEM_B, st>>>(image, P, a);
+    else tc::decode_tc2_kernel<<<grid, tc::THREADS, tc::D2_SMEM_B, st>>>(image, P, a);
     prof_end(DIF_PROF_DECODE, st);
     DIF_COUNT_LAUNCH(1);
     return check_launch("decode_tc_kernel");

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(MLP_THREADS) icp_linearize_kernel(
         __syncthreads();
         for (int idx = threadIdx.x; idx < MLP_T * 32; idx += MLP_THREADS) {
             const int t = idx / 32, j = idx % 32;
-            if (j < DIF_L) { const int sl = slot_s[t]; s.cat[(96 + j) * MLP_TP + t] = sl >= 0 ? __ldg(m.latent + (int64_t)sl * DIF_L + j) : 0.f; }
+            if (j < DIF_L) { const int sl = slot_s[t]; s.cat[(96 + j) * MLP_TP + t] = sl >= 0 ? __ldg(m.latent + (int64_t)sl * m.lat_stride + j) : 0.f; }
         }
         __syncthreads();
         decoder_forward_tile(P, s);
@@ -150,7 +150,7 @@ int icp_launch(const dif_map_view* map, const void* decoder_prepared, const floa
     if (!map || !decoder_prepared || (!pose_host && !frame_dev) || !scratch || !out_dev || n < 0 || n >= (int64_t(1) << 31) || (n > 0 && !obs_xyz))
         return DIF_E_INVALID;
     if (scratch_sz < dif_icp_scratch_bytes(n)) return DIF_E_WORKSPACE;
-    MapRO m{map->indexer, map->latent_vecs, map->voxel_obs_count, make_grid(map), map->ignore_count_th};
+    MapRO m{map->indexer, map->latent_vecs, map->voxel_obs_count, make_grid(map), map->ignore_count_th, map->latent_stride > 0 ? map->latent_stride : DIF_L};
     Pose p = {};
     if (pose_host) compose_pose(pose_host, p);
     Carver c(scratch);

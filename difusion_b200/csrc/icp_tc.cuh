@@ -84,9 +84,7 @@ __device__ __forceinline__ void icp_gather_row(const IcpTcArgs& a, const IcpFram
         }
         rx = __fsub_rn(__fsub_rn(p.x, (float)ix), 0.5f); ry = __fsub_rn(__fsub_rn(p.y, (float)iy), 0.5f); rz = __fsub_rn(__fsub_rn(p.z, (float)iz), 0.5f);
     }
-    const float* lp = a.m.latent + slot * DIF_L;
-#pragma unroll
-    for (int j = 0; j < DIF_L; ++j) x[j] = __ldg(lp + j);
+    load_latent_row(a.m.latent, slot, a.m.lat_stride, x);
     x[29] = rx; x[30] = ry; x[31] = rz;
 }
 

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(MLP_THREADS) decode_simt_kernel(DecodeArgs a) 
             const int64_t row = row_s[t];
             float v = 0.f;
             if (row >= 0) {
-                if (j < DIF_L) v = __ldg(a.latent + row * DIF_L + j);
+                if (j < DIF_L) v = __ldg(a.latent + row * a.lat_stride + j);
                 else if (a.mode == 0) v = __ldg(a.xyz + (base + t) * 3 + (j - DIF_L));
                 else {
                     const int li = lat_i[t], c = j - DIF_L, nn = a.lat_n;
@@ -177,17 +177,17 @@ int launch_decode(DecodeArgs a, int64_t n_max, cudaStream_t st) {
     return check_launch("decode_simt_kernel");
 }
 
-int launch_decode_explicit(const float* P, const float* latent, const int32_t* rows, const float* xyz, int64_t n,
+int launch_decode_explicit(const float* P, const float* latent, int lat_stride, const int32_t* rows, const float* xyz, int64_t n,
                            const int32_t* out_index, float sdf_sign, float* sdf, float* std, float* grad, int grad_head, cudaStream_t st) {
-    DecodeArgs a{P, latent, rows, xyz, n, out_index, sdf_sign, sdf, std, grad, grad_head, 0, 1, 0.f, 0.f, nullptr, nullptr};
+    DecodeArgs a{P, latent, lat_stride, rows, xyz, n, out_index, sdf_sign, sdf, std, grad, grad_head, 0, 1, 0.f, 0.f, nullptr, nullptr};
     return launch_decode(a, n, st);
 }
 
 // lattice decode for mesh extraction; list == nullptr: all n_blocks * lat_n^3 points, else the first *n_dev entries of list
-int launch_decode_lattice(const float* P, const float* latent, const int32_t* block_slots, int64_t n_blocks, int lat_n, float lat_step,
+int launch_decode_lattice(const float* P, const float* latent, int lat_stride, const int32_t* block_slots, int64_t n_blocks, int lat_n, float lat_step,
                           float lat_a, const uint32_t* list, const int32_t* n_dev, int64_t n_max, float sdf_sign, float* sdf, float* std,
                           cudaStream_t st) {
-    DecodeArgs a{P, latent, block_slots, nullptr, n_blocks * lat_n * lat_n * lat_n, nullptr, sdf_sign, sdf, std, nullptr, 0,
+    DecodeArgs a{P, latent, lat_stride, block_slots, nullptr, n_blocks * lat_n * lat_n * lat_n, nullptr, sdf_sign, sdf, std, nullptr, 0,
                  list ? 2 : 1, lat_n, lat_step, lat_a, list, n_dev};
     return launch_decode(a, n_max, st);
 }
@@ -230,13 +230,15 @@ int dif_prepare_encoder(const float* blob_dev, void* prepared_dev, void* stream)
     return prepare_encoder_tc((const float*)prepared_dev, (unsigned char*)prepared_dev + (size_t)EncW::FP32_END * sizeof(float), (cudaStream_t)stream);
 }
 
-int dif_decode(const void* decoder_prepared, const float* latent, const int32_t* rows, const float* xyz, int64_t n,
+int dif_decode(const void* decoder_prepared, const float* latent, int latent_stride, const int32_t* rows, const float* xyz, int64_t n,
                const int32_t* out_index, float sdf_sign, float* sdf, float* std, float* dsdf_dxyz, float* dstd_dxyz, void* stream) {
-    if (n < 0 || !decoder_prepared || (n > 0 && (!latent || !xyz || !sdf || !std))) return DIF_E_INVALID;
+    if (n < 0 || !decoder_prepared || latent_stride < DIF_L || (n > 0 && (!latent || !xyz || !sdf || !std))) return DIF_E_INVALID;
+    if (latent_stride == 32 && ((uintptr_t)latent & 15)) return DIF_E_INVALID;          // 32-float rows are read with 16-byte loads
+    const int lat_stride = latent_stride;
     const float* P = (const float*)decoder_prepared;
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = launch_decode_explicit(P, latent, rows, xyz, n, out_index, sdf_sign, sdf, std, dsdf_dxyz, 0, st);
-    if (rc == DIF_OK && dstd_dxyz) rc = launch_decode_explicit(P, latent, rows, xyz, n, out_index, sdf_sign, sdf, std, dstd_dxyz, 1, st);
+    int rc = launch_decode_explicit(P, latent, lat_stride, rows, xyz, n, out_index, sdf_sign, sdf, std, dsdf_dxyz, 0, st);
+    if (rc == DIF_OK && dstd_dxyz) rc = launch_decode_explicit(P, latent, lat_stride, rows, xyz, n, out_index, sdf_sign, sdf, std, dstd_dxyz, 1, st);
     return rc;
 }
 

@@ -10,7 +10,7 @@ namespace dif {
 
 constexpr int XROW = 32;
 
-__global__ void shard_pack_kernel(const float* __restrict__ latent, const int32_t* __restrict__ xchg_slots, const int32_t* __restrict__ n_xchg,
+__global__ void shard_pack_kernel(const float* __restrict__ latent, int lat_stride, const int32_t* __restrict__ xchg_slots, const int32_t* __restrict__ n_xchg,
                                   int64_t cap_rows, float* __restrict__ send) {
     const int count = *n_xchg;
     const int64_t rows = count < cap_rows ? count : cap_rows;
@@ -21,11 +21,11 @@ __global__ void shard_pack_kernel(const float* __restrict__ latent, const int32_
     const int slot = xchg_slots[r];
     float v = 0.f;
     if (w == 0) v = __int_as_float(slot);
-    else if (w <= DIF_L) v = latent[(int64_t)slot * DIF_L + (w - 1)];
+    else if (w <= DIF_L) v = latent[(int64_t)slot * lat_stride + (w - 1)];
     send[(r + 1) * XROW + w] = v;
 }
 
-__global__ void shard_unpack_kernel(float* __restrict__ latent, int64_t capacity, const float* __restrict__ gathered, int world, int my_rank,
+__global__ void shard_unpack_kernel(float* __restrict__ latent, int lat_stride, int64_t capacity, const float* __restrict__ gathered, int world, int my_rank,
                                     int64_t cap_rows, int32_t* __restrict__ overflow) {
     const int src = blockIdx.y;
     const float* buf = gathered + (int64_t)src * (cap_rows + 1) * XROW;
@@ -37,7 +37,7 @@ __global__ void shard_unpack_kernel(float* __restrict__ latent, int64_t capacity
     const int64_t r = e / XROW; const int w = (int)(e % XROW);
     if (r >= rows || w == 0 || w > DIF_L) return;
     const int slot = __float_as_int(buf[(r + 1) * XROW]);
-    if (slot >= 0 && slot < capacity) latent[(int64_t)slot * DIF_L + (w - 1)] = buf[(r + 1) * XROW + w];
+    if (slot >= 0 && slot < capacity) latent[(int64_t)slot * lat_stride + (w - 1)] = buf[(r + 1) * XROW + w];
 }
 
 }  // namespace dif
@@ -51,7 +51,7 @@ size_t dif_shard_xchg_bytes(int64_t cap_rows) { return (size_t)(cap_rows + 1) * 
 int dif_shard_pack(const dif_map_view* map, const int32_t* n_xchg_dev, int64_t cap_rows, float* send_buf, void* stream) {
     if (!map || !map->xchg_slots || !n_xchg_dev || cap_rows <= 0 || !send_buf) return DIF_E_INVALID;
     const int64_t words = (cap_rows + 1) * XROW;
-    shard_pack_kernel<<<(unsigned)((words + 255) / 256), 256, 0, (cudaStream_t)stream>>>(map->latent_vecs, map->xchg_slots, n_xchg_dev, cap_rows, send_buf);
+    shard_pack_kernel<<<(unsigned)((words + 255) / 256), 256, 0, (cudaStream_t)stream>>>(map->latent_vecs, map->latent_stride > 0 ? map->latent_stride : DIF_L, map->xchg_slots, n_xchg_dev, cap_rows, send_buf);
     DIF_COUNT_LAUNCH(1);
     return check_launch("shard_pack_kernel");
 }
@@ -60,7 +60,7 @@ int dif_shard_unpack(const dif_map_view* map, const float* gathered, int world, 
     if (!map || !gathered || world < 1 || cap_rows <= 0 || !overflow_dev) return DIF_E_INVALID;
     const int64_t words = cap_rows * XROW;
     const dim3 grid((unsigned)((words + 255) / 256), (unsigned)world);
-    shard_unpack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(map->latent_vecs, map->capacity, gathered, world, map->shard_rank, cap_rows, overflow_dev);
+    shard_unpack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(map->latent_vecs, map->latent_stride > 0 ? map->latent_stride : DIF_L, map->capacity, gathered, world, map->shard_rank, cap_rows, overflow_dev);
     DIF_COUNT_LAUNCH(1);
     return check_launch("shard_unpack_kernel");
 }

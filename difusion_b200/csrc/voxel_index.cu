@@ -25,13 +25,14 @@ enum { CTR_N_SAMPLES = 0, CTR_N_TOUCHED = 1, CTR_BASE_SLOT = 2, CTR_OVERFLOW = 3
 struct MapDev {          // by-value copy of dif_map_view for kernels
     int64_t* indexer; float* latent; int64_t* pos; float* obs; uint8_t* dirty; int32_t* n_occ; int64_t capacity;
     Grid g; int prune; float ignore_th, enc_th;
-    int shard_rank, shard_world; int32_t* xchg;
+    int shard_rank, shard_world; int32_t* xchg; int lat_stride;
 };
 static MapDev to_dev(const dif_map_view* m) {
     MapDev d; d.indexer = m->indexer; d.latent = m->latent_vecs; d.pos = m->latent_vecs_pos; d.obs = m->voxel_obs_count;
     d.dirty = m->slot_dirty; d.n_occ = m->n_occupied; d.capacity = m->capacity; d.g = make_grid(m);
     d.prune = m->prune_min_vox_obs; d.ignore_th = m->ignore_count_th; d.enc_th = m->encoder_count_th;
     d.shard_rank = m->shard_rank; d.shard_world = m->shard_world > 1 ? m->shard_world : 1; d.xchg = m->xchg_slots;
+    d.lat_stride = m->latent_stride > 0 ? m->latent_stride : DIF_L;
     return d;
 }
 
@@ -286,9 +287,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) alloc_kernel(MapDev m, uint32_t*
                     const int b = __ffs(bits) - 1; bits &= bits - 1;
                     const int64_t lin = (w0 + j) * 32 + b;
                     m.indexer[lin] = slot; m.pos[slot] = lin; m.obs[slot] = 0.f;
-                    float* row = m.latent + (int64_t)slot * DIF_L;
-#pragma unroll
-                    for (int q = 0; q < DIF_L; ++q) row[q] = 0.f;
+                    float* row = m.latent + (int64_t)slot * m.lat_stride;
+                    for (int q = 0; q < m.lat_stride; ++q) row[q] = 0.f;             // (padding columns of a 32-float row included)
                     ++slot;
                 }
             }
@@ -464,7 +464,7 @@ __global__ void fuse_kernel(MapDev m, const int32_t* __restrict__ touched, const
         const bool owned = m.shard_world == 1 || shard_owner(m.pos[slot], m.shard_world) == m.shard_rank;
         const int64_t so = (int64_t)slot * DIF_SUM_STRIDE + lane;
         if (owned && lane < DIF_L) {
-            const int64_t o = (int64_t)slot * DIF_L + lane;
+            const int64_t o = (int64_t)slot * m.lat_stride + lane;
             const float sum = __fadd_rn(slot_sum[so], __fmul_rn(m.latent[o], n_old));
             m.latent[o] = __fdiv_rn(sum, n_new);
         }

@@ -128,7 +128,7 @@ class _DecodeFn(torch.autograd.Function):
         std = torch.empty(n, dtype=torch.float32, device=dev)
         need = xyz.requires_grad
         g = torch.empty((n, 3), dtype=torch.float32, device=dev) if need else None
-        _lib.check(L.dif_decode(prep.decoder.data_ptr(), _lib.ptr(lat), None, _lib.ptr(x), n, None, 1.0, _lib.ptr(sdf), _lib.ptr(std),
+        _lib.check(L.dif_decode(prep.decoder.data_ptr(), _lib.ptr(lat), LATENT_DIM, None, _lib.ptr(x), n, None, 1.0, _lib.ptr(sdf), _lib.ptr(std),
                                 _lib.ptr(g), None, _lib.stream_ptr(dev)), "dif_decode")
         ctx.prep = prep
         ctx.save_for_backward(x, lat, g if need else torch.empty(0, device=dev))
@@ -148,7 +148,7 @@ class _DecodeFn(torch.autograd.Function):
                 s1 = torch.empty(n, dtype=torch.float32, device=x.device)
                 g0 = torch.empty((n, 3), dtype=torch.float32, device=x.device)
                 g1 = torch.empty((n, 3), dtype=torch.float32, device=x.device)
-                _lib.check(L.dif_decode(ctx.prep.decoder.data_ptr(), _lib.ptr(lat), None, _lib.ptr(x), n, None, 1.0, _lib.ptr(s0),
+                _lib.check(L.dif_decode(ctx.prep.decoder.data_ptr(), _lib.ptr(lat), LATENT_DIM, None, _lib.ptr(x), n, None, 1.0, _lib.ptr(s0),
                                         _lib.ptr(s1), _lib.ptr(g0), _lib.ptr(g1), _lib.stream_ptr(x.device)), "dif_decode")
                 grad = grad + g_std.unsqueeze(-1) * g1
         return grad, None, None

@@ -183,7 +183,7 @@ class DenseIndexedMap:
     def _grow(self, new_cap: int):
         dev = self.device
         with torch.cuda.device(dev):
-            lat = torch.zeros((new_cap, LATENT_DIM), dtype=torch.float32, device=dev)
+            lat = torch.zeros((new_cap, _lib.LATENT_ROW_FLOATS), dtype=torch.float32, device=dev)   # 128-byte rows, columns 29..31 stay zero
             pos = torch.full((new_cap,), -1, dtype=torch.long, device=dev)
             obs = torch.zeros((new_cap,), dtype=torch.float32, device=dev)
             opt = torch.zeros((new_cap,), dtype=torch.bool, device=dev)
@@ -263,7 +263,7 @@ class DenseIndexedMap:
         return max(1, _next_pow2(self.n_occupied))         # the reference's doubling rule, map.py:266-268
 
     indexer = property(lambda self: self._indexer)
-    latent_vecs = property(lambda self: self._latent[:self._cap_ref()])
+    latent_vecs = property(lambda self: self._latent[:self._cap_ref(), :LATENT_DIM])        # the reference's (capacity, 29) tensor: a strided view
     latent_vecs_pos = property(lambda self: self._pos[:self._cap_ref()])
     voxel_obs_count = property(lambda self: self._obs[:self._cap_ref()])
     voxel_optimized = property(lambda self: self._optimized[:self._cap_ref()])
@@ -288,7 +288,7 @@ class DenseIndexedMap:
         c = cv["latent_vecs"].size(0)
         self._indexer.copy_(cv["indexer"])
         self._latent.zero_(); self._pos.fill_(-1); self._obs.zero_(); self._optimized.zero_(); self._dirty.zero_()
-        self._latent[:c], self._pos[:c], self._obs[:c], self._optimized[:c] = cv["latent_vecs"], cv["latent_vecs_pos"], \
+        self._latent[:c, :LATENT_DIM], self._pos[:c], self._obs[:c], self._optimized[:c] = cv["latent_vecs"], cv["latent_vecs_pos"], \
             cv["voxel_obs_count"], cv["voxel_optimized"]
         self.n_occupied = n
 
@@ -311,6 +311,7 @@ class DenseIndexedMap:
         v.encoder_count_th = float(a.encoder_count_th)
         v.shard_rank, v.shard_world = self._shard_rank, self._shard_world
         v.xchg_slots = self._xchg.data_ptr() if self._xchg is not None else None
+        v.latent_stride = _lib.LATENT_ROW_FLOATS
         self._view_key, self._view_obj = key, v
         return v
 
@@ -551,7 +552,7 @@ class _GetSdfFn(torch.autograd.Function):
         std = torch.empty(M, dtype=torch.float32, device=dev)
         need = xyz.requires_grad
         g = torch.empty((M, 3), dtype=torch.float32, device=dev) if need else None
-        _lib.check(m._L.dif_decode(m._prep.decoder.data_ptr(), m._latent.data_ptr(), rows.data_ptr(), x.data_ptr(), M, None, 1.0,
+        _lib.check(m._L.dif_decode(m._prep.decoder.data_ptr(), m._latent.data_ptr(), _lib.LATENT_ROW_FLOATS, rows.data_ptr(), x.data_ptr(), M, None, 1.0,
                                    sdf.data_ptr(), std.data_ptr(), _lib.ptr(g), None, _lib.stream_ptr(dev)), "dif_decode")
         ctx.m, ctx.n = m, xyz.size(0)
         ctx.save_for_backward(idx, rows, x, g if need else torch.empty(0, device=dev))
@@ -569,7 +570,7 @@ class _GetSdfFn(torch.autograd.Function):
             M = x.size(0)
             s0 = torch.empty(M, dtype=torch.float32, device=x.device); s1 = torch.empty_like(s0)
             g0 = torch.empty((M, 3), dtype=torch.float32, device=x.device); g1 = torch.empty_like(g0)
-            _lib.check(m._L.dif_decode(m._prep.decoder.data_ptr(), m._latent.data_ptr(), rows.data_ptr(), x.data_ptr(), M, None, 1.0,
+            _lib.check(m._L.dif_decode(m._prep.decoder.data_ptr(), m._latent.data_ptr(), _lib.LATENT_ROW_FLOATS, rows.data_ptr(), x.data_ptr(), M, None, 1.0,
                                        s0.data_ptr(), s1.data_ptr(), g0.data_ptr(), g1.data_ptr(), _lib.stream_ptr(x.device)), "dif_decode")
             grad_rel = grad_rel + g_std.unsqueeze(-1) * g1
         grad = torch.zeros((ctx.n, 3), dtype=torch.float32, device=x.device)

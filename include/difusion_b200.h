@@ -79,6 +79,10 @@ typedef struct dif_map_view {
      * the slots whose latent rows this rank owns and changed: the caller all-gathers (slot, row) pairs and writes them back. */
     int32_t  shard_rank, shard_world;
     int32_t* xchg_slots;         /* [>= min(8*n_points, capacity)] or NULL */
+    /* floats between consecutive rows of latent_vecs: 29 = the reference's packed rows, 32 = rows padded to 128 bytes (16-byte
+     * aligned: the gather kernels then fetch a row with 8 vector loads instead of 29 scalar ones; the Python mirror stores the
+     * table this way and exposes the reference's (capacity, 29) tensor as a strided view).  0 is read as 29. */
+    int32_t  latent_stride;
 } dif_map_view;
 
 /* ---- integrate_keyframe  (system/map.py:340-452; SURVEY rows a-2 .. a-6) -----------------------------
@@ -123,10 +127,10 @@ int dif_integrate(const dif_map_view* map, const void* encoder_prepared,
 
 /* ---- network evaluation  (network/utility.py:61-126 forward_model; di_decoder.py:55-86; di_encoder.py:26-30) --
  * dif_decode: sdf/std (and optionally d sdf/d xyz, d std/d xyz) for n samples.  Sample i reads latent row
- *   rows ? rows[i] : i   of `latent` (row stride 29 floats); rows[i] < 0 marks a padding sample (outputs 0).
+ *   rows ? rows[i] : i   of `latent` (row stride latent_stride floats); rows[i] < 0 marks a padding sample (outputs 0).
  *   out_index (nullable) scatters result i to position out_index[i]; sdf_sign multiplies sdf (map.py:687). */
-int dif_decode(const void* decoder_prepared, const float* latent, const int32_t* rows, const float* xyz /*[n][3]*/,
-               int64_t n, const int32_t* out_index, float sdf_sign,
+int dif_decode(const void* decoder_prepared, const float* latent, int latent_stride /* floats per row: 29, or 32 (16-byte aligned rows) */,
+               const int32_t* rows, const float* xyz /*[n][3]*/, int64_t n, const int32_t* out_index, float sdf_sign,
                float* sdf, float* std, float* dsdf_dxyz /*[n][3] or NULL*/, float* dstd_dxyz /*[n][3] or NULL*/, void* stream);
 int dif_encode(const void* encoder_prepared, const float* xyzn /*[n][6]*/, int64_t n, float* latent_out /*[n][29]*/, void* stream);
 

@@ -322,6 +322,25 @@ class OracleMap:
         return tri, fid, std
 
 
+# ----------------------------------------------------------------------------------------- a-12 / f-2
+def host_cache_keep_mask(cache_ids: np.ndarray, new_ids: np.ndarray) -> np.ndarray:
+    """map.py:708-709 + _get_valid_idx (:20-26): a cached triangle survives iff its PLIVox id is not among the new ones.
+    (The reference searches the sorted unique new ids; for a cached id above their maximum it reads one past the end of the
+    array - undefined under numba - where the intent, and this restatement, is "keep".)  Pinned against the executed reference
+    by tests/golden/make_golden_merge.py -> tests/golden/ref_host_merge.npz."""
+    return ~np.isin(cache_ids, np.unique(new_ids))
+
+
+def host_cache_merge(cache, new, voxel_size: np.float32, bound_min: np.ndarray):
+    """map.py:698-714: voxel units -> world (two rounded fp32 ops), drop cached rows of re-meshed PLIVoxes, append.
+    cache / new: (tri (T,3,3) f32, id (T,) i64, std (T,3) f32); cache may be None."""
+    world = (new[0] * np.float32(voxel_size) + bound_min.astype(np.float32), new[1], new[2])
+    if cache is None:
+        return world
+    keep = host_cache_keep_mask(cache[1], new[1])
+    return tuple(np.concatenate([c[keep], n], 0) for c, n in zip(cache, world))
+
+
 # ----------------------------------------------------------------------------------------- a-9
 def compose(Ra, ta, Rb, tb):
     """Isometry.dot (motion_util.py:277-278) on rotation matrices, float64."""

@@ -71,7 +71,7 @@ def test_decoder_ragged_and_padding(golden, model, dev):
     rows[::3] = -1
     lat, xyz = _t(fx["latent"][:n], dev), _t(fx["xyz"][:n], dev)
     sdf = torch.full((n,), 7.0, device=dev); std = torch.full((n,), 7.0, device=dev)
-    _lib.check(_lib.lib().dif_decode(prep.decoder.data_ptr(), lat.data_ptr(), rows.data_ptr(), xyz.data_ptr(), n, None, -1.0,
+    _lib.check(_lib.lib().dif_decode(prep.decoder.data_ptr(), lat.data_ptr(), lat.stride(0), rows.data_ptr(), xyz.data_ptr(), n, None, -1.0,
                                      sdf.data_ptr(), std.data_ptr(), None, None, _lib.stream_ptr(dev)), "dif_decode")
     live = (rows >= 0).cpu().numpy()
     assert close(-sdf.cpu().numpy()[live], fx["sdf"][:n][live], TOL) and np.all(sdf.cpu().numpy()[~live] == 0)
@@ -508,27 +508,32 @@ def test_mesh_scene_against_oracle(model, dev):
     assert abs(mesh_inc.triangles.shape[0] - mesh_all.triangles.shape[0]) < 0.2 * mesh_all.triangles.shape[0]
 
 
-def test_device_mesh_cache_merge_matches_reference_host_merge(model, dev):
-    """dif_mesh_cache_merge vs a numpy restatement of the reference's host merge (map.py:698-714,
-    _get_valid_idx :20-26): bit-exact rows, reference order (kept cached rows, then new rows), world transform of :698."""
+def test_device_mesh_cache_merge_matches_reference_host_merge(golden, model, dev):
+    """dif_mesh_cache_merge vs the reference's host merge (map.py:698-714).  The keep masks come from the reference's
+    own `_get_valid_idx` (:20-26) EXECUTED on these id streams (tests/golden/make_golden_merge.py -> ref_host_merge.npz); rows must be
+    bit-exact, in the reference order (kept cached rows, then new rows), with the world transform of :698."""
     import ctypes
     from difusion_b200 import _lib
+    from oracle import dif_oracle as O
     L = _lib.lib()
-    rng = np.random.default_rng(3)
+    fx = golden["ref_host_merge"]
+    rng = np.random.default_rng(11)
     n_cells, vs, bmin = 50_000, np.float32(0.05), np.array([-1.5, 0.25, 2.0], np.float32)
     persist = torch.zeros(L.dif_mesh_cache_scratch_bytes(n_cells, 1 << 16), dtype=torch.uint8, device=dev)
     cache = None
-    for step, (n_new, id_hi) in enumerate([(5000, 400), (3000, 800), (0, 1), (7777, 50_000), (1, 3)]):
+    for step in range(5):
+        fid = fx[f"s{step}.new_ids"]
+        n_new = fid.shape[0]
         tri = rng.uniform(0, 40, (n_new, 3, 3)).astype(np.float32)
-        fid = np.sort(rng.integers(0, id_hi, n_new)).astype(np.int64)          # MC emits per-PLIVox runs; any order must work
-        rng.shuffle(fid)
         std = rng.uniform(0, 0.15, (n_new, 3)).astype(np.float32)
         world = tri * vs + bmin                                                # map.py:698 (two rounded fp32 ops)
         if cache is None:
             exp = (world, fid, std)
         else:
-            keep = ~np.isin(cache[1], np.unique(fid))                          # == _get_valid_idx
+            keep = np.unpackbits(fx[f"s{step}.keep"])[:cache[1].shape[0]].astype(bool)     # the executed reference's mask
+            assert np.array_equal(keep, O.host_cache_keep_mask(cache[1], fid))
             exp = tuple(np.concatenate([c[keep], n], 0) for c, n in zip(cache, (world, fid, std)))
+        assert exp[1].shape[0] == int(fx[f"s{step}.n_cache_after"])
         n_cache = 0 if cache is None else cache[0].shape[0]
         d_cache = [None] * 3 if cache is None else [_t(c, dev) for c in cache]
         d_new = [_t(tri, dev), _t(fid, dev), _t(std, dev)]

@@ -59,3 +59,26 @@ def test_map_state(golden, oracle_weights, name):
         tri, fid, std3 = mc_oracle.marching_cubes_interp(m.indexer.reshape(m.n_xyz), foc, mp, hs, hd, int(4e6), m.n_xyz,
                                                          float(fx["mesh.max_std"]))
         assert abs(tri.shape[0] - int(fx["mesh.n_tri_oracle_mc"])) <= 8      # threshold flips on ~1e-6 sdf noise
+
+
+def test_host_cache_merge_restatement_against_executed_reference(golden):
+    """a-12 / f-2: oracle.host_cache_keep_mask vs the keep masks the reference's own numba `_get_valid_idx` produced
+    (tests/golden/make_golden_merge.py), replayed over the same id stream."""
+    from oracle import dif_oracle as O
+    fx = golden["ref_host_merge"]
+    cache_ids = None
+    for step in range(5):
+        fid = fx[f"s{step}.new_ids"]
+        if cache_ids is None:
+            cache_ids = fid
+        else:
+            keep = np.unpackbits(fx[f"s{step}.keep"])[:cache_ids.shape[0]].astype(bool)
+            assert np.array_equal(keep, O.host_cache_keep_mask(cache_ids, fid))
+            cache_ids = np.concatenate([cache_ids[keep], fid])
+        assert cache_ids.shape[0] == int(fx[f"s{step}.n_cache_after"])
+    # the full merge (world transform + order) on a tiny hand-checkable case
+    tri = np.arange(2 * 9, dtype=np.float32).reshape(2, 3, 3)
+    c = O.host_cache_merge(None, (tri, np.array([5, 9]), np.zeros((2, 3), np.float32)), np.float32(0.5), np.array([1, 2, 3], np.float32))
+    assert np.array_equal(c[0][0, 0], np.array([1.0, 2.5, 4.0], np.float32))
+    c2 = O.host_cache_merge(c, (tri[:1], np.array([9]), np.ones((1, 3), np.float32)), np.float32(0.5), np.array([1, 2, 3], np.float32))
+    assert c2[1].tolist() == [5, 9] and np.array_equal(c2[0][0], c[0][0]) and c2[2][1, 0] == 1.0
