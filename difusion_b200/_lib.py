@@ -13,7 +13,7 @@ LIB_PATH = Path(os.environ["DIF_LIB_PATH"]) if os.environ.get("DIF_LIB_PATH") el
 
 ABI_VERSION = 2
 DIF_STAT_COUNT = 12
-STAT_N_KEPT, STAT_N_NEW, STAT_N_SAMPLES, STAT_N_UPDATED, STAT_N_OCCUPIED, STAT_FLAGS, STAT_N_FOCUSED, STAT_N_XCHG, STAT_SEQ = range(9)
+STAT_N_KEPT, STAT_N_NEW, STAT_N_SAMPLES, STAT_N_UPDATED, STAT_N_OCCUPIED, STAT_FLAGS, STAT_N_FOCUSED, STAT_N_XCHG, STAT_SEQ, STAT_N_ROWS = range(10)
 FRAME_HEADER_FLOATS, FRAME_POINT_FLOATS = 32, 9           # DIF_FRAME_HEADER_FLOATS / DIF_FRAME_POINT_FLOATS
 FRAME_TRACK, FRAME_INTEGRATE = 1, 2
 LATENT_ROW_FLOATS = 32       # the map stores 128-byte latent rows (dif_map_view.latent_stride); columns 29..31 are padding
@@ -27,7 +27,8 @@ class MapView(C.Structure):
                 ("capacity", C.c_int64), ("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32),
                 ("bound_min", C.c_float * 3), ("voxel_size", C.c_float), ("prune_min_vox_obs", C.c_int32),
                 ("ignore_count_th", C.c_float), ("encoder_count_th", C.c_float),
-                ("shard_rank", C.c_int32), ("shard_world", C.c_int32), ("xchg_slots", C.c_void_p), ("latent_stride", C.c_int32)]
+                ("shard_rank", C.c_int32), ("shard_world", C.c_int32), ("xchg_slots", C.c_void_p), ("latent_stride", C.c_int32),
+                ("shard_block_log2", C.c_int32), ("row_of_slot", C.c_void_p), ("n_rows", C.c_void_p), ("row_capacity", C.c_int64)]
 
 
 class FrameParams(C.Structure):
@@ -42,10 +43,11 @@ _FP = C.POINTER(C.c_float)          # small HOST float arrays (intrinsics, K R K
 # name -> (restype, argtypes); this table is also what tests/test_abi.py checks against include/difusion_b200.h
 SIGNATURES = {
     "dif_abi_version": (C.c_int, []),
-    "dif_shard_owner": (C.c_int, [_I64, C.c_int]),
-    "dif_shard_xchg_bytes": (_SZ, [_I64]),
+    "dif_shard_owner": (C.c_int, [_I64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "dif_shard_xchg_bytes": (_SZ, [_I64, C.c_int]),
     "dif_shard_pack": (C.c_int, [_MV, _P, _I64, _P, _P]),
-    "dif_shard_unpack": (C.c_int, [_MV, _P, C.c_int, _I64, _P, _P]),
+    "dif_shard_unpack": (C.c_int, [_MV, _P, _I64, _P, _P]),
+    "dif_shard_select_points": (C.c_int, [_MV, _P, _I64, _P, _P, _P, _P]),
     "dif_profile_hook": (C.c_int, [C.c_int, _P, _P]),
     "dif_launch_count": (C.c_uint64, [C.c_int]),
     "dif_debug_tc_timing": (C.c_int, [_P]),

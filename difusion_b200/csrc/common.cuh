@@ -89,13 +89,44 @@ __device__ __forceinline__ bool in_grid(const Grid& g, int ix, int iy, int iz) {
     return (unsigned)ix < (unsigned)g.nx && (unsigned)iy < (unsigned)g.ny && (unsigned)iz < (unsigned)g.nz;
 }
 
-// owner rank of a PLIVox: 64-bit finaliser (splitmix64) of its linear id, modulo the number of ranks
-__host__ __device__ __forceinline__ int shard_owner(int64_t lin, int world) {
-    uint64_t z = (uint64_t)lin + 0x9E3779B97F4A7C15ull;
+// ---- hash-sharded map: ownership --------------------------------------------------------------------------------------------
+// owner(cell) = splitmix64(id of the cell's super-block) % world; a super-block is (2^k)^3 cells.  Hashing blocks instead of
+// single cells keeps a PLIVox and (almost all of) its 26 neighbours on one rank, so only the rows on a block's surface ever
+// have to travel (the blend of mc_interp_kernel.cu:103-181 reads the 3x3x3 neighbourhood).
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z ^= z >> 31;
-    return (int)(z % (uint64_t)world);
+    return z ^ (z >> 31);
+}
+struct Shard { int rank, world, k; };          // k = log2 of the super-block edge in cells
+__host__ __device__ __forceinline__ int shard_block_owner(int bx, int by, int bz, int nbx, int nby, int nbz, int world) {
+    (void)nbx;
+    return (int)(mix64((uint64_t)bz + (uint64_t)nbz * ((uint64_t)by + (uint64_t)nby * (uint64_t)bx)) % (uint64_t)world);
+}
+__host__ __device__ __forceinline__ int shard_owner_xyz(int nx, int ny, int nz, int ix, int iy, int iz, int k, int world) {
+    const int nbx = ((nx - 1) >> k) + 1, nby = ((ny - 1) >> k) + 1, nbz = ((nz - 1) >> k) + 1;
+    return shard_block_owner(ix >> k, iy >> k, iz >> k, nbx, nby, nbz, world);
+}
+__host__ __device__ __forceinline__ int shard_owner_lin(int nx, int ny, int nz, int64_t lin, int k, int world) {
+    const int iz = (int)(lin % nz), iy = (int)((lin / nz) % ny), ix = (int)(lin / ((int64_t)nz * ny));
+    return shard_owner_xyz(nx, ny, nz, ix, iy, iz, k, world);
+}
+// Bit r set: rank r owns the cell or one of its 26 neighbours' super-blocks, i.e. rank r keeps this cell's latent row (as owner
+// or in its halo).  Only cells on the surface of their super-block have neighbours in other blocks (world <= 32).
+__host__ __device__ __forceinline__ uint32_t shard_holder_mask(int nx, int ny, int nz, int64_t lin, int k, int world) {
+    const int iz = (int)(lin % nz), iy = (int)((lin / nz) % ny), ix = (int)(lin / ((int64_t)nz * ny));
+    const int nbx = ((nx - 1) >> k) + 1, nby = ((ny - 1) >> k) + 1, nbz = ((nz - 1) >> k) + 1;
+    const int bx = ix >> k, by = iy >> k, bz = iz >> k, e = (1 << k) - 1;
+    // neighbour-block offsets per axis: -1 if the cell sits on the low face of its block, +1 on the high face (grid-clamped)
+    const int x0 = ((ix & e) == 0 && ix > 0) ? -1 : 0, x1 = ((ix & e) == e && ix < nx - 1) ? 1 : 0;
+    const int y0 = ((iy & e) == 0 && iy > 0) ? -1 : 0, y1 = ((iy & e) == e && iy < ny - 1) ? 1 : 0;
+    const int z0 = ((iz & e) == 0 && iz > 0) ? -1 : 0, z1 = ((iz & e) == e && iz < nz - 1) ? 1 : 0;
+    uint32_t m = 0;
+    for (int dx = x0; dx <= x1; ++dx)
+        for (int dy = y0; dy <= y1; ++dy)
+            for (int dz = z0; dz <= z1; ++dz) m |= 1u << shard_block_owner(bx + dx, by + dy, bz + dz, nbx, nby, nbz, world);
+    return m;
 }
 
 // One latent row (29 floats) into x[0..28] (x[29..31] are left for the caller).  Rows padded to 32 floats are 16-byte aligned:

@@ -11,6 +11,7 @@ struct DecodeArgs {
     const float* P; const float* latent; int lat_stride; const int32_t* rows; const float* xyz; int64_t n;
     const int32_t* out_index; float sdf_sign; float* sdf; float* std; float* grad; int grad_head;
     int mode; int lat_n; float lat_step, lat_a; const uint32_t* list; const int32_t* n_dev;
+    const int32_t* row_map;      // lattice modes on a sharded map: block slot -> local latent row (NULL = identity)
 };
 
 __device__ __forceinline__ float lattice_coord(const DecodeArgs& a, int i) {
@@ -29,6 +30,7 @@ __device__ __forceinline__ void decode_sample_source(const DecodeArgs& a, int64_
     } else {
         const int64_t g = a.mode == 1 ? sidx : (int64_t)a.list[sidx];
         row = a.rows[g / n3]; li = (int)(g % n3); out = g;
+        if (a.row_map && row >= 0) row = a.row_map[row];
     }
 }
 

@@ -14,7 +14,7 @@
 // in place: the tensor pipe works on layer l+1 while the rest of layer l's epilogue is still converting.
 //
 //   L0: x tile (smem) -> R0   E0: R0 in place      L1: R0 -> R1   E1: R1 in place
-//   L2: R1 -> R0 (N = 96)     E2: R0[0,96) in place + the 32 inputs parked in R0[96,128) (skip connection)
+//   L2: R1 -> R0 (N = 96)     E2: R0[0,96) in place; the 32 inputs were parked in R0[96,128) at E1 (skip connection)
 //   L3: R0 -> R1              E3: heads read R1.   Next tile: L0 -> R0 right behind L3 (in-order pipe), L1 waits for E3.
 //
 // Hand-off barriers per slot: ACCa (L0, L2) / ACCb (L1, L3) accumulator complete (tcgen05.commit); G0..G3 one per 32-column
@@ -31,7 +31,10 @@ constexpr uint32_t D2_SMEM_B = D2_OFF_BAR + 176 + 16;           // 21 barriers (
 static_assert(D2_SMEM_B <= 232448, "shared memory budget");
 enum { D2_W = 0, D2_X = 1, D2_XF = 3, D2_E = 5, D2_ACCA = 7, D2_ACCB = 9, D2_G = 11 };      // per-slot barriers: index + slot; G: 11 + 4*slot + g (.. 18)
 
-constexpr int MMA_WARP2 = 19;          // second issuer warp (slot 1)
+#ifndef DIF_D2_ISSUERS
+#define DIF_D2_ISSUERS 1               // 1: one issuer, slots strictly alternating (default); 2: one issuer warp per slot (A/B)
+#endif
+constexpr int MMA_WARP2 = 19;          // second issuer warp (DIF_D2_ISSUERS == 2)
 
 // Development aid (tools/tc_trace.py, build with -DDIF_TC_TRACE): CTA 0 logs (event id, SM clock) per warp into the timing buffer.
 #ifdef DIF_TC_TRACE
@@ -100,30 +103,26 @@ __device__ __forceinline__ void issue_hidden_layer(uint32_t R0, uint32_t R1, uin
     constexpr int N = LAYER == 2 ? 96 : 128;
     const uint32_t acc = LAYER == 2 ? R0 : R1, a_base = LAYER == 2 ? R1 : R0;
     // group g = 2 i + h  (column half h, epilogue iteration i)  ->  K steps: layers 1, 2: {4h + 2i, +1}; layer 3: i = 0: {3h, 3h + 1}, i = 1: {3h + 2, 6 + h}
+    // The two column halves finish an iteration at about the same time, so their groups are awaited and issued together (12 MMAs
+    // behind one wait / fence / elect sequence: that sequence costs ~250 cycles, too much to pay per 384 cycles of tensor work).
     mbar_wait_spin(bg, ph_g);
+    mbar_wait_spin(bg + 8, ph_g);
     if (LAYER == 1 && wait_e) { mbar_wait_spin(e_bar, ph_e); ph_e ^= 1; }             // heads of the previous tile have read R1
     trace(16 + 4 * LAYER);
     tc_fence_after();
-    if (elect_one()) issue_group<N, 0, 1, true>(acc, a_base, wh, wl);
-    __syncwarp();
-    trace(48 + 4 * LAYER);
-    mbar_wait_spin(bg + 8, ph_g);
-    trace(17 + 4 * LAYER);
-    tc_fence_after();
-    if (elect_one()) { if (LAYER < 3) issue_group<N, 4, 5, false>(acc, a_base, wh, wl); else issue_group<N, 3, 4, false>(acc, a_base, wh, wl); }
+    if (elect_one()) {
+        issue_group<N, 0, 1, true>(acc, a_base, wh, wl);
+        if (LAYER < 3) issue_group<N, 4, 5, false>(acc, a_base, wh, wl); else issue_group<N, 3, 4, false>(acc, a_base, wh, wl);
+    }
     __syncwarp();
     trace(49 + 4 * LAYER);
     mbar_wait_spin(bg + 16, ph_g);
+    mbar_wait_spin(bg + 24, ph_g);
     trace(18 + 4 * LAYER);
     tc_fence_after();
-    if (elect_one()) { if (LAYER < 3) issue_group<N, 2, 3, false>(acc, a_base, wh, wl); else issue_group<N, 2, 6, false>(acc, a_base, wh, wl); }
-    __syncwarp();
-    trace(50 + 4 * LAYER);
-    mbar_wait_spin(bg + 24, ph_g);
-    trace(19 + 4 * LAYER);
-    tc_fence_after();
     if (elect_one()) {
-        if (LAYER < 3) issue_group<N, 6, 7, false>(acc, a_base, wh, wl); else issue_group<N, 5, 7, false>(acc, a_base, wh, wl);
+        if (LAYER < 3) { issue_group<N, 2, 3, false>(acc, a_base, wh, wl); issue_group<N, 6, 7, false>(acc, a_base, wh, wl); }
+        else { issue_group<N, 2, 6, false>(acc, a_base, wh, wl); issue_group<N, 5, 7, false>(acc, a_base, wh, wl); }
         mma_commit(commit_bar);
     }
     __syncwarp();
@@ -166,6 +165,77 @@ __global__ void __launch_bounds__(THREADS, 1) decode_tc2_kernel(const unsigned c
     tc_fence_after();
     const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_ptr_s, 0);
 
+#if DIF_D2_ISSUERS == 1
+    if (warp == MMA_WARP) {
+        // ===================================================== MMA issuer: ONE warp, the two slots STRICTLY ALTERNATING layer by layer
+        // (L0 A, L0 B, L1 A, L1 B, ...), every hand-off group awaited with a blocking wait in a fixed order.  With one issuer per
+        // slot the two tiles ran in lockstep (a shared in-order pipe synchronises its clients: whoever is behind gets the pipe
+        // alone and catches up), so both slots converted at the same time and both wanted the tensor pipe at the same time -
+        // measured ~5 k cycles per layer pair for 3.1 k cycles of MMA work.  Alternation puts them in anti-phase: while slot A's
+        // layer l+1 is issued group by group behind its epilogue, slot B's epilogue warps have the ALUs to themselves, and vice versa.
+        if (lane == 0) {
+            mbar_expect_tx(bar0 + 8 * D2_W, IMAGE_B);
+            constexpr uint32_t CH = 32768;
+            for (uint32_t off = 0; off < IMAGE_B; off += CH) bulk_g2s(sbase + off, image + off, (IMAGE_B - off) < CH ? (IMAGE_B - off) : CH, bar0 + 8 * D2_W);
+        }
+        __syncwarp();
+        mbar_wait(bar0 + 8 * D2_W, 0);
+        TC_ACC(0, tcur);                                   // [0] weight image load
+        const uint64_t w0h = smem_desc(sbase + OFF_W0, 128 * 16, 128), w0l = smem_desc(sbase + PLANE_B + OFF_W0, 128 * 16, 128);
+        const uint64_t w1h = smem_desc(sbase + OFF_W1, 128 * 16, 128), w1l = smem_desc(sbase + PLANE_B + OFF_W1, 128 * 16, 128);
+        const uint64_t w2h = smem_desc(sbase + OFF_W2, 96 * 16, 128), w2l = smem_desc(sbase + PLANE_B + OFF_W2, 96 * 16, 128);
+        const uint64_t w3h = smem_desc(sbase + OFF_W3, 128 * 16, 128), w3l = smem_desc(sbase + PLANE_B + OFF_W3, 128 * 16, 128);
+        const uint64_t xh0 = smem_desc(sbase + OFF_X, X_CHUNK_B, 128), xl0 = smem_desc(sbase + OFF_X + X_PLANE_B, X_CHUNK_B, 128);
+        const uint64_t xh1 = smem_desc(sbase + OFF_X + 2 * X_PLANE_B, X_CHUNK_B, 128), xl1 = smem_desc(sbase + OFF_X + 3 * X_PLANE_B, X_CHUNK_B, 128);
+        const uint32_t A0 = tmem, A1 = tmem + 128, B0 = tmem + 256, B1 = tmem + 384;              // slot A: R0 / R1, slot B: R0 / R1
+        const uint32_t bgA = bar0 + 8 * D2_G, bgB = bar0 + 8 * (D2_G + 4);
+        uint32_t ph_eA = 0, ph_eB = 0, ph_g = 0;           // ph_g: all group barriers flip once per hidden layer, both slots in step
+        auto trace = [&](int ev) { TC_TRACE(ev); TC_ACC((ev < 48 ? 1 : 2), tcur); };
+        // L0 of a slot's NEXT tile is issued right behind its L3 when the producer has the x tile ready by then (one probe, no
+        // wait): R0 is free as soon as L3 is in the in-order pipe, and the tile boundary (heads + refill) stops being a bubble.
+        bool l0A = false, l0B = false;                     // L0 of the current iteration already issued (early, in the previous one)
+        auto issue_l0 = [&](const int s) {
+            tc_fence_after();
+            if (elect_one()) {
+                if (s == 0) { issue_layer(idesc_f16(128), 128 * 16, 0, 2, A0, 0, 0, xh0, xl0, w0h, w0l); mma_commit(bar0 + 8 * D2_ACCA); }
+                else { issue_layer(idesc_f16(128), 128 * 16, 0, 2, B0, 0, 0, xh1, xl1, w0h, w0l); mma_commit(bar0 + 8 * (D2_ACCA + 1)); }
+            }
+            __syncwarp();
+        };
+        uint32_t ph_xA = 0, ph_xB = 0;
+        for (int64_t it = 0;; ++it) {
+            const int64_t t0 = blockIdx.x + (int64_t)gridDim.x * (2 * it), t1 = t0 + gridDim.x;
+            if (t0 >= n_tiles) break;
+            const bool liveB = t1 < n_tiles;
+            const bool nextA = t0 + 2 * (int64_t)gridDim.x < n_tiles, nextB = t1 + 2 * (int64_t)gridDim.x < n_tiles;
+            // ---- L0: x tile (smem) -> R0
+            if (!l0A) {
+                mbar_wait_spin(bar0 + 8 * D2_X, ph_xA); ph_xA ^= 1;
+                TC_TRACE(1); TC_ACC(1, tcur);
+                issue_l0(0);
+                TC_TRACE(2); TC_ACC(2, tcur);
+            }
+            if (liveB && !l0B) {
+                mbar_wait_spin(bar0 + 8 * (D2_X + 1), ph_xB); ph_xB ^= 1;
+                TC_ACC(1, tcur);
+                issue_l0(1);
+                TC_ACC(2, tcur);
+            }
+            l0A = l0B = false;
+            // ---- L1 (R0 -> R1), L2 (R1 -> R0, N = 96), L3 (R0 -> R1): four hand-off groups each, constant operands
+            issue_hidden_layer<1>(A0, A1, w1h, w1l, bgA, ph_g, bar0 + 8 * D2_ACCB, bar0 + 8 * D2_E, it > 0, ph_eA, trace);
+            if (liveB) issue_hidden_layer<1>(B0, B1, w1h, w1l, bgB, ph_g, bar0 + 8 * (D2_ACCB + 1), bar0 + 8 * (D2_E + 1), it > 0, ph_eB, trace);
+            issue_hidden_layer<2>(A0, A1, w2h, w2l, bgA, ph_g ^ 1u, bar0 + 8 * D2_ACCA, 0u, false, ph_eA, trace);
+            if (liveB) issue_hidden_layer<2>(B0, B1, w2h, w2l, bgB, ph_g ^ 1u, bar0 + 8 * (D2_ACCA + 1), 0u, false, ph_eB, trace);
+            issue_hidden_layer<3>(A0, A1, w3h, w3l, bgA, ph_g, bar0 + 8 * D2_ACCB, 0u, false, ph_eA, trace);
+            if (nextA && __all_sync(0xffffffffu, mbar_test(bar0 + 8 * D2_X, ph_xA))) { ph_xA ^= 1; TC_TRACE(1); issue_l0(0); TC_TRACE(2); l0A = true; }
+            if (liveB) {
+                issue_hidden_layer<3>(B0, B1, w3h, w3l, bgB, ph_g, bar0 + 8 * (D2_ACCB + 1), 0u, false, ph_eB, trace);
+                if (nextB && __all_sync(0xffffffffu, mbar_test(bar0 + 8 * (D2_X + 1), ph_xB))) { ph_xB ^= 1; issue_l0(1); l0B = true; }
+            }
+            ph_g ^= 1;
+        }
+#else
     if (warp == MMA_WARP || warp == MMA_WARP2) {
         // ===================================================== MMA issuer of slot s (warp 16: slot 0 + weight load, warp 19: slot 1)
         // One issuer warp PER SLOT, each walking its own tiles with blocking waits in a fixed order: a single issuer polling both
@@ -209,6 +279,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_tc2_kernel(const unsigned c
             issue_hidden_layer<3>(R0, R1, w3h, w3l, bg, ph_g, bb, be, false, ph_e, trace);
             ph_g ^= 1;
         }
+#endif
     } else if (warp >= PRODUCER_WARP0) {
         // ===================================================== gather producer of slot s: one sample per lane, two stages
         // Stage A resolves WHERE a tile's 128 samples come from (latent row index + xyz: 4 samples x 4 registers per lane) one
@@ -228,7 +299,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_tc2_kernel(const unsigned c
                 decode_sample_source(a, sidx, n_total, n3, row, out, li);
                 r = (int)row;
                 if (a.mode == 0) {
-                    const float* xp = a.xyz + (row >= 0 ? sidx : 0) * 3;
+                    const float* xp = a.xyz + (sidx < n_total ? sidx : 0) * 3;      // (address independent of the loaded row: no load chain)
                     p = make_float3(__ldg(xp), __ldg(xp + 1), __ldg(xp + 2));
                 } else {
                     const int q1 = (int)(((float)li + 0.5f) * inv_n), q2 = (int)(((float)q1 + 0.5f) * inv_n);
@@ -289,6 +360,15 @@ __global__ void __launch_bounds__(THREADS, 1) decode_tc2_kernel(const unsigned c
         const int head_slot = *reinterpret_cast<const int*>(image + IMAGE_B);
         const float head_bias = __ldg(P + (half ? DecW::bu : DecW::b4));
         mbar_wait(bar0 + 8 * D2_W, 0);                 // biases arrive with the weight image
+        float pend_pre = 0.f; int64_t pend_tile = -1;  // outputs of the previous tile, not yet written
+        auto finish_output = [&](int64_t t, float pre) {
+            const int64_t sidx = t * TILE + row;
+            int64_t src_row, out; int li_unused;
+            decode_sample_source(a, sidx, n_total, n3, src_row, out, li_unused);
+            float* dst = half ? a.std : a.sdf;
+            if (src_row >= 0) dst[out] = half ? 0.05f + 0.5f * softplus_ref(pre) : a.sdf_sign * tanhf(pre);
+            else if (sidx < n_total && a.mode == 0 && !a.out_index) dst[out] = 0.f;
+        };
         for (int64_t it = 0;; ++it) {
             const int64_t tile = blockIdx.x + (int64_t)gridDim.x * (2 * it + s);
             if (tile >= n_tiles) break;
@@ -303,6 +383,19 @@ __global__ void __launch_bounds__(THREADS, 1) decode_tc2_kernel(const unsigned c
                 TC_TRACE(80 + layer);
                 TC_ACC(4, tcur);                               // [4] waiting for the accumulator
                 tc_fence_after();
+                if (layer == 1) {
+                    // Layer 1 has completed, so R0 (its A operand) is dead until layer 2 writes columns 0..95: park this half's 16 inputs
+                    // (k = 16*half .. +15: hi plane k-chunks 2*half, 2*half+1, then the lo plane's) in R0[96 + 16*half ..) NOW - they are the
+                    // skip-connection K chunks 6 / 7 of layer 3 - and hand the x tile back to the producer three layers before it is
+                    // needed again (parked at E2 the refill came ~3 k cycles too late for the next tile's layer 0).
+                    const unsigned char* xp = smem + OFF_X + s * 2 * X_PLANE_B + (2 * half) * X_CHUNK_B + row * 16;
+                    const uint4 h0 = *reinterpret_cast<const uint4*>(xp), h1 = *reinterpret_cast<const uint4*>(xp + X_CHUNK_B);
+                    const uint4 l0 = *reinterpret_cast<const uint4*>(xp + X_PLANE_B), l1 = *reinterpret_cast<const uint4*>(xp + X_PLANE_B + X_CHUNK_B);
+                    const uint32_t xv[16] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w, l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+                    tmem_st16(R0 + 96 + 16 * half, xv);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar0 + 8 * (D2_XF + s));       // our generic-proxy reads of the x tile are complete
+                }
                 // ---- group 0: 32 columns = 2 K chunks
                 {
                     uint32_t v0[16], v1[16];
@@ -328,16 +421,8 @@ __global__ void __launch_bounds__(THREADS, 1) decode_tc2_kernel(const unsigned c
                 } else {
                     uint32_t v0[16];
                     tmem_ld16_nowait(R + c_base + 32, v0);
-                    // inputs k = 16*half .. 16*half+15: hi plane k-chunks 2*half, 2*half+1, then the lo plane's
-                    const unsigned char* xp = smem + OFF_X + s * 2 * X_PLANE_B + (2 * half) * X_CHUNK_B + row * 16;
-                    const uint4 h0 = *reinterpret_cast<const uint4*>(xp), h1 = *reinterpret_cast<const uint4*>(xp + X_CHUNK_B);
-                    const uint4 l0 = *reinterpret_cast<const uint4*>(xp + X_PLANE_B), l1 = *reinterpret_cast<const uint4*>(xp + X_PLANE_B + X_CHUNK_B);
-                    const uint32_t xv[16] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w, l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-                    tmem_st16(R + 96 + 16 * half, xv);
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar0 + 8 * (D2_XF + s));       // our generic-proxy reads of the x tile are complete
                     tmem_ld_wait();
-                    convert_inplace16(v0, b + 32, R + c_base + 32);
+                    convert_inplace16(v0, b + 32, R + c_base + 32);           // (this group's second K chunk, the parked inputs, is in place since E1)
                 }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
@@ -345,6 +430,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_tc2_kernel(const unsigned c
                 if (lane == 0) mbar_arrive(g_bar + 16);
                 TC_TRACE(100 + layer);
                 TC_ACC(5, tcur);                               // [5] hidden-layer conversion
+                if (layer == 0 && pend_tile >= 0) { finish_output(pend_tile, pend_pre); pend_tile = -1; }
             }
             // ---- layer 3 + one head per column-half warp on CUDA cores (half 0 -> sdf, half 1 -> std; di_decoder.py:65-70,84)
             mbar_wait(acc_b, ph_b); ph_b ^= 1;
@@ -376,15 +462,12 @@ __global__ void __launch_bounds__(THREADS, 1) decode_tc2_kernel(const unsigned c
             __syncwarp();
             if (lane == 0) mbar_arrive(bar0 + 8 * (D2_E + s));
             TC_TRACE(110);
-            const int64_t sidx = tile * TILE + row;
-            int64_t src_row, out; int li_unused;
-            decode_sample_source(a, sidx, n_total, n3, src_row, out, li_unused);
-            const float pre = p0 + p1 + head_bias;
-            float* dst = half ? a.std : a.sdf;
-            if (src_row >= 0) dst[out] = half ? 0.05f + 0.5f * softplus_ref(pre) : a.sdf_sign * tanhf(pre);
-            else if (sidx < n_total && a.mode == 0 && !a.out_index) dst[out] = 0.f;
-            TC_ACC(6, tcur);                                   // [6] last layer + heads + output
+            // the activation + store of this tile's outputs is deferred until the NEXT tile's first conversion is handed off: the
+            // chain heads(t) -> E0(t+1) -> L1(t+1) is what the tensor pipe waits for at a tile boundary
+            pend_pre = p0 + p1 + head_bias; pend_tile = tile;
+            TC_ACC(6, tcur);                                   // [6] last layer + heads
         }
+        if (pend_tile >= 0) finish_output(pend_tile, pend_pre);
     }
 #ifndef DIF_TC_TRACE
     if (timing && lane == 0) {

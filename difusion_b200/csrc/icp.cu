@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(MLP_THREADS) icp_linearize_kernel(
                 const int ix = (int)ceilf(p.x) - 1, iy = (int)ceilf(p.y) - 1, iz = (int)ceilf(p.z) - 1;
                 if (p.x == p.x && p.y == p.y && p.z == p.z && in_grid(m.g, ix, iy, iz)) {
                     const int64_t sl = m.indexer[lin_id(m.g, ix, iy, iz)];
-                    if (sl >= 0 && m.obs[sl] > m.ignore_th) slot = (int)sl;
+                    if (sl >= 0 && m.obs[sl] > m.ignore_th) slot = m.row_of ? m.row_of[sl] : (int)sl;       // (latent ROW from here on)
                 }
                 rx = __fsub_rn(__fsub_rn(p.x, (float)ix), 0.5f); ry = __fsub_rn(__fsub_rn(p.y, (float)iy), 0.5f); rz = __fsub_rn(__fsub_rn(p.z, (float)iz), 0.5f);
             }
@@ -150,7 +150,8 @@ int icp_launch(const dif_map_view* map, const void* decoder_prepared, const floa
     if (!map || !decoder_prepared || (!pose_host && !frame_dev) || !scratch || !out_dev || n < 0 || n >= (int64_t(1) << 31) || (n > 0 && !obs_xyz))
         return DIF_E_INVALID;
     if (scratch_sz < dif_icp_scratch_bytes(n)) return DIF_E_WORKSPACE;
-    MapRO m{map->indexer, map->latent_vecs, map->voxel_obs_count, make_grid(map), map->ignore_count_th, map->latent_stride > 0 ? map->latent_stride : DIF_L};
+    MapRO m{map->indexer, map->latent_vecs, map->voxel_obs_count, make_grid(map), map->ignore_count_th, map->latent_stride > 0 ? map->latent_stride : DIF_L,
+            map->shard_world > 1 ? map->row_of_slot : nullptr};
     Pose p = {};
     if (pose_host) compose_pose(pose_host, p);
     Carver c(scratch);

@@ -4,7 +4,8 @@
 
 namespace dif {
 
-struct MapRO { const int64_t* indexer; const float* latent; const float* obs; Grid g; float ignore_th; int lat_stride; };
+struct MapRO { const int64_t* indexer; const float* latent; const float* obs; Grid g; float ignore_th; int lat_stride;
+               const int32_t* row_of; };     // row_of: sharded map, slot -> local latent row (-1: not stored on this rank); NULL = identity
 struct Pose { float Rc[9], tc[3], Rd[9], td[3], Rl[9]; };      // composite (last*delta), delta, last rotation
 
 // composite pose exactly as the host path forms it: fp64 products of the fp32 inputs, rounded once (tracker.py:181)

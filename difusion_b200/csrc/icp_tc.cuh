@@ -80,7 +80,11 @@ __device__ __forceinline__ void icp_gather_row(const IcpTcArgs& a, const IcpFram
         const int ix = (int)ceilf(p.x) - 1, iy = (int)ceilf(p.y) - 1, iz = (int)ceilf(p.z) - 1;
         if (p.x == p.x && p.y == p.y && p.z == p.z && in_grid(a.m.g, ix, iy, iz)) {
             const int64_t sl = a.m.indexer[lin_id(a.m.g, ix, iy, iz)];
-            if (sl >= 0 && a.m.obs[sl] > a.m.ignore_th) { slot = sl; valid = true; }
+            if (sl >= 0 && a.m.obs[sl] > a.m.ignore_th) {
+                slot = a.m.row_of ? (int64_t)a.m.row_of[sl] : sl;                 // latent ROW (sharded map: -1 = not on this rank)
+                valid = slot >= 0;
+                if (!valid) slot = 0;
+            }
         }
         rx = __fsub_rn(__fsub_rn(p.x, (float)ix), 0.5f); ry = __fsub_rn(__fsub_rn(p.y, (float)iy), 0.5f); rz = __fsub_rn(__fsub_rn(p.z, (float)iz), 0.5f);
     }

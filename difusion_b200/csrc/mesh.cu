@@ -7,8 +7,8 @@
 
 namespace dif {
 
-int launch_decode_lattice(const float* P, const float* latent, int lat_stride, const int32_t* block_slots, int64_t n_blocks, int lat_n, float lat_step,
-                          float lat_a, const uint32_t* list, const int32_t* n_dev, int64_t n_max, float sdf_sign, float* sdf, float* std,
+int launch_decode_lattice(const float* P, const float* latent, int lat_stride, const int32_t* row_map, const int32_t* block_slots, int64_t n_blocks,
+                          int lat_n, float lat_step, float lat_a, const uint32_t* list, const int32_t* n_dev, int64_t n_max, float sdf_sign, float* sdf, float* std,
                           cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------ trilinear x2 + select
@@ -375,7 +375,7 @@ int dif_mesh_decode(const dif_map_view* map, const void* decoder_prepared, const
     int rc;
     if (!fast || lr < 2) {
         const float step = (float)((sb - sa) / (hr - 1));
-        rc = launch_decode_lattice(P, map->latent_vecs, map->latent_stride > 0 ? map->latent_stride : DIF_L, block_slots, n_blocks, hr, step, (float)sa, nullptr, nullptr, n_blocks * h3, -1.f,
+        rc = launch_decode_lattice(P, map->latent_vecs, map->latent_stride > 0 ? map->latent_stride : DIF_L, map->shard_world > 1 ? map->row_of_slot : nullptr, block_slots, n_blocks, hr, step, (float)sa, nullptr, nullptr, n_blocks * h3, -1.f,
                                    cube_sdf, cube_std, st);
         if (rc) return rc;
         write_counts_kernel<<<1, 1, 0, st>>>(counts_dev, (int32_t)(n_blocks * h3), nullptr);
@@ -388,7 +388,7 @@ int dif_mesh_decode(const dif_map_view* map, const void* decoder_prepared, const
     int32_t* n_sel = c.take<int32_t>(1);
     cudaMemsetAsync(n_sel, 0, sizeof(int32_t), st);
     const float step_l = (float)((sb - sa) / (lr - 1)), step_h = (float)((sb - sa) / (hr - 1));
-    rc = launch_decode_lattice(P, map->latent_vecs, map->latent_stride > 0 ? map->latent_stride : DIF_L, block_slots, n_blocks, lr, step_l, (float)sa, nullptr, nullptr, n_blocks * l3, 1.f,
+    rc = launch_decode_lattice(P, map->latent_vecs, map->latent_stride > 0 ? map->latent_stride : DIF_L, map->shard_world > 1 ? map->row_of_slot : nullptr, block_slots, n_blocks, lr, step_l, (float)sa, nullptr, nullptr, n_blocks * l3, 1.f,
                                low_sdf, low_std, st);
     if (rc) return rc;
     const int64_t total = n_blocks * h3;
@@ -402,7 +402,7 @@ int dif_mesh_decode(const dif_map_view* map, const void* decoder_prepared, const
         }
     }
     DIF_COUNT_LAUNCH(2);
-    rc = launch_decode_lattice(P, map->latent_vecs, map->latent_stride > 0 ? map->latent_stride : DIF_L, block_slots, n_blocks, hr, step_h, (float)sa, list, n_sel, total, -1.f, cube_sdf, cube_std, st);
+    rc = launch_decode_lattice(P, map->latent_vecs, map->latent_stride > 0 ? map->latent_stride : DIF_L, map->shard_world > 1 ? map->row_of_slot : nullptr, block_slots, n_blocks, hr, step_h, (float)sa, list, n_sel, total, -1.f, cube_sdf, cube_std, st);
     if (rc) return rc;
     write_counts_kernel<<<1, 1, 0, st>>>(counts_dev, (int32_t)(n_blocks * l3), n_sel);
     return check_launch("dif_mesh_decode");

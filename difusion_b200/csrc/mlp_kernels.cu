@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(MLP_THREADS) decode_simt_kernel(DecodeArgs a) 
                 } else {
                     const int64_t g = a.mode == 1 ? sidx : (int64_t)a.list[sidx];
                     row = a.rows[g / n3]; li = (int)(g % n3); o = g;
+                    if (a.row_map && row >= 0) row = a.row_map[row];
                 }
             }
             row_s[threadIdx.x] = row; out_s[threadIdx.x] = o; lat_i[threadIdx.x] = li;
@@ -179,16 +180,16 @@ int launch_decode(DecodeArgs a, int64_t n_max, cudaStream_t st) {
 
 int launch_decode_explicit(const float* P, const float* latent, int lat_stride, const int32_t* rows, const float* xyz, int64_t n,
                            const int32_t* out_index, float sdf_sign, float* sdf, float* std, float* grad, int grad_head, cudaStream_t st) {
-    DecodeArgs a{P, latent, lat_stride, rows, xyz, n, out_index, sdf_sign, sdf, std, grad, grad_head, 0, 1, 0.f, 0.f, nullptr, nullptr};
+    DecodeArgs a{P, latent, lat_stride, rows, xyz, n, out_index, sdf_sign, sdf, std, grad, grad_head, 0, 1, 0.f, 0.f, nullptr, nullptr, nullptr};
     return launch_decode(a, n, st);
 }
 
 // lattice decode for mesh extraction; list == nullptr: all n_blocks * lat_n^3 points, else the first *n_dev entries of list
-int launch_decode_lattice(const float* P, const float* latent, int lat_stride, const int32_t* block_slots, int64_t n_blocks, int lat_n, float lat_step,
-                          float lat_a, const uint32_t* list, const int32_t* n_dev, int64_t n_max, float sdf_sign, float* sdf, float* std,
-                          cudaStream_t st) {
+int launch_decode_lattice(const float* P, const float* latent, int lat_stride, const int32_t* row_map, const int32_t* block_slots, int64_t n_blocks,
+                          int lat_n, float lat_step, float lat_a, const uint32_t* list, const int32_t* n_dev, int64_t n_max, float sdf_sign,
+                          float* sdf, float* std, cudaStream_t st) {
     DecodeArgs a{P, latent, lat_stride, block_slots, nullptr, n_blocks * lat_n * lat_n * lat_n, nullptr, sdf_sign, sdf, std, nullptr, 0,
-                 list ? 2 : 1, lat_n, lat_step, lat_a, list, n_dev};
+                 list ? 2 : 1, lat_n, lat_step, lat_a, list, n_dev, row_map};
     return launch_decode(a, n_max, st);
 }
 
@@ -199,7 +200,6 @@ using namespace dif;
 extern "C" {
 
 int dif_debug_tc_timing(void* dev_buf) { return dif::set_tc_timing_buffer((unsigned long long*)dev_buf); }
-int dif_shard_owner(int64_t linear_id, int world) { return world > 1 ? dif::shard_owner(linear_id, world) : 0; }
 int dif_abi_version(void) { return DIF_ABI_VERSION; }
 int dif_profile_hook(int which, void* start_event, void* stop_event) {
     if (which < 0 || which >= DIF_PROF_COUNT) return DIF_E_INVALID;

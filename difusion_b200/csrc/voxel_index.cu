@@ -26,13 +26,21 @@ struct MapDev {          // by-value copy of dif_map_view for kernels
     int64_t* indexer; float* latent; int64_t* pos; float* obs; uint8_t* dirty; int32_t* n_occ; int64_t capacity;
     Grid g; int prune; float ignore_th, enc_th;
     int shard_rank, shard_world; int32_t* xchg; int lat_stride;
+    int shard_k; int32_t* row_of; int32_t* n_rows; int64_t row_cap;      // sharded storage: slot -> local latent row
 };
+// latent row of a slot on this rank (-1: not stored here); identity for the unsharded map
+__device__ __forceinline__ int64_t lat_row(const MapDev& m, int64_t slot) { return m.row_of ? (int64_t)m.row_of[slot] : slot; }
+__device__ __forceinline__ bool owns_cell(const MapDev& m, int64_t lin) {
+    return m.shard_world == 1 || shard_owner_lin(m.g.nx, m.g.ny, m.g.nz, lin, m.shard_k, m.shard_world) == m.shard_rank;
+}
 static MapDev to_dev(const dif_map_view* m) {
     MapDev d; d.indexer = m->indexer; d.latent = m->latent_vecs; d.pos = m->latent_vecs_pos; d.obs = m->voxel_obs_count;
     d.dirty = m->slot_dirty; d.n_occ = m->n_occupied; d.capacity = m->capacity; d.g = make_grid(m);
     d.prune = m->prune_min_vox_obs; d.ignore_th = m->ignore_count_th; d.enc_th = m->encoder_count_th;
     d.shard_rank = m->shard_rank; d.shard_world = m->shard_world > 1 ? m->shard_world : 1; d.xchg = m->xchg_slots;
     d.lat_stride = m->latent_stride > 0 ? m->latent_stride : DIF_L;
+    d.shard_k = m->shard_block_log2; d.row_of = d.shard_world > 1 ? m->row_of_slot : nullptr; d.n_rows = m->n_rows;
+    d.row_cap = d.row_of ? m->row_capacity : m->capacity;
     return d;
 }
 
@@ -287,8 +295,19 @@ __global__ void __launch_bounds__(SCAN_THREADS) alloc_kernel(MapDev m, uint32_t*
                     const int b = __ffs(bits) - 1; bits &= bits - 1;
                     const int64_t lin = (w0 + j) * 32 + b;
                     m.indexer[lin] = slot; m.pos[slot] = lin; m.obs[slot] = 0.f;
-                    float* row = m.latent + (int64_t)slot * m.lat_stride;
-                    for (int q = 0; q < m.lat_stride; ++q) row[q] = 0.f;             // (padding columns of a 32-float row included)
+                    int64_t r = slot;
+                    if (m.row_of) {                          // sharded storage: a row only where this rank owns the PLIVox or keeps it in its halo
+                        r = -1;
+                        if (shard_holder_mask(m.g.nx, m.g.ny, m.g.nz, lin, m.shard_k, m.shard_world) >> m.shard_rank & 1u) {
+                            r = atomicAdd(m.n_rows, 1);
+                            if (r >= m.row_cap) { r = -1; atomicOr(stats + DIF_STAT_FLAGS, 4); }
+                        }
+                        m.row_of[slot] = (int32_t)r;
+                    }
+                    if (r >= 0) {
+                        float* row = m.latent + r * m.lat_stride;
+                        for (int q = 0; q < m.lat_stride; ++q) row[q] = 0.f;         // (padding columns of a 32-float row included)
+                    }
                     ++slot;
                 }
             }
@@ -367,7 +386,7 @@ __global__ void gather_kernel(MapDev m, int n, const dif_frame_params* __restric
                     const int s = to[k] < m.enc_th ? (int)ts[k] : -1;        // T membership (target_slot)
                     slots[k] = s;
                     // sharded map: every rank counts the observation, only the owner of the PLIVox encodes it
-                    mine[k] = s >= 0 && (m.shard_world == 1 || shard_owner(tl[k], m.shard_world) == m.shard_rank);
+                    mine[k] = s >= 0 && owns_cell(m, tl[k]);
                     cnt += mine[k];
                 }
             }
@@ -454,17 +473,21 @@ __global__ void fuse_kernel(MapDev m, const int32_t* __restrict__ touched, const
     const int n_touched = ctr[CTR_N_TOUCHED];
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    if (blockIdx.x == 0 && threadIdx.x == 0) { stats[DIF_STAT_N_SAMPLES] = ctr[CTR_N_SAMPLES]; stats[DIF_STAT_N_UPDATED] = n_touched; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        stats[DIF_STAT_N_SAMPLES] = ctr[CTR_N_SAMPLES]; stats[DIF_STAT_N_UPDATED] = n_touched;
+        stats[DIF_STAT_N_ROWS] = m.row_of ? *m.n_rows : *m.n_occ;
+    }
     for (int w = warp; w < n_touched; w += n_warps) {
         const int slot = touched[w];
         const float cnt = (float)slot_cnt[slot];
         const float n_old = m.obs[slot];
         const float n_new = __fadd_rn(n_old, cnt);
         __syncwarp();
-        const bool owned = m.shard_world == 1 || shard_owner(m.pos[slot], m.shard_world) == m.shard_rank;
+        const int64_t lrow = lat_row(m, slot);
+        const bool owned = owns_cell(m, m.pos[slot]) && lrow >= 0;
         const int64_t so = (int64_t)slot * DIF_SUM_STRIDE + lane;
         if (owned && lane < DIF_L) {
-            const int64_t o = (int64_t)slot * m.lat_stride + lane;
+            const int64_t o = lrow * m.lat_stride + lane;
             const float sum = __fadd_rn(slot_sum[so], __fmul_rn(m.latent[o], n_old));
             m.latent[o] = __fdiv_rn(sum, n_new);
         }
@@ -487,8 +510,11 @@ __global__ void map_query_kernel(MapDev m, const float* __restrict__ xyz, int n,
         const int ix = (int)ceilf(p.x) - 1, iy = (int)ceilf(p.y) - 1, iz = (int)ceilf(p.z) - 1;
         int slot = -1;
         if (p.x == p.x && p.y == p.y && p.z == p.z && in_grid(m.g, ix, iy, iz)) {
-            const int64_t s = m.indexer[lin_id(m.g, ix, iy, iz)];
-            if (s >= 0 && m.obs[s] > m.ignore_th) slot = (int)s;      // strict '>' (map.py:571)
+            const int lin = lin_id(m.g, ix, iy, iz);
+            const int64_t s = m.indexer[lin];
+            // strict '>' (map.py:571).  The output is the latent ROW; on a sharded map only the owner answers (-1 elsewhere), so that
+            // the ranks' partial results add up to the single-GPU answer
+            if (s >= 0 && m.obs[s] > m.ignore_th && owns_cell(m, lin)) slot = (int)lat_row(m, s);
         }
         valid = slot >= 0;
         slot_out[i] = slot;

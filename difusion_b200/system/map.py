@@ -120,7 +120,8 @@ class DenseIndexedMap:
     STATUS_SURF_BIT = 1 << 1
 
     def __init__(self, model, args: argparse.Namespace, latent_dim: int, device: torch.device, enable_async: bool = False,
-                 optimization_device: torch.device = None, initial_capacity: int = 1 << 16):
+                 optimization_device: torch.device = None, initial_capacity: int = 1 << 16, shard=None, shard_block_log2: int = 4,
+                 initial_rows: int = None):
         device = torch.device(device)
         if device.type != "cuda":
             raise _lib.DifusionLibraryError("DenseIndexedMap needs a CUDA device: difusion_b200 has no CPU fallback")
@@ -158,9 +159,19 @@ class DenseIndexedMap:
         self._pending_error = None
         self._reset_epoch = 0
         self.n_frames_with_dropped_points = 0
-        self._shard_rank, self._shard_world, self._xchg = 0, 1, None       # see difusion_b200/shard.py
+        # hash-sharded map (difusion_b200/shard.py): `shard` carries rank / world; the latent table then holds only the rows this
+        # rank owns or keeps in its halo, addressed through _row_of (slot -> local row)
+        self._shard_rank, self._shard_world, self._xchg = 0, 1, None
+        self._shard_k, self._row_of, self._n_rows_dev, self._row_cap = 0, None, None, 0
         self._cap_phys = 0
         self._latent = self._pos = self._obs = self._optimized = self._dirty = None
+        if shard is not None and shard.world > 1:
+            self._shard_rank, self._shard_world, self._shard_k = shard.rank, shard.world, int(shard_block_log2)
+            with torch.cuda.device(device):
+                self._row_of = torch.full((1,), -1, dtype=torch.int32, device=device)
+                self._n_rows_dev = torch.zeros(1, dtype=torch.int32, device=device)
+                self._xchg = torch.empty(1 << 16, dtype=torch.int32, device=device)
+            self._grow_rows(max(1, int(initial_rows or initial_capacity)))
         self._persist = None
         self._scratch = None
         self._scratch_points = 0
@@ -181,19 +192,38 @@ class DenseIndexedMap:
 
     # ------------------------------------------------------------------ state (reference cold_vars, map.py:199-211)
     def _grow(self, new_cap: int):
+        """Double the per-slot arrays.  On a sharded map (``_row_of`` set, difusion_b200/shard.py) the latent table is indexed by
+        LOCAL row, not by slot, and grows separately (``_grow_rows``)."""
         dev = self.device
+        sharded_rows = self._row_of is not None
         with torch.cuda.device(dev):
-            lat = torch.zeros((new_cap, _lib.LATENT_ROW_FLOATS), dtype=torch.float32, device=dev)   # 128-byte rows, columns 29..31 stay zero
             pos = torch.full((new_cap,), -1, dtype=torch.long, device=dev)
             obs = torch.zeros((new_cap,), dtype=torch.float32, device=dev)
             opt = torch.zeros((new_cap,), dtype=torch.bool, device=dev)
             dirty = torch.zeros((new_cap,), dtype=torch.uint8, device=dev)
             if self._cap_phys:
                 c = self._cap_phys
-                lat[:c], pos[:c], obs[:c], opt[:c], dirty[:c] = self._latent, self._pos, self._obs, self._optimized, self._dirty
-            self._latent, self._pos, self._obs, self._optimized, self._dirty = lat, pos, obs, opt, dirty
+                pos[:c], obs[:c], opt[:c], dirty[:c] = self._pos, self._obs, self._optimized, self._dirty
+            self._pos, self._obs, self._optimized, self._dirty = pos, obs, opt, dirty
+            if sharded_rows:
+                row_of = torch.full((new_cap,), -1, dtype=torch.int32, device=dev)
+                row_of[:self._cap_phys] = self._row_of[:self._cap_phys]
+                self._row_of = row_of
+            else:
+                lat = torch.zeros((new_cap, _lib.LATENT_ROW_FLOATS), dtype=torch.float32, device=dev)   # 128-byte rows, columns 29..31 stay zero
+                if self._cap_phys:
+                    lat[:self._cap_phys] = self._latent
+                self._latent = lat
+                self._row_cap = new_cap
             self._cap_phys = new_cap
             self._persist = torch.zeros(self._L.dif_integrate_persist_bytes(self._n_cells, new_cap), dtype=torch.uint8, device=dev)
+
+    def _grow_rows(self, new_rows: int):
+        """Sharded map: grow the local latent table (rows = PLIVoxes this rank owns or keeps in its halo)."""
+        lat = torch.zeros((new_rows, _lib.LATENT_ROW_FLOATS), dtype=torch.float32, device=self.device)
+        if self._latent is not None:
+            lat[:self._latent.size(0)] = self._latent
+        self._latent, self._row_cap = lat, new_rows
 
     def _retire_stats(self, block: bool):
         """Consume finished integrate results (all of them when block=True).  Nothing is ever raised from the non-blocking path:
@@ -217,7 +247,8 @@ class DenseIndexedMap:
         self._n_occ_host = st[_lib.STAT_N_OCCUPIED]
         self.last_integrate_stats = dict(n_kept=st[0], n_new=st[1], n_samples=st[2], n_updated=st[3], n_occupied=st[4],
                                          flags=st[5], n_focused=st[6])
-        if st[_lib.STAT_FLAGS] & 2:
+        self._n_rows_host = st[_lib.STAT_N_ROWS]
+        if st[_lib.STAT_FLAGS] & 6:
             self._pending_error = RuntimeError("PLIVox capacity exhausted inside dif_integrate (internal sizing error)")
         if st[_lib.STAT_FLAGS] & 1:
             self.n_frames_with_dropped_points += 1
@@ -233,6 +264,8 @@ class DenseIndexedMap:
         self._indexer.fill_(-1)
         self._latent.zero_(); self._pos.fill_(-1); self._obs.zero_(); self._optimized.zero_(); self._dirty.zero_()
         self._n_occ_dev.zero_()
+        if self._row_of is not None:
+            self._row_of.fill_(-1); self._n_rows_dev.zero_()
         self._n_occ_host = 0
         self._pending_error = None
         self._reset_epoch += 1
@@ -293,7 +326,7 @@ class DenseIndexedMap:
         self.n_occupied = n
 
     def _view(self) -> _lib.MapView:
-        key = (self._indexer.data_ptr(), self._latent.data_ptr(), self._cap_phys, self._shard_rank, self._shard_world,
+        key = (self._indexer.data_ptr(), self._latent.data_ptr(), self._cap_phys, self._shard_rank, self._shard_world, self._row_cap,
                self._xchg.data_ptr() if self._xchg is not None else 0)
         if self._view_key == key:
             return self._view_obj
@@ -312,6 +345,10 @@ class DenseIndexedMap:
         v.shard_rank, v.shard_world = self._shard_rank, self._shard_world
         v.xchg_slots = self._xchg.data_ptr() if self._xchg is not None else None
         v.latent_stride = _lib.LATENT_ROW_FLOATS
+        v.shard_block_log2 = self._shard_k
+        v.row_of_slot = self._row_of.data_ptr() if self._row_of is not None else None
+        v.n_rows = self._n_rows_dev.data_ptr() if self._n_rows_dev is not None else None
+        v.row_capacity = self._row_cap
         self._view_key, self._view_obj = key, v
         return v
 
@@ -353,6 +390,12 @@ class DenseIndexedMap:
                 self._retire_stats(block=True)
                 if self._n_occ_host + worst > self._cap_phys:
                     self._grow(_next_pow2(self._n_occ_host + worst))
+            if self._row_of is not None:                     # sharded map: the local latent table follows the same worst-case rule
+                pending = worst * (len(self._stats_inflight) + 1)
+                if getattr(self, "_n_rows_host", 0) + pending > self._row_cap:
+                    self._retire_stats(block=True)
+                    if self._n_rows_host + worst > self._row_cap:
+                        self._grow_rows(max(2 * self._row_cap, self._n_rows_host + 2 * worst))
             if n > self._scratch_points:
                 self._scratch_points = max(n, 1 << 15)
                 self._scratch = torch.empty(self._L.dif_integrate_scratch_bytes(self._scratch_points), dtype=torch.uint8, device=self.device)

@@ -75,14 +75,19 @@ typedef struct dif_map_view {
     float    encoder_count_th;   /* :34 */
     /* -- hash-sharded map (new: the reference is single-GPU).  shard_world <= 1: unsharded.  Integer state is
      * replicated (every rank runs the same index kernels on the same frame); the encoder MLP + latent fusion of a PLIVox run
-     * only on owner(cell) = mix64(linear id) % shard_world.  After dif_integrate, xchg_slots[0 .. stats[DIF_STAT_N_XCHG]) lists
-     * the slots whose latent rows this rank owns and changed: the caller all-gathers (slot, row) pairs and writes them back. */
+     * only on its owner.  After dif_integrate, xchg_slots[0 .. stats[DIF_STAT_N_XCHG]) lists the slots whose latent rows this
+     * rank owns and changed: dif_shard_pack sends the boundary ones to the ranks that keep them in their halo. */
     int32_t  shard_rank, shard_world;
     int32_t* xchg_slots;         /* [>= min(8*n_points, capacity)] or NULL */
     /* floats between consecutive rows of latent_vecs: 29 = the reference's packed rows, 32 = rows padded to 128 bytes (16-byte
      * aligned: the gather kernels then fetch a row with 8 vector loads instead of 29 scalar ones; the Python mirror stores the
      * table this way and exposes the reference's (capacity, 29) tensor as a strided view).  0 is read as 29. */
     int32_t  latent_stride;
+    /* -- sharded storage (see "hash-sharded map" below).  row_of_slot == NULL: latent row of slot s is row s (unsharded map). */
+    int32_t  shard_block_log2;   /* super-block edge = 2^k cells (ownership and halo granularity); 0 = per-cell ownership */
+    int32_t* row_of_slot;        /* [capacity] slot -> row of latent_vecs on THIS rank, -1 = not stored here (caller initialises to -1) */
+    int32_t* n_rows;             /* device scalar: rows of latent_vecs in use on this rank */
+    int64_t  row_capacity;       /* rows latent_vecs can hold on this rank */
 } dif_map_view;
 
 /* ---- integrate_keyframe  (system/map.py:340-452; SURVEY rows a-2 .. a-6) -----------------------------
@@ -97,9 +102,10 @@ enum {
     DIF_STAT_N_SAMPLES = 2,      /* encoder samples gathered (map.py:434)                         */
     DIF_STAT_N_UPDATED = 3,      /* PLIVoxes fused (len(surface_blatent_mapping), map.py:437)     */
     DIF_STAT_N_OCCUPIED = 4,     /* n_occupied after the call                                     */
-    DIF_STAT_FLAGS = 5,          /* bit0: a point fell outside the grid (dropped); bit1: capacity exhausted */
+    DIF_STAT_FLAGS = 5,          /* bit0: a point fell outside the grid (dropped); bit1: capacity exhausted; bit2: row_capacity exhausted (sharded) */
     DIF_STAT_N_FOCUSED = 6,      /* points passing the focus mask (map.py:389-397)                */
     DIF_STAT_N_XCHG = 7,         /* sharded map: owned PLIVoxes fused by this call (length of xchg_slots) */
+    DIF_STAT_N_ROWS = 9,         /* sharded map: latent rows in use on this rank after the call (== n_occupied when unsharded) */
     DIF_STAT_SEQ = 8,            /* frame->seq echoed back (0 without a frame block): tells a lagging reader which frame the counters belong to */
     DIF_STAT_COUNT = 12
 };
@@ -262,19 +268,35 @@ uint64_t dif_launch_count(int reset);
  * (development aid used by tools/tc_timing.py). */
 int dif_debug_tc_timing(void* dev_buf);
 
-/* ---- hash-sharded map: the per-frame latent exchange (new; the reference is single-GPU) ---------------------------------------
- * Each rank packs the PLIVoxes it owns and fused this frame (map->xchg_slots[0 .. *n_xchg_dev), written by dif_integrate) into
- * send_buf = [1 + cap_rows][32] floats (row 0: header, word 0 = row count; row 1+i: slot bits, 29 latents, 2 pad words); ONE NCCL
- * all-gather of dif_shard_xchg_bytes(cap_rows) per rank moves them (torch.distributed.all_gather_into_tensor); dif_shard_unpack
- * writes the rows of all other ranks into map->latent_vecs.  No host synchronisation: a rank publishing more than cap_rows rows
- * raises *overflow_dev to its row count (atomicMax; checked lazily by the host, which then grows cap_rows past it and re-synchronises). */
-size_t dif_shard_xchg_bytes(int64_t cap_rows);
+/* ---- hash-sharded map (new; the reference is single-GPU.  SURVEY 8e, BASELINE configs[4]) -----------------------------------------
+ * Ownership: owner(cell) = splitmix64(id of the cell's super-block) % shard_world, super-block = (2^shard_block_log2)^3 cells
+ * (default 16^3).  Integer state (indexer, slot numbering, latent_vecs_pos, voxel_obs_count) is replicated: every rank runs the same
+ * index kernels on the same frame.  The floating-point payload is sharded: a rank stores latent rows only for the PLIVoxes it owns
+ * plus a one-cell halo around its super-blocks (the 26-neighbourhood the marching-cubes blend of an owned PLIVox reads,
+ * mc_interp_kernel.cu:103-181), addressed through row_of_slot; the encoder MLP and the fusion of a PLIVox run on its owner only.
+ * Per frame ONE exchange: the owner of a row that another rank keeps in its halo (a BOUNDARY row: the PLIVox touches a face, edge
+ * or corner of its super-block) sends it to exactly those ranks.
+ *   dif_shard_pack   : map->xchg_slots[0 .. *n_xchg_dev) (owned rows fused this frame, written by dif_integrate) -> send_buf =
+ *                      [world][1 + cap_rows][32] floats; segment d is what rank d receives.  Segment row 0 = header: word 0 = rows for
+ *                      d (may exceed cap_rows: the excess is dropped and reported), word 1 = the largest per-destination count of
+ *                      this sender; row 1+i: slot (int32 bits), 29 latents, 2 pad words.
+ *   one all-to-all   : equal splits of dif_shard_xchg_bytes(cap_rows, 1) bytes (torch.distributed.all_to_all_single).
+ *   dif_shard_unpack : recv_buf [world][1 + cap_rows][32] -> the halo rows of this rank.  *overflow_dev = max over senders of header
+ *                      word 1 if it exceeds cap_rows - the same value on every rank (each receives every sender's header), so the
+ *                      host's lazy recovery (grow + re-publish) is a collective decision without a collective.
+ * No host synchronisation anywhere; sizes never leave the device.
+ *   dif_shard_select_points: the tracker's points whose PLIVox this rank owns, compacted (camera frame, order not preserved) into
+ *                      out_obs, with their count and the poses in *out_frame_dev: dif_icp_linearize(out_obs, n, NULL, out_frame_dev)
+ *                      then linearises this rank's share; the caller all-reduces the 44 doubles. */
+size_t dif_shard_xchg_bytes(int64_t cap_rows, int world);
 int dif_shard_pack(const dif_map_view* map, const int32_t* n_xchg_dev, int64_t cap_rows, float* send_buf, void* stream);
-int dif_shard_unpack(const dif_map_view* map, const float* gathered /*[world][1 + cap_rows][32]*/, int world, int64_t cap_rows,
+int dif_shard_unpack(const dif_map_view* map, const float* recv_buf /*[world][1 + cap_rows][32]*/, int64_t cap_rows,
                      int32_t* overflow_dev, void* stream);
+int dif_shard_select_points(const dif_map_view* map, const float* obs_xyz /*[n][3] camera frame*/, int64_t n, const float* pose_host /*[24]*/,
+                            float* out_obs /*[n][3]*/, dif_frame_params* out_frame_dev, void* stream);
 
-/* owner rank of a PLIVox in a hash-sharded map: splitmix64(linear id) % world (host mirror of the device function). */
-int dif_shard_owner(int64_t linear_id, int world);
+/* owner rank of a PLIVox (host mirror of the device function): linear id -> super-block -> splitmix64 % world. */
+int dif_shard_owner(int64_t linear_id, int nx, int ny, int nz, int block_log2, int world);
 
 int dif_abi_version(void);
 const char* dif_last_error(void);        /* thread-local text of the last DIF_E_LAUNCH */

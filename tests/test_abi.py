@@ -43,7 +43,8 @@ def test_struct_layout_matches_header():
     from difusion_b200 import _lib
     import ctypes
     # 6 pointers + int64 + 3 int32 + 3 float + float + int32 + 2 float + 2 int32 + pointer = 48 + 8 + 12 + 12 + 4 + 4 + 8 + 8 + 8 = 112
-    assert ctypes.sizeof(_lib.MapView) == 120 and _lib.MapView.xchg_slots.offset == 104 and _lib.MapView.latent_stride.offset == 112
+    assert ctypes.sizeof(_lib.MapView) == 144 and _lib.MapView.xchg_slots.offset == 104 and _lib.MapView.latent_stride.offset == 112
+    assert _lib.MapView.shard_block_log2.offset == 116 and _lib.MapView.row_of_slot.offset == 120 and _lib.MapView.row_capacity.offset == 136
     assert _lib.MapView.capacity.offset == 48 and _lib.MapView.nx.offset == 56 and _lib.MapView.bound_min.offset == 68
 
 
