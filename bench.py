@@ -260,6 +260,97 @@ def extra_decoder_sweep(torch, dev, L, _lib, net_util, model, table, n_rows, flu
     return sweep
 
 
+def extra_config5(torch, dist, dev, model, rank, world, extent, n_frames, flush):
+    """BASELINE configs[4] / SURVEY 8(e): ONE stream against a ~1 M-PLIVox map (scene S3: 50 m x 50 m height field, 5 cm PLIVoxes,
+    1000 x 1000 x 40 dense index) hash-sharded over the `world` ranks (world == 1: the same stream on the unsharded map).  The map is
+    built with bulk integrate_keyframe calls over the terrain, then `n_frames` S1-sized views are tracked + integrated:
+    step = ICP linearisation of the rank's owned points + all-reduce of 44 doubles, integrate_keyframe (index kernels replicated,
+    encoder + fusion on the owner), ONE all-to-all of the boundary latent rows.  Device time per step (CUDA events), max over ranks."""
+    from difusion_b200 import synthetic as S, shard
+    from difusion_b200.system.map import DenseIndexedMap
+    sc = S.scene_S3(extent=extent)
+    t_build0 = time.perf_counter()
+    if world > 1:
+        group = shard.ShardGroup()
+        m = shard.make_sharded_map(model, sc.map_args(), 29, dev, group, initial_capacity=1 << 22, initial_rows=1 << 19)
+    else:
+        m = DenseIndexedMap(model, sc.map_args(), 29, dev, initial_capacity=1 << 22)
+    n_pts_build = 0
+    for p, n in S.s3_terrain_points(extent=extent, rows_per_batch=100):
+        m.integrate_keyframe(torch.from_numpy(p).to(dev), torch.from_numpy(n).to(dev))
+        n_pts_build += p.shape[0]
+    n_occ = m.n_occupied
+    torch.cuda.synchronize(dev)
+    build_s = time.perf_counter() - t_build0
+    observed = int((m._obs[:n_occ] > 0).sum().item())
+    views = [S.s3_view(f, extent=extent, n_frames=max(n_frames, 8)) for f in range(n_frames + 3)]
+    d_views = []
+    for pc, nc, R, t in views:
+        xw, nw = S.to_world(pc, nc, R, t)
+        d_views.append((torch.from_numpy(pc).to(dev), torch.from_numpy(xw).to(dev), torch.from_numpy(nw).to(dev), R, t))
+
+    def step(f):
+        pc, xw, nw, R, t = d_views[f]
+        out = m.icp_linearize(pc, R, t, np.eye(3), np.zeros(3), huber_k=5.0, want_grad=True)
+        m.integrate_keyframe(xw, nw)
+        return out
+    for f in range(3):                                   # warm-up (also grows the exchange buffers if needed)
+        step(f)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(n_frames)]
+    last = None
+    for f in range(n_frames):
+        flush.zero_()
+        ev[f][0].record()
+        last = step(3 + f)
+        ev[f][1].record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    ms = float(sum(e[0].elapsed_time(e[1]) for e in ev))
+    res = {"n_gpus": world, "plivoxes_allocated": n_occ, "plivoxes_observed": observed, "grid": m.n_xyz, "frames": n_frames,
+           "points_per_frame": int(np.mean([v[0].shape[0] for v in views[3:]])), "build_points": n_pts_build, "build_seconds": build_s,
+           "icp_valid_points_last_frame": float(last[43].item())}
+    if world > 1:
+        tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+        rows = torch.tensor([m.n_rows], dtype=torch.int64, device=dev)
+        all_rows = [torch.zeros_like(rows) for _ in range(world)]
+        dist.all_gather(all_rows, rows)
+        ex = m.last_exchange
+        # the collective alone: the same all-to-all on the same buffers, 20 back-to-back launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(3):
+            m.shard.all_to_all_fixed(m._xsend, m._xrecv)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(20):
+            m.shard.all_to_all_fixed(m._xsend, m._xrecv)
+        e1.record(); torch.cuda.synchronize(dev)
+        a2a_us = 1e3 * e0.elapsed_time(e1) / 20
+        e0.record()
+        junk = torch.zeros(44, dtype=torch.float64, device=dev)
+        for _ in range(20):
+            dist.all_reduce(junk)
+        e1.record(); torch.cuda.synchronize(dev)
+        ar_us = 1e3 * e0.elapsed_time(e1) / 20
+        rows_l = [int(r.item()) for r in all_rows]
+        res.update({"latent_rows_per_rank": rows_l, "latent_bytes_per_rank_max": 128 * max(rows_l), "latent_bytes_unsharded": 128 * n_occ,
+                    "rows_fraction_max": max(rows_l) / max(n_occ, 1), "super_block": "16^3 cells",
+                    "exchange_last_frame": {"boundary_rows_sent_rank0": ex["rows_sent"], "boundary_rows_received_rank0": ex["rows_received"],
+                                            "buffer_bytes_per_rank": ex["bytes_per_rank"], "segment_rows": ex["capacity"]},
+                    "collectives_per_frame": "1 all_to_all_single (boundary rows, fixed-size segments) + 1 all_reduce of 44 doubles (ICP)",
+                    "all_to_all_us": a2a_us, "all_reduce_44_us": ar_us,
+                    "limiting_collective": "all_to_all_single" if a2a_us >= ar_us else "all_reduce"})
+    res.update({"frames_per_s": n_frames / (ms * 1e-3), "ms_per_frame": ms / n_frames})
+    del m
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -271,6 +362,9 @@ def main():
     ap.add_argument("--no-sweep", action="store_true", help="skip the decoder batch sweep (config 3) extras")
     ap.add_argument("--no-full-loop", action="store_true", help="skip the full track_camera + integrate + mesh loop extra")
     ap.add_argument("--no-graph", action="store_true", help="launch the frame's kernels directly instead of replaying the captured CUDA graph")
+    ap.add_argument("--no-config5", action="store_true", help="skip the sharded 1 M-PLIVox stream extra (BASELINE configs[4])")
+    ap.add_argument("--config5-extent", type=float, default=50.0, help="side of the S3 height field in metres (50 -> ~1 M PLIVoxes)")
+    ap.add_argument("--config5-frames", type=int, default=24)
     ap.add_argument("--sharded", action="store_true", help="N>1: ONE stream on a hash-sharded map (strong scaling) instead of N replicas")
     a = ap.parse_args()
     K, Wm = a.steps, max(a.warmup, 0)
@@ -436,6 +530,12 @@ def main():
         tt = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         total_ms, e2e_ms = tt.tolist()
+    config5 = {}
+    if not a.no_config5:
+        try:
+            config5 = extra_config5(torch, dist, dev, model, rank, world, a.config5_extent, a.config5_frames, flush)
+        except Exception as e:                                   # (every rank raises or none: the inputs are identical)
+            config5 = {"error": f"{type(e).__name__}: {e}"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -490,7 +590,8 @@ def main():
            f"one CUDA-graph replay per step ({launches_per_pass} kernels per {K}-step pass inside the graphs, counted in the direct-launch pass)",
            "roofline": roofline, "cpu_baseline": cpu,
            "same_prefix": {"frames": ns, "gpu_frames_per_s": ns / (gpu_prefix_ms * 1e-3), "cpu_frames_per_s": ns / cpu_sec},
-           "map": {"n_occupied": n_occ, "last_integrate": stats_dev}, "decoder_sweep": sweep, "full_loop": full_loop}
+           "map": {"n_occupied": n_occ, "last_integrate": stats_dev}, "decoder_sweep": sweep, "full_loop": full_loop,
+           "config5_sharded_stream": config5}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

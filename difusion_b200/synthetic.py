@@ -191,3 +191,60 @@ def render_rgbd(scene: Scene, R: np.ndarray, t: np.ndarray, step: int = 1, noise
     rgb = np.clip(rgb, 0.0, 1.0)
     rgb[np.isnan(depth)] = 0.0
     return rgb.astype(np.float32), depth
+
+
+# ---- S3 (BASELINE configs[4]): a 50 m x 50 m height field at 5 cm PLIVoxes -> ~1 M active PLIVoxes ---------------------
+# z = sum of sines (amplitude < 0.6 m, wavelengths 3-11 m), dense index 1000 x 1000 x 40 = 40 M cells.  Two generators:
+#   * s3_terrain_points: the whole surface as (points, normals) batches, to BUILD the map (bulk integrate_keyframe calls);
+#   * s3_view: one S1-sized frame (a 320 x 240 sample pattern over a ~4 m x 3 m footprint seen from above, 2 cm box filter
+#     -> ~30 k points) at a position that moves along a Lissajous path, to STREAM against the built map.
+S3_EXTENT = 50.0
+
+
+def scene_S3(voxel_size: float = 0.05, extent: float = S3_EXTENT) -> Scene:
+    return Scene("S3", [0.0, 0.0, -1.0], [extent, extent, 1.0], voxel_size, 2, 4.0, room=None, extra={"extent": extent})
+
+
+def s3_height(x, y):
+    return (0.22 * np.sin(2 * np.pi * x / 7.0) * np.cos(2 * np.pi * y / 11.0) + 0.18 * np.sin(2 * np.pi * (x + 0.5 * y) / 5.0)
+            + 0.12 * np.cos(2 * np.pi * (y - 0.3 * x) / 3.0))
+
+
+def s3_normal(x, y):
+    a, b, c = 2 * np.pi / 7.0, 2 * np.pi / 11.0, 2 * np.pi / 5.0
+    d = 2 * np.pi / 3.0
+    hx = 0.22 * a * np.cos(a * x) * np.cos(b * y) + 0.18 * c * np.cos(c * (x + 0.5 * y)) + 0.12 * d * 0.3 * np.sin(d * (y - 0.3 * x))
+    hy = -0.22 * b * np.sin(a * x) * np.sin(b * y) + 0.18 * c * 0.5 * np.cos(c * (x + 0.5 * y)) - 0.12 * d * np.sin(d * (y - 0.3 * x))
+    n = np.stack([-hx, -hy, np.ones_like(hx)], -1)
+    return n / np.linalg.norm(n, axis=-1, keepdims=True)
+
+
+def s3_terrain_points(extent: float = S3_EXTENT, spacing: float = 0.02, rows_per_batch: int = 400, seed: int = 0):
+    """Yields (xyz, normal) float32 batches covering [m, extent - m]^2 on a jittered `spacing` lattice (>= 4 points per 5 cm cell)."""
+    rng = np.random.default_rng(seed)
+    m = 0.2
+    xs = np.arange(m, extent - m, spacing)
+    for r0 in range(0, xs.shape[0], rows_per_batch):
+        x, y = np.meshgrid(xs[r0:r0 + rows_per_batch], xs, indexing="ij")
+        x = x + rng.uniform(-0.3, 0.3, x.shape) * spacing
+        y = y + rng.uniform(-0.3, 0.3, y.shape) * spacing
+        p = np.stack([x, y, s3_height(x, y)], -1).reshape(-1, 3).astype(np.float32)
+        yield p, s3_normal(x, y).reshape(-1, 3).astype(np.float32)
+
+
+def s3_view(frame: int, extent: float = S3_EXTENT, n_frames: int = 200):
+    """One frame against S3: returns (pc_cam, n_cam, R, t) like stream_frames().  The camera looks straight down from 3 m; its
+    320 x 240 sample pattern covers a 4 m x 3 m footprint (1.25 cm pitch), filtered to 2 cm as the tracker does."""
+    ph = 2 * np.pi * frame / n_frames
+    cx, cy = extent / 2 + 0.35 * extent * np.sin(ph), extent / 2 + 0.35 * extent * np.sin(2 * ph + 0.3)
+    u, v = np.meshgrid((np.arange(320) - 159.5) * 0.0125, (np.arange(240) - 119.5) * 0.0125)
+    x, y = cx + u, cy + v
+    pw = np.stack([x, y, s3_height(x, y)], -1).reshape(-1, 3)
+    nw = s3_normal(x, y).reshape(-1, 3)
+    R = np.array([[1.0, 0.0, 0.0], [0.0, -1.0, 0.0], [0.0, 0.0, -1.0]])          # camera z axis points down
+    t = np.array([cx, cy, 3.0])
+    pc = ((pw - t) @ R).astype(np.float32)                                        # world -> camera: R^T (p - t)
+    nc = (nw @ R).astype(np.float32)
+    pc, nc = box_filter(pc, nc, 0.02)
+    nc = nc / np.maximum(np.linalg.norm(nc, axis=1, keepdims=True), 1e-12)
+    return pc.astype(np.float32), nc.astype(np.float32), R, t

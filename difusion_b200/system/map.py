@@ -157,6 +157,7 @@ class DenseIndexedMap:
         self._stats_last = [0] * _lib.DIF_STAT_COUNT
         self._n_occ_host = 0
         self._pending_error = None
+        self._n_rows_host = 0
         self._reset_epoch = 0
         self.n_frames_with_dropped_points = 0
         # hash-sharded map (difusion_b200/shard.py): `shard` carries rank / world; the latent table then holds only the rows this
@@ -267,6 +268,7 @@ class DenseIndexedMap:
         if self._row_of is not None:
             self._row_of.fill_(-1); self._n_rows_dev.zero_()
         self._n_occ_host = 0
+        self._n_rows_host = 0
         self._pending_error = None
         self._reset_epoch += 1
         self.last_integrate_stats = None
@@ -392,7 +394,7 @@ class DenseIndexedMap:
                     self._grow(_next_pow2(self._n_occ_host + worst))
             if self._row_of is not None:                     # sharded map: the local latent table follows the same worst-case rule
                 pending = worst * (len(self._stats_inflight) + 1)
-                if getattr(self, "_n_rows_host", 0) + pending > self._row_cap:
+                if self._n_rows_host + pending > self._row_cap:
                     self._retire_stats(block=True)
                     if self._n_rows_host + worst > self._row_cap:
                         self._grow_rows(max(2 * self._row_cap, self._n_rows_host + 2 * worst))
