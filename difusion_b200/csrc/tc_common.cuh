@@ -180,6 +180,59 @@ __device__ __forceinline__ void issue_layer(uint32_t idesc, uint32_t wk_bytes, i
     }
 }
 
+// ---- second-generation pipeline helpers (decode_tc2.cuh, encode_tc.cu): in-place conversion, group hand-off ----------------------
+// issuer-side wait: no back-off - try_wait suspends the thread in hardware and wakes it ~60 cycles after the phase flips
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "WAITSPIN:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@!p bra WAITSPIN;\n\t}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+// ReLU + fp16 hi/lo split of a pair with the ReLU folded into the two conversions (cvt.*.relu): for x >= 0 this is split_pair
+// (hi = x truncated to 11 significant bits, lo = fp16(x - hi)); for x < 0 the truncated hi is <= 0 in magnitude order and
+// x - hi is <= 0, so both conversions clamp to +0 - the same result as splitting max(x, 0), with two FMNMX fewer per pair.
+__device__ __forceinline__ void relu_split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const float ah = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u), bh = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(bh), "f"(ah));          // (first source -> upper half)
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - bh), "f"(a - ah));
+}
+
+// 16 accumulator columns -> +bias, ReLU, hi/lo split -> the same 16 columns: [8 packed hi | 8 packed lo] = one K=16 A operand
+__device__ __forceinline__ void convert_inplace16(const uint32_t* v, const float* b, uint32_t col_addr) {
+    uint32_t o[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float4 bb = *reinterpret_cast<const float4*>(b + 4 * j);
+        relu_split_pair(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y, o[2 * j], o[8 + 2 * j]);
+        relu_split_pair(__uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w, o[2 * j + 1], o[8 + 2 * j + 1]);
+    }
+    tmem_st16(col_addr, o);
+}
+
+// one hand-off group: 2 K steps x 3 passes (hi*hi, lo*hi, hi*lo) of one layer; A chunk ks lives at a_base + 16 ks (hi) / + 8 (lo).
+// Everything but the bases is a compile-time constant: with run-time K-step indices every operand had to be moved into a uniform
+// register right before its UTCHMMA and the issuer needed ~80-100 cycles per MMA (measured: 400-600 cycles per 6-MMA group against
+// the 384 cycles the tensor pipe needs for them).
+template <int N, int KS0, int KS1, bool FIRST>
+__device__ __forceinline__ void issue_group(uint32_t acc, uint32_t a_base, uint64_t w_hi_d, uint64_t w_lo_d) {
+    constexpr uint32_t idesc = idesc_f16(N);
+    constexpr uint32_t step = (2 * N * 16) >> 4;                 // descriptor increment per K = 16 step
+    mma_ts(acc, a_base + 16 * KS0, w_hi_d + (uint64_t)(KS0 * step), idesc, FIRST ? 0u : 1u);
+    mma_ts(acc, a_base + 16 * KS1, w_hi_d + (uint64_t)(KS1 * step), idesc, 1u);
+    mma_ts(acc, a_base + 16 * KS0 + 8, w_hi_d + (uint64_t)(KS0 * step), idesc, 1u);
+    mma_ts(acc, a_base + 16 * KS1 + 8, w_hi_d + (uint64_t)(KS1 * step), idesc, 1u);
+    mma_ts(acc, a_base + 16 * KS0, w_lo_d + (uint64_t)(KS0 * step), idesc, 1u);
+    mma_ts(acc, a_base + 16 * KS1, w_lo_d + (uint64_t)(KS1 * step), idesc, 1u);
+}
+
 // Optional phase timing (tools/tc_timing.py): cycles spent per role and phase, summed per warp into a global buffer.
 __device__ unsigned long long* g_tc_timing = nullptr;       // [gridDim][20 warps][8 counters]
 #define TC_T0() const long long _t0 = timing ? clock64() : 0
