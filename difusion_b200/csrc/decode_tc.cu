@@ -324,6 +324,13 @@ __global__ void prepare_tc_kernel(const float* __restrict__ P, unsigned char* __
         }
     }
     if (tid == 0) *reinterpret_cast<int*>(image + IMAGE_B) = head_slot;
+    if (tid < 64) {                                   // staging copy of c_head_g3 (copied into the constant bank by the host right after)
+        uint32_t* g3 = reinterpret_cast<uint32_t*>(image + IMAGE_B + 16);
+        const float wa = G3_SCALE * P[DecW::w4 + 2 * tid], wb = G3_SCALE * P[DecW::w4 + 2 * tid + 1];
+        split_pair(wa, wb, g3[tid], g3[64 + tid]);
+        const __half2 rn = __floats2half2_rn(wa, wb);
+        g3[128 + tid] = *reinterpret_cast<const uint32_t*>(&rn);
+    }
     float* b = reinterpret_cast<float*>(image + OFF_BIAS);
     for (int i = tid; i < 128; i += nth) {
         b[i] = P[DecW::b0 + i]; b[128 + i] = P[DecW::b1 + i]; b[352 + i] = P[DecW::b3 + i];
@@ -341,7 +348,7 @@ __global__ void prepare_tc_kernel(const float* __restrict__ P, unsigned char* __
 namespace dif {
 
 
-size_t decoder_tc_image_bytes() { return tc::IMAGE_B + 16; }
+size_t decoder_tc_image_bytes() { return tc::IMAGE_B + 16 + sizeof(tc::c_head_g3[0]); }
 
 int set_tc_timing_buffer(unsigned long long* dev_buf) {
     return cudaMemcpyToSymbol(tc::g_tc_timing, &dev_buf, sizeof(dev_buf)) == cudaSuccess ? DIF_OK : DIF_E_LAUNCH;
@@ -355,6 +362,8 @@ int prepare_decoder_tc(const float* P, unsigned char* image, cudaStream_t st) {
                                 cudaMemcpyDeviceToDevice, st) != cudaSuccess) return check_launch("cudaMemcpyToSymbolAsync(c_head_w)");
     tc::prepare_tc_kernel<<<64, 256, 0, st>>>(P, image, slot);
     DIF_COUNT_LAUNCH(1);
+    if (cudaMemcpyToSymbolAsync(tc::c_head_g3, image + tc::IMAGE_B + 16, sizeof(tc::c_head_g3[0]), (size_t)slot * sizeof(tc::c_head_g3[0]),
+                                cudaMemcpyDeviceToDevice, st) != cudaSuccess) return check_launch("cudaMemcpyToSymbolAsync(c_head_g3)");
     return check_launch("prepare_tc_kernel");
 }
 

@@ -157,6 +157,8 @@ int icp_launch(const dif_map_view* map, const void* decoder_prepared, const floa
     Carver c(scratch);
     float* partials = c.take<float>((size_t)DIF_NUM_SMS * 3 * ICP_VALS);
     unsigned int* counter = c.take<unsigned int>(1);
+    unsigned long long* ll = c.take<unsigned long long>((size_t)DIF_NUM_SMS * 64);
+    unsigned int* epoch = c.take<unsigned int>(1);
     // `scratch` is zero-filled once by the caller; both kernels leave the counter zeroed again when they finish and write
     // every partial row they later read, so no memset is needed per call.
     // tensor-core path (decoder forward + backward on tcgen05) for frames worth of points; DIF_ICP_PATH=simt forces fp32 SIMT
@@ -164,7 +166,7 @@ int icp_launch(const dif_map_view* map, const void* decoder_prepared, const floa
     const bool force_simt = path_env && path_env[0] == 's';
     if (!force_simt && n >= 2048) {
         static_assert((size_t)DIF_NUM_SMS * 32 * sizeof(double) <= (size_t)DIF_NUM_SMS * 3 * ICP_VALS * sizeof(float), "partials region");
-        IcpTcArgs a{m, obs_xyz, obs_stride, (int)n, frame_dev, p, huber_k, want_grad, reinterpret_cast<double*>(partials), counter, out_dev};
+        IcpTcArgs a{m, obs_xyz, obs_stride, (int)n, frame_dev, p, huber_k, want_grad, reinterpret_cast<double*>(partials), counter, out_dev, ll, epoch};
         return launch_icp_tc(decoder_prepared, a, st);
     }
     const int64_t n_tiles = (n + MLP_T - 1) / MLP_T;
@@ -188,7 +190,7 @@ extern "C" {
 
 size_t dif_icp_scratch_bytes(int64_t n) {
     (void)n;
-    return align_up((size_t)DIF_NUM_SMS * 3 * ICP_VALS * sizeof(float)) + 256;
+    return align_up((size_t)DIF_NUM_SMS * 3 * ICP_VALS * sizeof(float)) + 256 + align_up((size_t)DIF_NUM_SMS * 64 * sizeof(unsigned long long)) + 256;
 }
 
 int dif_icp_linearize(const dif_map_view* map, const void* decoder_prepared, const float* obs_xyz, int64_t n, const float* pose_host,

@@ -40,6 +40,8 @@ struct IcpTcArgs {
     double* partials;             // [grid][32] per-CTA fp64 sums: 21 upper-triangular H, 6 g, energy, M (every row fully written)
     unsigned int* done_counter;   // zero on entry, left zero on exit
     double* out;                  // [44]
+    unsigned long long* ll;       // [grid][32][2] epoch-tagged words of the per-CTA rows (icp_tc2_kernel)
+    unsigned int* epoch;          // epoch of the last completed launch on this scratch
 };
 
 int launch_icp_tc(const void* decoder_prepared, const IcpTcArgs& a, cudaStream_t st);

@@ -448,15 +448,25 @@ __global__ void __launch_bounds__(THREADS, 1) icp_tc_kernel(const unsigned char*
 
 }  // namespace tc
 
+}  // namespace dif
+#include "icp_tc2.cuh"
+namespace dif {
+
 int launch_icp_tc(const void* decoder_prepared, const IcpTcArgs& a, cudaStream_t st) {
     const float* P = (const float*)decoder_prepared;
     const unsigned char* image = (const unsigned char*)decoder_prepared + (size_t)DecW::FP32_END * sizeof(float);
     const int64_t n_tiles = ((int64_t)a.n + tc::TILE - 1) / tc::TILE;
     const int grid = (int)(n_tiles < DIF_NUM_SMS ? (n_tiles > 0 ? n_tiles : 1) : DIF_NUM_SMS);
     static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(tc::icp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::ICP_SMEM_B); attr_set = true; }
+    if (!attr_set) {
+        cudaFuncSetAttribute(tc::icp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::ICP_SMEM_B);
+        cudaFuncSetAttribute(tc::icp_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::I2_SMEM_B);
+        attr_set = true;
+    }
+    const char* v = getenv("DIF_ICP_V");                     // "1": the first pipeline (separate accumulator / operand regions), kept for A/B timing
     prof_begin(DIF_PROF_ICP, st);
-    launch_pdl(tc::icp_tc_kernel, grid, tc::THREADS, tc::ICP_SMEM_B, st, image, P, a);
+    if (v && v[0] == '1') launch_pdl(tc::icp_tc_kernel, grid, tc::THREADS, tc::ICP_SMEM_B, st, image, P, a);
+    else launch_pdl(tc::icp_tc2_kernel, grid, tc::I2_THREADS, tc::I2_SMEM_B, st, image, P, a);
     prof_end(DIF_PROF_ICP, st);
     DIF_COUNT_LAUNCH(1);
     return check_launch("icp_tc_kernel");

@@ -36,6 +36,11 @@ enum { BAR_W = 0, BAR_X0 = 1, BAR_X1 = 2, BAR_ACC0 = 3, BAR_ACC1 = 4, BAR_A0 = 5
 // products use them as FFMA operands.  A prepared decoder records its slot in the word that follows its weight image.
 constexpr int HEAD_SLOTS = 8;
 __constant__ float c_head_w[HEAD_SLOTS][2][128];
+// Backward seed of the ICP kernel: G3_SCALE * w4 as fp16 pair words (pair p = columns 2p, 2p+1): [0,64) hi (truncated to 11
+// bits), [64,128) lo, [128,192) rounded to nearest (single-pass variant).  The power-of-two scale keeps the small gradients of
+// the deeper backward stages inside fp16's normal range; it is divided out exactly with the per-row seed.
+constexpr float G3_SCALE = 16.f;
+__constant__ uint32_t c_head_g3[HEAD_SLOTS][192];
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

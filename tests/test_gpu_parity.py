@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN, close, fixture_args, frac_off
+from conftest import GOLDEN, close, fixture_args, frac_off, hg_errors
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
@@ -121,8 +121,12 @@ def test_map_against_reference_fixture(golden, model, dev, name):
         delta = Isometry(q=Rotation(matrix=fx["hg.R_delta"]), t=fx["hg.t_delta"])
         H, g, E = trk.compute_sdf_Hg(0, last, delta, _t(fx["hg.obs"], dev), no_grad=False)
         assert H.shape == (6, 6) and H.dtype == np.float64 and np.allclose(H, H.T)
-        assert np.abs(H - fx["hg.H"]).max() <= 2e-4 * np.abs(fx["hg.H"]).max()
-        assert np.abs(g - fx["hg.g"]).max() <= 2e-4 * np.abs(fx["hg.g"]).max()
+        # element-wise at the Gram scale (conftest.hg_errors), and far inside the old max-norm bound
+        gram, strict = hg_errors(H, g, E, fx["hg.H"], fx["hg.g"], float(fx["hg.E"]))
+        print(f"[{name}] H,g vs the executed reference: err/tol {gram:.3f} at the Gram scale, {strict:.2f} at |b| (cancelled off-diagonals)")
+        assert gram <= 1.0
+        assert np.abs(H - fx["hg.H"]).max() <= 1e-4 * np.abs(fx["hg.H"]).max()        # (the CPU restatement itself: 1e-4, tests/test_oracle_golden.py)
+        assert np.abs(g - fx["hg.g"]).max() <= 1e-4 * np.abs(fx["hg.g"]).max()
         assert close(E, float(fx["hg.E"]), TOL)
         H2, g2, E2 = trk.compute_sdf_Hg(-1, last, delta, _t(fx["hg.obs"], dev), no_grad=True)
         assert H2 is None and g2 is None and close(E2, float(fx["hg.E_nograd"]), TOL)
@@ -308,6 +312,31 @@ def test_large_batch_properties(model, dev):
         assert float((fd - ga[:, c]).abs().median()) < 2e-3
 
 
+def test_decoder_config3_full_size(model, dev):
+    """BASELINE config 3 at its full size (2^22 samples): a seeded 32 k sub-sample against the oracle (chunked), the head and the
+    ragged tail of the batch bit-identical to the same samples decoded in a small batch (tile position must not matter)."""
+    from difusion_b200.network import utility as net_util
+    from oracle import dif_oracle as O
+    W = O.load_weights_npz(GOLDEN / "weights.npz")
+    g = torch.Generator().manual_seed(11)
+    n = (1 << 22) + 77                                          # ragged last tile
+    table = torch.randn(23000, 29, generator=g) * 0.2
+    rows = torch.randint(0, 23000, (n,), generator=g)
+    xyz = torch.rand(n, 3, generator=g) * 2 - 1
+    lat_d, xyz_d = table.to(dev)[rows.to(dev)], xyz.to(dev)
+    sdf, std = net_util.forward_model(model.decoder, latent_input=lat_d, xyz_input=xyz_d)
+    assert sdf.shape == (n, 1) and bool(torch.isfinite(sdf).all()) and bool(torch.isfinite(std).all())
+    pick = torch.randperm(n, generator=g)[:32768]
+    pick[:128] = torch.arange(n - 128, n)                       # the ragged tail is in the sample
+    for c in range(0, pick.numel(), 8192):
+        pc_ = pick[c:c + 8192]
+        o_sdf, o_std = O.decoder_forward(W.dec, table[rows[pc_]], xyz[pc_])
+        assert close(sdf.cpu()[pc_, 0].numpy(), o_sdf.numpy(), TOL) and close(std.cpu()[pc_, 0].numpy(), o_std.numpy(), TOL)
+    pd = pick.to(dev)
+    s_small, u_small = net_util.forward_model(model.decoder, latent_input=lat_d[pd], xyz_input=xyz_d[pd])
+    assert torch.equal(s_small, sdf[pd]) and torch.equal(u_small, std[pd])
+
+
 def test_large_map_properties(model, dev):
     """BASELINE config-5 scale: a 1000 x 1000 x 40 = 40 M-cell dense index (320 MB), S1-sized views into a height field.
     The oracle cannot hold this in reasonable time, so the integer state is checked against an independent torch
@@ -419,7 +448,8 @@ def test_tensor_core_icp_matches_fp32_path(golden, model, dev, monkeypatch):
         n_simt = float(m.icp_linearize(obs, last.q.rotation_matrix, last.t, delta.q.rotation_matrix, delta.t)[43])
         monkeypatch.delenv("DIF_ICP_PATH", raising=False)
         assert n_tc == n_simt > 1000                              # identical valid sets (integer lookup path)
-        assert np.abs(H - H2).max() <= 2e-4 * np.abs(H2).max() and np.abs(g - g2).max() <= 2e-4 * np.abs(g2).max()
+        assert hg_errors(H, g, E, H2, g2, E2)[0] <= 1.0           # element-wise, Gram scale (conftest.hg_errors)
+        assert np.abs(H - H2).max() <= 5e-5 * np.abs(H2).max() and np.abs(g - g2).max() <= 5e-5 * np.abs(g2).max()
         assert close(E, E2, 1e-5) and close(E_ng, E2, 1e-5)
     # ragged sizes / single tile / one slot only
     for n in (2048, 2049, 4000):
@@ -428,7 +458,25 @@ def test_tensor_core_icp_matches_fp32_path(golden, model, dev, monkeypatch):
         monkeypatch.setenv("DIF_ICP_PATH", "simt")
         o2 = m.icp_linearize(obs[:n], last.q.rotation_matrix, last.t, delta.q.rotation_matrix, delta.t).cpu().numpy()
         monkeypatch.delenv("DIF_ICP_PATH", raising=False)
-        assert o[43] == o2[43] and np.abs(o[:36] - o2[:36]).max() <= 2e-4 * np.abs(o2[:36]).max() and close(o[42], o2[42], 1e-5)
+        assert o[43] == o2[43] and np.abs(o[:36] - o2[:36]).max() <= 5e-5 * np.abs(o2[:36]).max() and close(o[42], o2[42], 1e-5)
+    # many tiles per slot (producer warps, early F0 behind B0, barrier phases over 16 iterations), with and without gradients
+    big = obs.repeat(16, 1).contiguous()
+    delta = Isometry.from_twist(np.asarray([0.004, -0.003, 0.002, 0.003, -0.002, 0.001]))
+    n_one = float(m.icp_linearize(obs, last.q.rotation_matrix, last.t, delta.q.rotation_matrix, delta.t)[43])
+    for grad in (True, False):
+        o = m.icp_linearize(big, last.q.rotation_matrix, last.t, delta.q.rotation_matrix, delta.t, 5.0, grad).cpu().numpy()
+        monkeypatch.setenv("DIF_ICP_PATH", "simt")
+        o2 = m.icp_linearize(big, last.q.rotation_matrix, last.t, delta.q.rotation_matrix, delta.t, 5.0, grad).cpu().numpy()
+        monkeypatch.delenv("DIF_ICP_PATH", raising=False)
+        assert o[43] == o2[43] == 16 * n_one and close(o[42], o2[42], 1e-5)
+        if grad:
+            assert hg_errors(o[:36].reshape(6, 6), o[36:42], o[42], o2[:36].reshape(6, 6), o2[36:42], o2[42])[0] <= 1.0
+    # the first pipeline (DIF_ICP_V=1, kept for A/B timing) still agrees
+    monkeypatch.setenv("DIF_ICP_V", "1")
+    o1 = m.icp_linearize(obs, last.q.rotation_matrix, last.t, delta.q.rotation_matrix, delta.t).cpu().numpy()
+    monkeypatch.delenv("DIF_ICP_V", raising=False)
+    o = m.icp_linearize(obs, last.q.rotation_matrix, last.t, delta.q.rotation_matrix, delta.t).cpu().numpy()
+    assert o1[43] == o[43] and np.abs(o1[:42] - o[:42]).max() <= 5e-5 * np.abs(o[:42]).max()
     # the tensor-core kernel reduces through per-CTA partials in a fixed order: results are bit-reproducible run to run
     delta = Isometry.from_twist(np.asarray([0.004, -0.003, 0.002, 0.003, -0.002, 0.001]))
     runs = [m.icp_linearize(obs, last.q.rotation_matrix, last.t, delta.q.rotation_matrix, delta.t).cpu().numpy() for _ in range(4)]
