@@ -103,14 +103,18 @@ __global__ void write_counts_kernel(int32_t* counts, int32_t n_low, const int32_
 //   stage 2: the (R+1)^3 blended corner values, each computed once (the reference recomputes a corner in up to 8 sub-cube
 //            threads).  All 16 cube loads of a corner are issued before the first is consumed (no early exit between them),
 //            so a thread has 16 independent L2/HBM requests in flight instead of a chain of 8 round trips.
-//   stage 3: one thread per sub-cube: case lookup, edge vertices, block scan of the triangle counts, ONE atomicAdd per CTA to
-//            reserve output; triangles are staged in shared memory and written out as contiguous float streams (full sectors).
+//   stage 3: (a) one thread per sub-cube: case lookup, block scan of the candidate triangle counts -> work list; (b) one thread
+//            per candidate triangle: its three edge vertices, the max_std filter, compaction, ONE atomicAdd per chunk to reserve
+//            output; triangles are staged in shared memory and written out as contiguous float streams (full sectors).
 // Float arithmetic is written with explicit round-to-nearest intrinsics and explicit fmaf in exactly the places where nvcc
 // (-fmad=true) contracts the reference source (read off the reference's PTX; see oracle/mc_oracle.c header), so case indices
 // and vertices are bit-identical to the reference extension and to the scalar restatement in oracle/mc_oracle.c.
+#ifndef DIF_MC_PREFETCH
+#define DIF_MC_PREFETCH 1
+#endif
 constexpr int MC_THREADS = 128;
 constexpr int MC_MAX_R = 8;
-constexpr int MC_STAGE_TRIS = 160;             // triangles a CTA can stage per PLIVox pass (more -> direct global stores)
+constexpr int MC_STAGE_TRIS = MC_THREADS;      // triangles staged per chunk: one candidate triangle per thread
 
 struct McArgs {
     const int64_t* indexer; int nx, ny, nz; const int64_t* valid_blocks; int64_t n_valid; const int32_t* mapping; int64_t mapping_len;
@@ -138,20 +142,19 @@ __global__ void __launch_bounds__(MC_THREADS) marching_cubes_kernel(McArgs a) {
     __shared__ float c_sdf[NC], c_std[NC];
     __shared__ float t_wm[R1], t_wp[R1];                    // per-axis blend weights of corner position p (mc_interp_kernel.cu:47-58)
     __shared__ int t_om[R1], t_op[R1];                      // per-axis cube coordinate read from the "minus" / "plus" contributor
-    __shared__ uint16_t s_emask[256];
     __shared__ uint8_t s_ntri[256];
     __shared__ int8_t s_tri[256][16];
     __shared__ float st_tri[MC_STAGE_TRIS * 9];
     __shared__ float st_std[MC_STAGE_TRIS * 3];
+    __shared__ uint32_t s_work[MC_THREADS * 5];             // candidate triangles of one sub-cube pass: sub | t << 9 | case << 12
     __shared__ int warp_tot[MC_THREADS / 32];
     __shared__ int block_base;
     const int tid = threadIdx.x;
     const float sbs = __fdiv_rn(1.0f, (float)R);
     const float qnan = __int_as_float(0x7fc00000);
     const int dx8[8] = {0, 1, 1, 0, 0, 1, 1, 0}, dy8[8] = {0, 0, 1, 1, 0, 0, 1, 1}, dz8[8] = {0, 0, 0, 0, 1, 1, 1, 1};
-    const int e_a[12] = {0, 1, 2, 3, 4, 5, 6, 7, 0, 1, 2, 3}, e_b[12] = {1, 2, 3, 0, 5, 6, 7, 4, 4, 5, 6, 7};
 
-    for (int i = tid; i < 256; i += MC_THREADS) { s_emask[i] = dif_mc_edge_mask[i]; s_ntri[i] = dif_mc_tri_count[i]; }
+    for (int i = tid; i < 256; i += MC_THREADS) s_ntri[i] = dif_mc_tri_count[i];
     for (int i = tid; i < 256 * 16; i += MC_THREADS) s_tri[i >> 4][i & 15] = dif_mc_tri_edges[i >> 4][i & 15];
     if (tid < R1) {
         const float rmid = R / 2.0f, rf = (float)R, pf = (float)tid;
@@ -183,6 +186,17 @@ __global__ void __launch_bounds__(MC_THREADS) marching_cubes_kernel(McArgs a) {
             if (slot != -1 && slot < a.mapping_len) batch = a.mapping[slot];
         }
         nb2[buf][t] = batch;
+#if DIF_MC_PREFETCH
+        // The PLIVox's OWN cube pair is pulled into L2 as two dense bulk prefetches (UBLKPF) one round ahead of its use: the gathers
+        // below touch 12-24 bytes per 40-byte row, and when they are the first touch DRAM is read in sparse 64-byte pieces (ncu,
+        // round 1: 2.4x the cube bytes from DRAM, 9 of 32 bytes used per sector); neighbours then find whole cubes in L2.
+        if (t == 13 && batch >= 0) {
+            constexpr uint32_t CB = (uint32_t)(N3 * sizeof(float)) & ~15u;
+            const int64_t off = ((int64_t)batch * N3) & ~(int64_t)3;                       // 16-byte aligned start
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(a.cube_sdf + off), "r"(CB) : "memory");
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(a.cube_std + off), "r"(CB) : "memory");
+        }
+#endif
     };
 #ifndef DIF_MC_ORDER
 #define DIF_MC_ORDER 0                  // 0: grid-stride (CTAs sweep the sorted block list in lockstep windows)  1: one contiguous run per CTA
@@ -242,96 +256,81 @@ __global__ void __launch_bounds__(MC_THREADS) marching_cubes_kernel(McArgs a) {
         __syncthreads();
         const int bx = s_b2[buf][0], by = s_b2[buf][1], bz = s_b2[buf][2];
         for (int sub0 = 0; sub0 < R3; sub0 += MC_THREADS) {
+            // ---- 3a: one thread per sub-cube: case index and candidate triangle count; exclusive block scan -> work list of
+            //      (sub-cube, triangle, case) items.  Only ~10 % of the sub-cubes of a surface PLIVox cross the surface: generating
+            //      the triangles per sub-cube ran 12 predicated edge evaluations per warp for 3-4 active lanes.
             const int sub = sub0 + tid;
-            int n_tri = 0, type = 0;
-            float4 vert[12];
+            int nt = 0, type = 0;
             if (sub < R3) {
                 const int rx = sub / (R * R), ry = (sub / R) % R, rz = sub % R;
-                float v[8], sd[8]; bool bad = false;
+                bool bad = false;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const int c = ((rx + dx8[i]) * R1 + ry + dy8[i]) * R1 + rz + dz8[i];
-                    v[i] = c_sdf[c]; sd[i] = c_std[c];
-                    bad |= !(v[i] == v[i]);
-                    if (v[i] < 0.f) type |= 1 << i;
+                    const float v = c_sdf[((rx + dx8[i]) * R1 + ry + dy8[i]) * R1 + rz + dz8[i]];
+                    bad |= !(v == v);
+                    if (v < 0.f) type |= 1 << i;
                 }
-                const int emask = bad ? 0 : s_emask[type];
-                if (emask) {
-#pragma unroll
-                    for (int e = 0; e < 12; ++e) {
-                        if (emask & (1 << e)) {
-                            const int p = e_a[e], q = e_b[e];
-                            const float3 p1 = make_float3(__fmaf_rn((float)(rx + dx8[p]), sbs, (float)bx),
-                                                          __fmaf_rn((float)(ry + dy8[p]), sbs, (float)by),
-                                                          __fmaf_rn((float)(rz + dz8[p]), sbs, (float)bz));
-                            const float3 p2 = make_float3(__fmaf_rn((float)(rx + dx8[q]), sbs, (float)bx),
-                                                          __fmaf_rn((float)(ry + dy8[q]), sbs, (float)by),
-                                                          __fmaf_rn((float)(rz + dz8[q]), sbs, (float)bz));
-                            vert[e] = edge_vertex(p1, p2, sd[p], sd[q], v[p], v[q]);
-                        }
-                    }
-                    const int nt = s_ntri[type];
-                    for (int t = 0; t < nt; ++t) {
-                        const float s0 = vert[s_tri[type][3 * t]].w, s1 = vert[s_tri[type][3 * t + 1]].w, s2 = vert[s_tri[type][3 * t + 2]].w;
-                        if (!(s0 > a.max_std || s1 > a.max_std || s2 > a.max_std)) ++n_tri;
-                    }
-                } else {
-                    type = 0;
-                }
+                nt = bad ? 0 : s_ntri[type];
             }
-            // block exclusive scan of n_tri; ONE reservation per CTA, issued by thread 0 while everybody stages its triangles
-            int incl = n_tri;
+            int incl = nt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += u; }
             if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
             __syncthreads();
-            int tot = 0, wpre = 0;
+            int n_items = 0, wpre = 0;
 #pragma unroll
-            for (int w = 0; w < MC_THREADS / 32; ++w) { const int t = warp_tot[w]; if (w < (tid >> 5)) wpre += t; tot += t; }
-            if (tid == 0 && tot) block_base = atomicAdd(a.count, tot);
-            const bool staged = tot <= MC_STAGE_TRIS;                // else (rare): direct stores once the base is known
-            const int local0 = wpre + incl - n_tri;
-            if (staged && n_tri) {
-                int local = local0;
-                const int nt = s_ntri[type];
-                for (int t = 0; t < nt; ++t) {
-                    const float4 v0 = vert[s_tri[type][3 * t]], v1 = vert[s_tri[type][3 * t + 1]], v2 = vert[s_tri[type][3 * t + 2]];
-                    if (v0.w > a.max_std || v1.w > a.max_std || v2.w > a.max_std) continue;
-                    float* o = st_tri + local * 9;
-                    o[0] = v0.x; o[1] = v0.y; o[2] = v0.z; o[3] = v1.x; o[4] = v1.y; o[5] = v1.z; o[6] = v2.x; o[7] = v2.y; o[8] = v2.z;
-                    float* os = st_std + local * 3;
-                    os[0] = v0.w; os[1] = v1.w; os[2] = v2.w;
-                    ++local;
+            for (int w = 0; w < MC_THREADS / 32; ++w) { const int t = warp_tot[w]; if (w < (tid >> 5)) wpre += t; n_items += t; }
+            for (int t = 0; t < nt; ++t) s_work[wpre + incl - nt + t] = (uint32_t)sub | ((uint32_t)t << 9) | ((uint32_t)type << 12);
+            __syncthreads();                                         // work list complete (warp_tot is free again after this barrier)
+            // ---- 3b: one thread per candidate triangle: its three edge vertices, the max_std filter, compaction, ONE reservation
+            //      per chunk; triangles are staged in shared memory and written out as contiguous float streams (full sectors)
+            for (int i0 = 0; i0 < n_items; i0 += MC_THREADS) {
+                const int i = i0 + tid;
+                bool keep = false;
+                float4 vv[3];
+                if (i < n_items) {
+                    const uint32_t wk = s_work[i];
+                    const int sb = wk & 511, t = (wk >> 9) & 7, ty = wk >> 12;
+                    const int rx = sb / (R * R), ry = (sb / R) % R, rz = sb % R;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const int e = s_tri[ty][3 * t + k];
+                        const int p = e < 8 ? e : e - 8, q = e < 4 ? ((e + 1) & 3) : (e < 8 ? 4 + ((e + 1) & 3) : e - 4);      // edge e joins corners p, q
+                        const int px = rx + (((p + 1) >> 1) & 1), py = ry + ((p >> 1) & 1), pz = rz + (p >> 2);
+                        const int qx = rx + (((q + 1) >> 1) & 1), qy = ry + ((q >> 1) & 1), qz = rz + (q >> 2);
+                        const int cp = (px * R1 + py) * R1 + pz, cq = (qx * R1 + qy) * R1 + qz;
+                        const float3 p1 = make_float3(__fmaf_rn((float)px, sbs, (float)bx), __fmaf_rn((float)py, sbs, (float)by), __fmaf_rn((float)pz, sbs, (float)bz));
+                        const float3 p2 = make_float3(__fmaf_rn((float)qx, sbs, (float)bx), __fmaf_rn((float)qy, sbs, (float)by), __fmaf_rn((float)qz, sbs, (float)bz));
+                        vv[k] = edge_vertex(p1, p2, c_std[cp], c_std[cq], c_sdf[cp], c_sdf[cq]);
+                    }
+                    keep = !(vv[0].w > a.max_std || vv[1].w > a.max_std || vv[2].w > a.max_std);
                 }
-            }
-            __syncthreads();                                         // staging complete, block_base visible
-            if (tot) {
-                const int64_t base = block_base;
-                if (staged) {
+                const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+                if ((tid & 31) == 0) warp_tot[tid >> 5] = __popc(ballot);
+                __syncthreads();
+                int tot = 0, pre = 0;
+#pragma unroll
+                for (int w = 0; w < MC_THREADS / 32; ++w) { const int t = warp_tot[w]; if (w < (tid >> 5)) pre += t; tot += t; }
+                if (tid == 0 && tot) block_base = atomicAdd(a.count, tot);
+                if (keep) {
+                    const int local = pre + __popc(ballot & ((1u << (tid & 31)) - 1u));
+                    float* o = st_tri + local * 9;
+                    o[0] = vv[0].x; o[1] = vv[0].y; o[2] = vv[0].z; o[3] = vv[1].x; o[4] = vv[1].y; o[5] = vv[1].z; o[6] = vv[2].x; o[7] = vv[2].y; o[8] = vv[2].z;
+                    float* os = st_std + local * 3;
+                    os[0] = vv[0].w; os[1] = vv[1].w; os[2] = vv[2].w;
+                }
+                __syncthreads();                                     // staging complete, block_base visible
+                if (tot) {
+                    const int64_t base = block_base;
                     const int64_t room = a.max_tri - base;           // triangles past max_tri are counted, not written
                     const int n_out = room <= 0 ? 0 : (room < tot ? (int)room : tot);
                     float* gt = a.tri + base * 9; float* gs = a.tri_std + base * 3; int64_t* gi = a.tri_id + base;
-                    for (int i = tid; i < n_out * 9; i += MC_THREADS) gt[i] = st_tri[i];
-                    for (int i = tid; i < n_out * 3; i += MC_THREADS) gs[i] = st_std[i];
-                    for (int i = tid; i < n_out; i += MC_THREADS) gi[i] = id;
-                } else if (n_tri) {
-                    int64_t out = base + local0;
-                    const int nt = s_ntri[type];
-                    for (int t = 0; t < nt; ++t) {
-                        const float4 v0 = vert[s_tri[type][3 * t]], v1 = vert[s_tri[type][3 * t + 1]], v2 = vert[s_tri[type][3 * t + 2]];
-                        if (v0.w > a.max_std || v1.w > a.max_std || v2.w > a.max_std) continue;
-                        if (out < a.max_tri) {
-                            float* o = a.tri + out * 9;
-                            o[0] = v0.x; o[1] = v0.y; o[2] = v0.z; o[3] = v1.x; o[4] = v1.y; o[5] = v1.z; o[6] = v2.x; o[7] = v2.y; o[8] = v2.z;
-                            float* os = a.tri_std + out * 3;
-                            os[0] = v0.w; os[1] = v1.w; os[2] = v2.w;
-                            a.tri_id[out] = id;
-                        }
-                        ++out;
-                    }
+                    for (int j = tid; j < n_out * 9; j += MC_THREADS) gt[j] = st_tri[j];
+                    for (int j = tid; j < n_out * 3; j += MC_THREADS) gs[j] = st_std[j];
+                    for (int j = tid; j < n_out; j += MC_THREADS) gi[j] = id;
                 }
+                __syncthreads();                                     // warp_tot / staging / block_base / (last chunk) the work list are reused
             }
-            if (sub0 + MC_THREADS < R3) __syncthreads();             // another pass reuses warp_tot / staging / block_base
         }
     }
 }

@@ -201,6 +201,22 @@ def render_rgbd(scene: Scene, R: np.ndarray, t: np.ndarray, step: int = 1, noise
 S3_EXTENT = 50.0
 
 
+# ---------------------------------------------------------------------------------------------------------------- scene S2
+def scene_S2(radius: float = 3.15, voxel_size: float = 0.05) -> Scene:
+    """SURVEY 8(d) scene S2 / BASELINE config 4: a sphere of `radius` metres seen from inside (~147 k PLIVoxes at 5 cm, R = 3.15)."""
+    half = radius + 0.15
+    return Scene("S2", [-half] * 3, [half] * 3, voxel_size, 2, 4.0)
+
+
+def s2_sphere_points(radius: float = 3.15, n_pts: int = 3_000_000):
+    """Fibonacci-lattice points on the sphere with inward normals (world frame), float32."""
+    i = np.arange(n_pts) + 0.5
+    phi = np.arccos(1 - 2 * i / n_pts)
+    th = np.pi * (1 + 5 ** 0.5) * i
+    d = np.stack([np.cos(th) * np.sin(phi), np.sin(th) * np.sin(phi), np.cos(phi)], 1)
+    return (radius * d).astype(np.float32), (-d).astype(np.float32)
+
+
 def scene_S3(voxel_size: float = 0.05, extent: float = S3_EXTENT) -> Scene:
     return Scene("S3", [0.0, 0.0, -1.0], [extent, extent, 1.0], voxel_size, 2, 4.0, room=None, extra={"extent": extent})
 

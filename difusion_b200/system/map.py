@@ -466,9 +466,11 @@ class DenseIndexedMap:
         if self._cache_persist is None or self._cache_persist.numel() < need:
             self._cache_persist = torch.zeros(self._L.dif_mesh_cache_scratch_bytes(self._n_cells, max(2 * n_cache, 1 << 20)),
                                               dtype=torch.uint8, device=dev)
-        o_tri = torch.empty((n_cache + n_new, 3, 3), dtype=torch.float32, device=dev)
-        o_id = torch.empty((n_cache + n_new,), dtype=torch.long, device=dev)
-        o_std = torch.empty((n_cache + n_new, 3), dtype=torch.float32, device=dev)
+        # fresh tensors (meshes handed out earlier keep their storage), sizes rounded so that the caching allocator finds a block
+        n_out = -(-(n_cache + n_new) // (1 << 19)) * (1 << 19)
+        o_tri = torch.empty((n_out, 3, 3), dtype=torch.float32, device=dev)
+        o_id = torch.empty((n_out,), dtype=torch.long, device=dev)
+        o_std = torch.empty((n_out, 3), dtype=torch.float32, device=dev)
         totals = torch.zeros(2, dtype=torch.long, device=dev)
         bm = (ctypes.c_float * 3)(*[float(np.float32(v)) for v in self.args.bound_min])
         _lib.check(self._L.dif_mesh_cache_merge(
@@ -487,10 +489,23 @@ class DenseIndexedMap:
         return dict(view=v, cap=self._cap_phys, tensors=(self._indexer, self._latent, self._pos, self._obs, self._dirty, self._n_occ_dev),
                     indexer=self._indexer, pos=self._pos)
 
+    def _ws(self, name: str, numel: int, dtype) -> torch.Tensor:
+        """Grow-only workspace of the mesh path (cubes, decode scratch, sample lists, marching-cubes output): a full extraction at
+        BASELINE config 4 needs ~2.5 GB of intermediates whose sizes change from call to call; asking the caching allocator for
+        them every time made it split, miss and cudaMalloc/cudaFree (device-synchronising) - 8 to 50 ms of a 10 ms extraction.
+        The returned view is valid until the next request for the same name."""
+        ws = self.__dict__.setdefault("_mesh_ws", {})
+        buf = ws.get(name)
+        if buf is None or buf.numel() < numel or buf.dtype != dtype:
+            buf = torch.empty(max(int(numel * 1.25), 1), dtype=dtype, device=self.device)
+            ws[name] = buf
+        return buf[:numel]
+
     def mesh_cubes(self, voxel_resolution: int, fast: bool = True, updated_vec_id: torch.Tensor = None, snap: dict = None):
         """Stages map.py:627-687 on the device: returns (focused_flatten_id (K,), vec_id_batch_mapping (cap,), high_sdf, high_std
         (B,2r,2r,2r) [sdf already negated], block_slots (B,), counts dict).  updated_vec_id None == all occupied PLIVoxes.
-        snap: a _snapshot() taken under modifying_lock (asynchronous extraction); default = the live map."""
+        snap: a _snapshot() taken under modifying_lock (asynchronous extraction); default = the live map.
+        The returned tensors are views of the map's mesh workspace (`_ws`): valid until the next mesh_cubes / extract_mesh call."""
         dev, L = self.device, self._L
         st = _lib.stream_ptr(dev)
         snap = snap or self._snapshot()
@@ -500,9 +515,9 @@ class DenseIndexedMap:
             self._mesh_persist_cap = cap
         k_max = cap if updated_vec_id is None else int(updated_vec_id.numel())
         upd = None if updated_vec_id is None else updated_vec_id.to(torch.int32).contiguous()
-        focused = torch.empty(max(k_max, 1), dtype=torch.long, device=dev)
-        block_slots = torch.empty(min(cap, 7 * max(k_max, 1)), dtype=torch.int32, device=dev)
-        mapping = torch.empty(cap, dtype=torch.int32, device=dev)
+        focused = self._ws("focused", max(k_max, 1), torch.long)
+        block_slots = self._ws("block_slots", min(cap, 7 * max(k_max, 1)), torch.int32)
+        mapping = self._ws("mapping", cap, torch.int32)
         counts = torch.zeros(2, dtype=torch.int32, device=dev)
         _lib.check(L.dif_mesh_select(ctypes.byref(view), _lib.ptr(upd), 0 if upd is None else upd.numel(), focused.data_ptr(),
                                      block_slots.data_ptr(), mapping.data_ptr(), counts.data_ptr(), self._mesh_persist.data_ptr(),
@@ -510,14 +525,34 @@ class DenseIndexedMap:
         K, B = counts.tolist()                               # host sync: output shapes depend on it
         r = int(voxel_resolution)
         hr = 2 * r
-        cube_sdf = torch.empty((B, hr, hr, hr), dtype=torch.float32, device=dev)
-        cube_std = torch.empty((B, hr, hr, hr), dtype=torch.float32, device=dev)
-        scratch = torch.empty(max(L.dif_mesh_decode_scratch_bytes(B, r), 256), dtype=torch.uint8, device=dev)
+        cube_sdf = self._ws("cube_sdf", B * hr ** 3, torch.float32).view(B, hr, hr, hr)
+        cube_std = self._ws("cube_std", B * hr ** 3, torch.float32).view(B, hr, hr, hr)
+        scratch = self._ws("decode_scratch", max(L.dif_mesh_decode_scratch_bytes(B, r), 256), torch.uint8)
         dcounts = torch.zeros(2, dtype=torch.int32, device=dev)
         _lib.check(L.dif_mesh_decode(ctypes.byref(view), self._prep.decoder.data_ptr(), block_slots.data_ptr(), B, r, int(bool(fast)),
                                      cube_sdf.data_ptr(), cube_std.data_ptr(), scratch.data_ptr(), scratch.numel(), dcounts.data_ptr(), st),
                    "dif_mesh_decode")
         return focused[:K], mapping, cube_sdf, cube_std, block_slots[:B], dcounts
+
+    def _marching_cubes_ws(self, indexer, focused, mapping, cube_sdf, cube_std, max_n_triangles: int, max_std: float):
+        """system.ext.marching_cubes_interp (mc.cpp:3-16) with its outputs in the mesh workspace instead of three fresh
+        max_n_triangles-sized tensors per call; an upper bound of 5 triangles per sub-cube caps the workspace."""
+        r = cube_sdf.size(1) // 2
+        cap = int(min(int(max_n_triangles), 5 * r ** 3 * max(int(focused.numel()), 1)))
+        tri = self._ws("mc_tri", cap * 9, torch.float32).view(cap, 3, 3)
+        fid = self._ws("mc_fid", cap, torch.int64)
+        std = self._ws("mc_std", cap * 3, torch.float32).view(cap, 3)
+        count = torch.zeros(1, dtype=torch.int32, device=self.device)
+        _lib.check(self._L.dif_marching_cubes(
+            indexer.data_ptr(), int(self.n_xyz[0]), int(self.n_xyz[1]), int(self.n_xyz[2]), focused.data_ptr(), focused.size(0),
+            mapping.data_ptr(), mapping.size(0), cube_sdf.data_ptr(), cube_std.data_ptr(), r, float(max_std),
+            tri.data_ptr(), fid.data_ptr(), std.data_ptr(), cap, count.data_ptr(), _lib.stream_ptr(self.device)), "dif_marching_cubes")
+        n = int(count.item())                      # the reference syncs here too (mc_interp_kernel.cu:367-369)
+        if n > cap:
+            import sys
+            sys.stderr.write(f"Warning from marching cube: the max triangle number is too small {n} vs {max_n_triangles}\n")
+            n = cap
+        return tri[:n], fid[:n], std[:n]
 
     def extract_mesh(self, voxel_resolution: int, max_n_triangles: int, fast: bool = True, max_std: float = 2000.0,
                      extract_async: bool = False, no_cache: bool = False, interpolate: bool = True):
@@ -566,9 +601,9 @@ class DenseIndexedMap:
                     focused = snap["pos"][owned].contiguous()
                 if cube_sdf.size(0) == 0 or focused.numel() == 0:
                     return
-                vertices, vertices_flatten_id, vertices_std = _ext.marching_cubes_interp(
-                    snap["indexer"].view(self.n_xyz), focused, mapping, cube_sdf, cube_std, max_n_triangles, self.n_xyz, max_std)
-                self._merge_into_cache(vertices.contiguous(), vertices_flatten_id.contiguous(), vertices_std.contiguous())
+                vertices, vertices_flatten_id, vertices_std = self._marching_cubes_ws(
+                    snap["indexer"], focused, mapping, cube_sdf, cube_std, max_n_triangles, max_std)
+                self._merge_into_cache(vertices, vertices_flatten_id, vertices_std)
 
         if extract_async:
             self.meshing_thread = threading.Thread(target=do_meshing, args=(voxel_resolution,), daemon=True)

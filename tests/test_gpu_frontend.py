@@ -262,3 +262,56 @@ def test_track_camera_end_to_end(dev):
     assert m.n_occupied > 3000
     err = np.linalg.norm(est[1].t - poses[1][1])
     assert err < 0.6 * np.linalg.norm(poses[1][1] - poses[0][1]) + 2e-3, err      # moved towards the true pose from the previous one
+
+
+def test_full_loop_pose_drift_against_loop_oracle(dev):
+    """SURVEY section 4 "Integration": the whole loop (reference main.py:71-94: track_camera with the shipped 3-group iter_config,
+    then integrate with the TRACKED pose) over 30 frames of the synthetic RGB-D stream, on the CUDA path, against the poses the CPU
+    loop oracle tracked on the same frames (tests/golden/loop_poses.npz, made by tests/golden/make_golden_loop.py).  Tracking errors
+    feed back into the map, so this bounds the accumulated divergence of the two implementations, frame by frame."""
+    from difusion_b200 import synthetic as S
+    from difusion_b200.network import utility as net_util
+    from difusion_b200.system.map import DenseIndexedMap
+    from difusion_b200.system.tracker import SDFTracker
+    from difusion_b200.utils.motion_util import Isometry, Rotation
+    fx = np.load(GOLDEN / "loop_poses.npz")
+    n = int(fx["R"].shape[0])
+    model, _ = net_util.load_model(str(GOLDEN / "weights.npz"))
+    sc = S.scene_S1(0.05)
+    m = DenseIndexedMap(model, sc.map_args(), 29, dev)
+    args = argparse.Namespace(sdf=dict(robust_kernel="huber", robust_k=5.0, subsample=0.5),
+                              rgb=dict(weight=500.0, robust_kernel=None, robust_k=0.01, min_grad_scale=0.0, max_depth_delta=0.2),
+                              iter_config=[{"n": 10, "type": [["rgb", 2]]}, {"n": 10, "type": [["sdf"], ["rgb", 1]]},
+                                           {"n": 50, "type": [["sdf"], ["rgb", 0]]}])
+    trk = SDFTracker(m, args)
+    calib = _Calib(S.ICL_FX, S.ICL_FY, S.ICL_CX, S.ICL_CY)
+    def ang(Ra, Rb):
+        return float(np.degrees(np.arccos(np.clip((np.trace(np.asarray(Ra) @ np.asarray(Rb).T) - 1) / 2, -1, 1))))
+    dt_mm, dr_deg, gt_mm, gt_deg, ogt_deg = [], [], [], [], []
+    for f in range(n):
+        R, t = S.orbit_pose(f, 200)
+        assert np.allclose(R, fx["R_gt"][f]) and np.allclose(t, fx["t_gt"][f])          # same stream as the fixture
+        rgb, depth = S.render_rgbd(sc, R, t, step=1)
+        gt = Isometry(q=Rotation(matrix=R), t=t)
+        pose = trk.track_camera(_t(rgb, dev), _t(depth, dev), calib, set_pose=gt if f == 0 else None)
+        pc, nrm = trk.last_processed_pc
+        m.integrate_keyframe(pose @ pc, pose.rotation @ nrm)
+        dR = np.asarray(pose.q.rotation_matrix) @ fx["R"][f].T
+        dt_mm.append(1e3 * float(np.linalg.norm(np.asarray(pose.t) - fx["t"][f])))
+        dr_deg.append(float(np.degrees(np.arccos(np.clip((np.trace(dR) - 1) / 2, -1, 1)))))
+        gt_mm.append(1e3 * float(np.linalg.norm(np.asarray(pose.t) - t)))
+        gt_deg.append(ang(pose.q.rotation_matrix, R)); ogt_deg.append(ang(fx["R"][f], R))
+        if f % 5 == 4:
+            print(f"[loop drift] frame {f}: gpu-oracle {dt_mm[-1]:.2f} mm {dr_deg[-1]:.3f} deg | gpu-gt {gt_mm[-1]:.2f} mm {gt_deg[-1]:.3f} deg | oracle-gt "
+                  f"{1e3 * float(np.linalg.norm(fx['t'][f] - t)):.2f} mm {ogt_deg[-1]:.3f} deg")
+    print(f"[loop drift] {n} frames: |t_gpu - t_oracle| max {max(dt_mm):.3f} mm (last {dt_mm[-1]:.3f}), rotation max {max(dr_deg):.4f} deg; "
+          f"|t_gpu - t_gt| max {max(gt_mm):.2f} mm; oracle |t - t_gt| max {1e3 * float(np.linalg.norm(fx['t'] - fx['t_gt'], axis=1).max()):.2f} mm; "
+          f"n_occupied {m.n_occupied} vs {int(fx['n_occupied'])}")
+    # Measured (B200): identical to 0.01 mm for 10 frames, 0.08 mm at frame 14, 0.33 mm / 0.02 deg at frame 19, 0.44 mm / 0.26 deg at
+    # frame 24 - and by frame 29 the CPU ORACLE has left the trajectory (4.0 deg from ground truth) while the CUDA path is within
+    # 0.08 deg of it: a feedback loop of two fp32 implementations bifurcates eventually (one Gauss-Newton step accepted on one side
+    # and rejected on the other, tracker.py:263-266).  The bound is therefore frame-by-frame over the first 20 frames, plus a bound
+    # of the CUDA path against GROUND TRUTH over all of them (the oracle's own error peaks at 15.95 mm).
+    assert max(dt_mm[:20]) < 1.0 and max(dr_deg[:20]) < 0.05, (max(dt_mm[:20]), max(dr_deg[:20]))
+    assert max(gt_mm) < 20.0 and max(gt_deg) < 0.5, (max(gt_mm), max(gt_deg))
+    assert abs(m.n_occupied - int(fx["n_occupied"])) <= 0.01 * int(fx["n_occupied"])
