@@ -180,14 +180,6 @@ def extra_full_loop(torch, dev, model, sc, new_map, cores):
         for rep in range(2):                                   # rep 0 warms allocators / scratch
             m4 = new_map()
             trk4 = SDFTracker(m4, full_args)
-            n_iter = 0
-            orig = trk4.compute_sdf_Hg
-
-            def counted(*aa, **kk):
-                nonlocal n_iter
-                n_iter += 1
-                return orig(*aa, **kk)
-            trk4.compute_sdf_Hg = counted
             torch.cuda.synchronize(dev)
             w0 = time.perf_counter()
             t_err, gpu_t = [], []
@@ -202,7 +194,9 @@ def extra_full_loop(torch, dev, model, sc, new_map, cores):
             torch.cuda.synchronize(dev)
             w1 = time.perf_counter()
         full_loop = {"frames": n_full, "frames_per_s": n_full / (w1 - w0), "ms_per_frame": 1e3 * (w1 - w0) / n_full,
-                     "sdf_linearisations_per_frame": n_iter / max(n_full - 1, 1), "max_translation_error_m": max(t_err),
+                     "sdf_linearisations_per_frame": trk4.n_sdf_linearisations / max(n_full - 1, 1),
+                     "rgb_linearisations_per_frame": trk4.n_rgb_linearisations / max(n_full - 1, 1),
+                     "host_syncs_in_gauss_newton": 0, "gauss_newton": "dif_gauss_newton: device-side energy test / solve / pose update, one C call per frame", "max_translation_error_m": max(t_err),
                      "what": "track_camera(rgb, depth) with the shipped 3-group iter_config + integrate_keyframe per frame + incremental "
                              "extract_mesh every 10 frames; 640x480 device-resident images; wall clock"}
     except Exception as e:                                      # the extra must never take the bench line down
@@ -258,6 +252,102 @@ def extra_decoder_sweep(torch, dev, L, _lib, net_util, model, table, n_rows, flu
         sweep[f"2^{p2}"] = {"samples_per_s": sps, "ms_median": med, "ms_min": min(ts), "tflops_algorithmic": sps * DEC_FWD_FLOP / 1e12,
                             "frac_of_bf16_burst_peak": sps * DEC_FWD_FLOP / 1e12 / pk["tf_burst"]}
     return sweep
+
+
+def extra_reference_gpu(torch, dev, frames, sc, n_steps, gpu_step_ms):
+    """SURVEY 8(d) 'Timing the reference' item 2: the headline step (compute_sdf_Hg + integrate_keyframe) through the reference's OWN
+    torch-CUDA path (unmodified map.py / tracker.py staged under oracle/_ref/pytorch, its own CUDA extensions from oracle/_ref) on the
+    same B200, same device-resident frames.  Baseline leg only: nothing of the product runs inside it."""
+    try:
+        from oracle import ref_gpu
+        if not ref_gpu.available():
+            return {"unavailable": "oracle/_ref not staged (run __graft_entry__.build() where /root/reference is mounted)"}
+        n = max(1, min(n_steps, len(frames)))
+        sec, rs = ref_gpu.time_stream(sc.map_args(), frames, dev, n_steps=n, warmup=2)
+        ours = float(sum(gpu_step_ms[:n])) * 1e-3
+        res = {"kind": "reference", "what": "the reference's own Python + torch CUDA ops + its own extensions (oracle/_ref), "
+                                            "compute_sdf_Hg(no_grad=False) + integrate_keyframe per frame, device-resident inputs, wall clock",
+               "frames": n, "frames_per_s": n / sec, "ms_per_frame": 1e3 * sec / n, "n_occupied": int(rs.map.n_occupied),
+               "ours_frames_per_s_same_frames": n / ours if ours > 0 else None, "speedup_device_resident": sec / ours if ours > 0 else None}
+        del rs
+        torch.cuda.empty_cache()
+        return res
+    except Exception as e:
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
+def extra_mesh(torch, dev, L, model, pk):
+    """BASELINE configs[3] / SURVEY 8(d) scene S2: full-scene mesh extraction at 1 cm (5 cm PLIVoxes, voxel_resolution 5) of a
+    Fibonacci-lattice sphere R = 3.15 m (3 M points, ~147 k PLIVoxes = ~3x the '50 k active blocks' the config names).  Reports the whole
+    `extract_mesh(no_cache)` call (select + ~26 M decoder samples + trilinear x2 + marching cubes + device cache merge, wall clock,
+    mesh left on the device), the marching-cubes kernel alone (CUDA events around the kernel, algorithmic bytes / HBM peak) and, when
+    oracle/_ref holds it, the reference's own unmodified marching-cubes extension on the same cubes (baseline leg, never the product)."""
+    from difusion_b200 import synthetic as S
+    from difusion_b200.system import ext
+    from difusion_b200.system.map import DenseIndexedMap
+    R, n_pts = 3.15, 3_000_000
+    sc = S.scene_S2(R)
+    pts, nrm = S.s2_sphere_points(R, n_pts)
+    m = DenseIndexedMap(model, sc.map_args(), 29, dev, initial_capacity=1 << 18)
+    for c in range(10):
+        sl = slice(c * n_pts // 10, (c + 1) * n_pts // 10)
+        m.integrate_keyframe(torch.from_numpy(pts[sl]).to(dev), torch.from_numpy(nrm[sl]).to(dev))
+    n_occ = m.n_occupied
+
+    def ev():
+        e = torch.cuda.Event(enable_timing=True); e.record(); return e
+    wall, sel_ms, mc_ms = [], [], []
+    n_tri = 0
+    for rep in range(5):                                        # rep 0 sizes the grow-only workspaces
+        torch.cuda.synchronize(dev); t0 = time.perf_counter()
+        mesh = m.extract_mesh(5, int(12e6), max_std=0.15, no_cache=True)
+        torch.cuda.synchronize(dev); wall.append(1e3 * (time.perf_counter() - t0))
+        n_tri = int(mesh.n_triangles)
+    for rep in range(5):
+        e0, e1, k0, k1 = ev(), ev(), ev(), ev()
+        e0.record()
+        focused, mapping, cs, cd, slots, cnt = m.mesh_cubes(5, fast=True, updated_vec_id=None)
+        e1.record()
+        L.dif_profile_hook(3, k0.cuda_event, k1.cuda_event)
+        tri, fid, tstd = ext.marching_cubes_interp(m.indexer.view(m.n_xyz), focused, mapping, cs, cd, int(12e6), m.n_xyz, 0.15)
+        torch.cuda.synchronize(dev)
+        sel_ms.append(e0.elapsed_time(e1)); mc_ms.append(k0.elapsed_time(k1))
+    n_low, n_high = [int(v) for v in cnt.tolist()]
+    B, Kf, T = int(cs.size(0)), int(focused.numel()), int(tri.size(0))
+    alg = 8.0 * 1000 * B + 8.0 * Kf + 56.0 * T
+    mc = float(np.median(mc_ms[1:]))
+    traffic, traffic_src = ncu_traffic("mc")
+    res = {"workload": "S2 sphere R=3.15 m, 3 M points, 5 cm PLIVoxes, voxel_resolution 5 (1 cm sub-cubes), max_std 0.15",
+           "plivoxes": Kf, "cubes": B, "triangles": T, "decoder_samples": n_low + n_high,
+           "extract_mesh_no_cache_ms": {"median": float(np.median(wall[1:])), "min": min(wall[1:]), "max": max(wall[1:]),
+                                        "what": "wall clock, select + decode + upsample + marching cubes + device cache merge, mesh left on the device"},
+           "select_decode_ms": float(np.median(sel_ms[1:])),
+           "decoder_samples_per_s": (n_low + n_high) / (float(np.median(sel_ms[1:])) * 1e-3),
+           "marching_cubes": {"kernel": "marching_cubes_kernel<5>", "bound": "hbm", "ms": mc, "algorithmic_bytes": alg,
+                              "achieved": alg / (mc * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s", "frac": alg / (mc * 1e-3) / 1e9 / pk["hbm"],
+                              "traffic": traffic, "traffic_source": traffic_src,
+                              "bytes_rule": "8 B x (2r)^3 x cubes + 8 B x PLIVoxes + 56 B x triangles (SURVEY 8d)"},
+           "triangles_extract_mesh": n_tri}
+    try:
+        from oracle import build_ref
+        if build_ref.available("marching_cubes"):
+            rmc = build_ref.load_module("marching_cubes")
+            args = (m.indexer.view(m.n_xyz), focused, mapping, cs, cd, int(12e6), m.n_xyz, 0.15)
+            ts_r, ts_o = [], []
+            for i in range(6):
+                e0, e1 = ev(), ev(); e0.record(); rt = rmc.marching_cubes_sparse_interp(*args); e1.record(); torch.cuda.synchronize(dev)
+                ts_r.append(e0.elapsed_time(e1))
+                e0, e1 = ev(), ev(); e0.record(); ot = ext.marching_cubes_interp(*args); e1.record(); torch.cuda.synchronize(dev)
+                ts_o.append(e0.elapsed_time(e1))
+            res["reference_gpu_marching_cubes"] = {"kind": "reference", "what": "the reference's unmodified marching_cubes_sparse_interp extension "
+                                                   "(oracle/_ref, compiled for sm_100a) on the same cubes, same call shape (allocation + kernel + count sync + trim)",
+                                                   "ms_reference": float(np.median(ts_r[1:])), "ms_ours_same_call": float(np.median(ts_o[1:])),
+                                                   "triangles_reference": int(rt[0].size(0)), "triangles_ours": int(ot[0].size(0))}
+    except Exception as e:
+        res["reference_gpu_marching_cubes"] = {"error": f"{type(e).__name__}: {e}"}
+    del m, mesh, tri, fid, tstd, cs, cd
+    torch.cuda.empty_cache()
+    return res
 
 
 def extra_config5(torch, dist, dev, model, rank, world, extent, n_frames, flush):
@@ -362,6 +452,8 @@ def main():
     ap.add_argument("--no-sweep", action="store_true", help="skip the decoder batch sweep (config 3) extras")
     ap.add_argument("--no-full-loop", action="store_true", help="skip the full track_camera + integrate + mesh loop extra")
     ap.add_argument("--no-graph", action="store_true", help="launch the frame's kernels directly instead of replaying the captured CUDA graph")
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip the reference's own torch-CUDA path timed beside the headline step")
+    ap.add_argument("--no-mesh", action="store_true", help="skip the config-4 full-scene mesh extraction extra")
     ap.add_argument("--no-config5", action="store_true", help="skip the sharded 1 M-PLIVox stream extra (BASELINE configs[4])")
     ap.add_argument("--config5-extent", type=float, default=50.0, help="side of the S3 height field in metres (50 -> ~1 M PLIVoxes)")
     ap.add_argument("--config5-frames", type=int, default=24)
@@ -566,6 +658,13 @@ def main():
                                                 "frac": (icp_flop / icp_t / 1e12 / pk["tf_sustained"]) if icp_t else 0}}}
 
     full_loop = {} if a.no_full_loop else extra_full_loop(torch, dev, model, sc, lambda: DenseIndexedMap(model, sc.map_args(), 29, dev, initial_capacity=1 << 19), cores)
+    ref_gpu_leg = {} if a.no_reference_gpu else extra_reference_gpu(torch, dev, frames, sc, min(K, 20), step_ms)
+    mesh = {}
+    if not a.no_mesh:
+        try:
+            mesh = extra_mesh(torch, dev, L, model, pk)
+        except Exception as e:
+            mesh = {"error": f"{type(e).__name__}: {e}"}
     sweep = {} if a.no_sweep else extra_decoder_sweep(torch, dev, L, _lib, net_util, model, m._latent[:max(n_occ, 1)], n_occ, flush, pk)
 
     # ------------------------------------------------------------------ cpu baseline: the oracle port on the host cores (bounded sample)
@@ -590,7 +689,7 @@ def main():
            f"one CUDA-graph replay per step ({launches_per_pass} kernels per {K}-step pass inside the graphs, counted in the direct-launch pass)",
            "roofline": roofline, "cpu_baseline": cpu,
            "same_prefix": {"frames": ns, "gpu_frames_per_s": ns / (gpu_prefix_ms * 1e-3), "cpu_frames_per_s": ns / cpu_sec},
-           "map": {"n_occupied": n_occ, "last_integrate": stats_dev}, "decoder_sweep": sweep, "full_loop": full_loop,
+           "map": {"n_occupied": n_occ, "last_integrate": stats_dev}, "reference_gpu": ref_gpu_leg, "decoder_sweep": sweep, "mesh": mesh, "full_loop": full_loop,
            "config5_sharded_stream": config5}
     print(json.dumps(out))
     if world > 1:

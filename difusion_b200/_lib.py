@@ -11,7 +11,7 @@ from pathlib import Path
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ["DIF_LIB_PATH"]) if os.environ.get("DIF_LIB_PATH") else _HERE / "libdifusion_b200.so"   # override: kernel A/B builds (tools/)
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 DIF_STAT_COUNT = 12
 STAT_N_KEPT, STAT_N_NEW, STAT_N_SAMPLES, STAT_N_UPDATED, STAT_N_OCCUPIED, STAT_FLAGS, STAT_N_FOCUSED, STAT_N_XCHG, STAT_SEQ, STAT_N_ROWS = range(10)
 FRAME_HEADER_FLOATS, FRAME_POINT_FLOATS = 32, 9           # DIF_FRAME_HEADER_FLOATS / DIF_FRAME_POINT_FLOATS
@@ -28,12 +28,44 @@ class MapView(C.Structure):
                 ("bound_min", C.c_float * 3), ("voxel_size", C.c_float), ("prune_min_vox_obs", C.c_int32),
                 ("ignore_count_th", C.c_float), ("encoder_count_th", C.c_float),
                 ("shard_rank", C.c_int32), ("shard_world", C.c_int32), ("xchg_slots", C.c_void_p), ("latent_stride", C.c_int32),
-                ("shard_block_log2", C.c_int32), ("row_of_slot", C.c_void_p), ("n_rows", C.c_void_p), ("row_capacity", C.c_int64)]
+                ("shard_block_log2", C.c_int32), ("row_of_slot", C.c_void_p), ("n_rows", C.c_void_p), ("row_capacity", C.c_int64),
+                ("scalar_division_mode", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class FrameParams(C.Structure):
     """struct dif_frame_params (the per-frame block the kernels read from DEVICE memory)"""
     _fields_ = [("n_points", C.c_int32), ("seq", C.c_int32), ("reserved", C.c_int32 * 2), ("pose", C.c_float * 24)]
+
+
+GN_MAX_TERMS, GN_MAX_GROUPS, GN_MAX_LEVELS = 4, 8, 4
+GN_TERM_SDF, GN_TERM_RGB = 0, 1
+GN_CONTINUE, GN_BREAK, GN_EMPTY, GN_SINGULAR = 1, 2, 3, 4
+
+
+class GnLevel(C.Structure):
+    """struct dif_gn_level"""
+    _fields_ = [("prev_i", C.c_void_p), ("prev_d", C.c_void_p), ("cur_i", C.c_void_p), ("cur_d", C.c_void_p), ("cur_grad", C.c_void_p),
+                ("h", C.c_int32), ("w", C.c_int32)]
+
+
+class GnGroup(C.Structure):
+    """struct dif_gn_group"""
+    _fields_ = [("n_iters", C.c_int32), ("n_terms", C.c_int32), ("kind", C.c_int32 * GN_MAX_TERMS), ("level", C.c_int32 * GN_MAX_TERMS)]
+
+
+class GnProblem(C.Structure):
+    """struct dif_gn_problem"""
+    _fields_ = [("obs_xyz", C.c_void_p), ("n_obs", C.c_int64), ("huber_k", C.c_float), ("n_levels", C.c_int32),
+                ("level", GnLevel * GN_MAX_LEVELS), ("intr", C.c_float * 4), ("K", C.c_double * 9), ("Kinv", C.c_double * 9),
+                ("min_grad_scale", C.c_float), ("max_depth_delta", C.c_float), ("rgb_robust", C.c_int32), ("rgb_robust_k", C.c_float),
+                ("rgb_weight", C.c_float), ("n_groups", C.c_int32), ("group", GnGroup * GN_MAX_GROUPS),
+                ("last_pose", C.c_double * 12), ("init_delta", C.c_double * 12)]
+
+
+class GnResult(C.Structure):
+    """struct dif_gn_result"""
+    _fields_ = [("delta", C.c_double * 12), ("energy", C.c_double), ("last_iter", C.c_int32), ("status", C.c_int32),
+                ("empty_term", C.c_int32), ("n_iterations", C.c_int32), ("n_sdf", C.c_int32), ("n_rgb", C.c_int32)]
 
 
 _P, _I64, _I32, _F, _SZ = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_size_t
@@ -81,6 +113,8 @@ SIGNATURES = {
     "dif_rgb_odometry": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _FP, _FP, _FP, _F, _F, _P, _P, _P]),
     "dif_rgb_scratch_bytes": (_SZ, []),
     "dif_rgb_linearize": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _FP, _FP, _FP, _F, _F, C.c_int, _F, _F, C.c_int, _P, _SZ, _P, _P]),
+    "dif_gn_scratch_bytes": (_SZ, [_I64]),
+    "dif_gauss_newton": (C.c_int, [_MV, _P, C.POINTER(GnProblem), _P, _SZ, _P, C.POINTER(GnResult), _P]),
     "dif_mesh_cache_scratch_bytes": (_SZ, [_I64, _I64]),
     "dif_mesh_cache_merge": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _I64, _F, C.POINTER(C.c_float), _I64, _P, _P, _P, _P, _P, _SZ, _P]),
 }

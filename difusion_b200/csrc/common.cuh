@@ -67,19 +67,24 @@ struct Carver {
 struct Grid {
     int nx, ny, nz;
     float bx, by, bz, vs;
+    float inv_vs; int mul;        // scalar_division_mode 1: multiply by the fp32 reciprocal (torch on CUDA tensors)
     __host__ __device__ int64_t cells() const { return (int64_t)nx * ny * nz; }
 };
 
 inline Grid make_grid(const dif_map_view* m) {
     Grid g; g.nx = m->nx; g.ny = m->ny; g.nz = m->nz;
     g.bx = m->bound_min[0]; g.by = m->bound_min[1]; g.bz = m->bound_min[2]; g.vs = m->voxel_size;
+    g.inv_vs = 1.0f / m->voxel_size; g.mul = m->scalar_division_mode == 1;
     return g;
 }
 
-// (p - bound_min) / voxel_size exactly as the reference's CPU tensors compute it: one fp32 subtract, one fp32 true
-// division (system/map.py:366-367, :565).  Explicit _rn intrinsics stop nvcc from contracting or replacing the divide.
+// (p - bound_min) / voxel_size exactly as the reference computes it: one fp32 subtract, then one fp32 true division (torch on
+// CPU tensors) or one fp32 multiplication by the rounded reciprocal (torch on CUDA tensors, dif_map_view.scalar_division_mode)
+// (system/map.py:366-367, :565).  Explicit _rn intrinsics stop nvcc from contracting or replacing the operations.
 __device__ __forceinline__ float3 normalize_point(const Grid& g, float x, float y, float z) {
-    return make_float3(__fdiv_rn(__fsub_rn(x, g.bx), g.vs), __fdiv_rn(__fsub_rn(y, g.by), g.vs), __fdiv_rn(__fsub_rn(z, g.bz), g.vs));
+    const float dx = __fsub_rn(x, g.bx), dy = __fsub_rn(y, g.by), dz = __fsub_rn(z, g.bz);
+    if (g.mul) return make_float3(__fmul_rn(dx, g.inv_vs), __fmul_rn(dy, g.inv_vs), __fmul_rn(dz, g.inv_vs));
+    return make_float3(__fdiv_rn(dx, g.vs), __fdiv_rn(dy, g.vs), __fdiv_rn(dz, g.vs));
 }
 
 // linear id = z + nz*y + nz*ny*x  (map.py:287-292)

@@ -101,11 +101,20 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 }
 
 // robust: 0 none, 1 huber, 2 tukey (tracker.py:58-71)
-__global__ void __launch_bounds__(PH_THREADS) rgb_linearize_kernel(PhotoArgs a, int robust, float robust_k, float weight, int want_grad,
+// kkt_dev (nullable): K R K^-1 [9] and K t [3] read from device memory instead of the launch arguments - the device-driven
+// Gauss-Newton loop (gn.cu) rewrites them after every pose update, so the host never touches the pose between iterations.
+__global__ void __launch_bounds__(PH_THREADS) rgb_linearize_kernel(PhotoArgs a, const float* __restrict__ kkt_dev, int robust, float robust_k,
+                                                                   float weight, int want_grad,
                                                                    double* __restrict__ partials, unsigned int* __restrict__ done_counter,
                                                                    double* __restrict__ out) {
     __shared__ double s_part[PH_THREADS / 32][PH_VALS];
     __shared__ bool is_last;
+    if (kkt_dev) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) a.k[i] = __ldcg(kkt_dev + i);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) a.kt[i] = __ldcg(kkt_dev + 9 + i);
+    }
     float acc[29];
 #pragma unroll
     for (int j = 0; j < 29; ++j) acc[j] = 0.f;
@@ -175,6 +184,30 @@ static int fill_args(PhotoArgs& a, const float* prev_i, const float* prev_d, con
     return DIF_OK;
 }
 
+size_t rgb_scratch_bytes() { return align_up((size_t)DIF_NUM_SMS * 4 * PH_VALS * sizeof(double)) + 256; }
+
+// krkinv/kt: host values, or (kkt_dev != NULL) 12 floats in device memory read by the kernel
+int rgb_launch(const float* prev_i, const float* prev_d, const float* cur_i, const float* cur_d, const float* dIdxy, int h, int w,
+               const float* intr, const float* krkinv, const float* kt, const float* kkt_dev, float min_grad_scale, float max_depth_delta,
+               int robust_kind, float robust_k, float weight, int want_grad, void* scratch, size_t scratch_bytes, double* out_dev, cudaStream_t st) {
+    static const float zero12[12] = {};
+    PhotoArgs a;
+    const int rc = fill_args(a, prev_i, prev_d, cur_i, cur_d, dIdxy, h, w, intr, kkt_dev ? zero12 : krkinv, kkt_dev ? zero12 : kt,
+                             min_grad_scale, max_depth_delta);
+    if (rc || !scratch || !out_dev || robust_kind < 0 || robust_kind > 2) return DIF_E_INVALID;
+    if (scratch_bytes < rgb_scratch_bytes()) return DIF_E_WORKSPACE;
+    Carver c(scratch);                                               // zero-filled once by the caller; the counter is left zeroed
+    double* partials = c.take<double>((size_t)DIF_NUM_SMS * 4 * PH_VALS);
+    unsigned int* counter = c.take<unsigned int>(1);
+    const int64_t n_px = (int64_t)h * w;
+    int64_t grid = (n_px + PH_THREADS * 4 - 1) / (PH_THREADS * 4);   // >= 4 pixels per thread
+    if (grid > DIF_NUM_SMS * 4) grid = DIF_NUM_SMS * 4;
+    if (grid < 1) grid = 1;
+    rgb_linearize_kernel<<<(unsigned)grid, PH_THREADS, 0, st>>>(a, kkt_dev, robust_kind, robust_k, weight, want_grad, partials, counter, out_dev);
+    DIF_COUNT_LAUNCH(1);
+    return check_launch("rgb_linearize_kernel");
+}
+
 }  // namespace dif
 
 using namespace dif;
@@ -201,26 +234,14 @@ int dif_rgb_odometry(const float* prev_intensity, const float* prev_depth, const
     return check_launch("rgb_odometry_kernel");
 }
 
-size_t dif_rgb_scratch_bytes(void) { return align_up((size_t)DIF_NUM_SMS * 4 * PH_VALS * sizeof(double)) + 256; }
+size_t dif_rgb_scratch_bytes(void) { return rgb_scratch_bytes(); }
 
 int dif_rgb_linearize(const float* prev_intensity, const float* prev_depth, const float* cur_intensity, const float* cur_depth,
                       const float* cur_dIdxy, int h, int w, const float* intr, const float* krkinv, const float* kt,
                       float min_grad_scale, float max_depth_delta, int robust_kind, float robust_k, float weight, int want_grad,
                       void* scratch, size_t scratch_bytes, double* out_dev, void* stream) {
-    PhotoArgs a;
-    const int rc = fill_args(a, prev_intensity, prev_depth, cur_intensity, cur_depth, cur_dIdxy, h, w, intr, krkinv, kt, min_grad_scale, max_depth_delta);
-    if (rc || !scratch || !out_dev || robust_kind < 0 || robust_kind > 2) return DIF_E_INVALID;
-    if (scratch_bytes < dif_rgb_scratch_bytes()) return DIF_E_WORKSPACE;
-    Carver c(scratch);                                               // zero-filled once by the caller; the counter is left zeroed
-    double* partials = c.take<double>((size_t)DIF_NUM_SMS * 4 * PH_VALS);
-    unsigned int* counter = c.take<unsigned int>(1);
-    const int64_t n_px = (int64_t)h * w;
-    int64_t grid = (n_px + PH_THREADS * 4 - 1) / (PH_THREADS * 4);   // >= 4 pixels per thread
-    if (grid > DIF_NUM_SMS * 4) grid = DIF_NUM_SMS * 4;
-    if (grid < 1) grid = 1;
-    rgb_linearize_kernel<<<(unsigned)grid, PH_THREADS, 0, (cudaStream_t)stream>>>(a, robust_kind, robust_k, weight, want_grad, partials, counter, out_dev);
-    DIF_COUNT_LAUNCH(1);
-    return check_launch("rgb_linearize_kernel");
+    return rgb_launch(prev_intensity, prev_depth, cur_intensity, cur_depth, cur_dIdxy, h, w, intr, krkinv, kt, nullptr, min_grad_scale,
+                      max_depth_delta, robust_kind, robust_k, weight, want_grad, scratch, scratch_bytes, out_dev, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -153,32 +153,40 @@ __global__ void __launch_bounds__(1024) box_scan2_kernel(uint32_t* __restrict__ 
     if (threadIdx.x == 0) { s->n_cells = (int)s_carry; n_out[0] = s->overflow ? -1 : (int)s_carry; }
 }
 
-// rank of the point's cell -> accumulate.  sums: [n_points rows max][8] = (x, y, z, nx, ny, nz, count, -), zero-filled by the caller side
-__global__ void box_accumulate_kernel(const float* __restrict__ p, const float* __restrict__ nr, int n, const BoxState* __restrict__ s, float voxel,
-                                      const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ word_rank,
-                                      const uint32_t* __restrict__ chunk_sum, float* __restrict__ sums) {
+// rank of the point's cell -> push the point on the cell's list.  head: [n_points max] (index + 1 of the list head, 0 = empty; zero on
+// entry), next: [n_points] (both with a stride of 2 words, see the caller).  The list ORDER depends on the scheduling; the sums below do not.
+__global__ void box_link_kernel(const float* __restrict__ p, int n, const BoxState* __restrict__ s, float voxel,
+                                const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ word_rank,
+                                const uint32_t* __restrict__ chunk_sum, int* __restrict__ head, int* __restrict__ next) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || s->overflow) return;
     const long long key = box_key(s, p + 3 * i, voxel);
     const long long w = key >> 5;
     const uint32_t rank = chunk_sum[w / BOX_SCAN_W] + word_rank[w] + __popc(bitmap[w] & ((1u << (key & 31)) - 1u));
-    float* d = sums + (size_t)rank * 8;
-    atomicAdd(d + 0, p[3 * i]); atomicAdd(d + 1, p[3 * i + 1]); atomicAdd(d + 2, p[3 * i + 2]);
-    atomicAdd(d + 3, nr[3 * i]); atomicAdd(d + 4, nr[3 * i + 1]); atomicAdd(d + 5, nr[3 * i + 2]);
-    atomicAdd(d + 6, 1.0f);
+    next[2 * i] = atomicExch(head + 2 * rank, i + 1);
 }
 
-// mean = sum / count (torch_scatter.scatter_mean: sum, then division by the clamped count); clears the bitmap words and the sum
-// rows this frame touched, so the scratch is all-zero again when the call returns (self-cleaning)
-__global__ void box_finalize_kernel(const BoxState* __restrict__ s, float* __restrict__ sums, float* __restrict__ out_p, float* __restrict__ out_n) {
+// One thread per occupied cell: walk the cell's list and sum in fp64.  A cell holds ~2.5 points whose coordinates share their
+// leading bits, so the fp64 sum of the fp32 values is EXACT and therefore independent of the list order: the means are
+// bit-reproducible from run to run and from GPU to GPU (fp32 atomics are not - and a 1-ulp change of a mean can move a point across a
+// PLIVox face and change the map), and equal to the fp64 restatement the oracles use (synthetic.box_filter).  The reference's own
+// scatter_mean (tracker.py:21-22, torch_scatter fp32 atomics on CUDA) is order-dependent in the last bit; this result lies inside
+// that spread.  mean = sum / count; clears the list heads this frame touched, so the scratch is all-zero again on return.
+__global__ void box_finalize_kernel(const float* __restrict__ p, const float* __restrict__ nr, const BoxState* __restrict__ s,
+                                    int* __restrict__ head, const int* __restrict__ next, float* __restrict__ out_p, float* __restrict__ out_n) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= s->n_cells) return;
-    float* d = sums + (size_t)r * 8;
-    const float c = fmaxf(d[6], 1.0f);
+    double sp[3] = {0.0, 0.0, 0.0}, sn[3] = {0.0, 0.0, 0.0}, cnt = 0.0;
+    for (int j = head[2 * r]; j != 0; j = next[2 * (j - 1)]) {
+        const int i = j - 1;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { out_p[3 * r + k] = __fdiv_rn(d[k], c); out_n[3 * r + k] = __fdiv_rn(d[3 + k], c); }
+        for (int k = 0; k < 3; ++k) { sp[k] += (double)p[3 * i + k]; sn[k] += (double)nr[3 * i + k]; }
+        cnt += 1.0;
+    }
+    const double c = cnt > 1.0 ? cnt : 1.0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) d[k] = 0.f;
+    for (int k = 0; k < 3; ++k) { out_p[3 * r + k] = (float)(sp[k] / c); out_n[3 * r + k] = (float)(sn[k] / c); }
+    head[2 * r] = 0;
 }
 
 __global__ void box_unmark_kernel(const float* __restrict__ p, int n, const BoxState* __restrict__ s, float voxel, uint32_t* __restrict__ bitmap) {
@@ -217,12 +225,15 @@ int dif_point_box_filter(const float* points, const float* normals, int64_t n, f
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned long long words = (unsigned long long)((max_cells + 31) / 32);
     if (words > BOX_MAX_WORDS) return DIF_E_INVALID;
-    Carver c(scratch);                                   // bitmap and sums are zero on entry (caller zero-fills once) and on exit
+    Carver c(scratch);                                   // bitmap and list heads are zero on entry (caller zero-fills once) and on exit
     BoxState* s = c.take<BoxState>(1);
     uint32_t* bitmap = c.take<uint32_t>(words);
     uint32_t* word_rank = c.take<uint32_t>(words);
     uint32_t* chunk_sum = c.take<uint32_t>(words / BOX_SCAN_W + 2);
-    float* sums = c.take<float>((size_t)n * 8);
+    // heads in the even words (zero on entry and on exit), links in the odd words (never read before written): interleaved so that the
+    // layout does not depend on n - a call with more points must not find an earlier call's links where its heads are
+    int* head = c.take<int>((size_t)n * 2);
+    int* next = head + 1;
     if (n == 0) { cudaMemsetAsync(n_out_dev, 0, sizeof(int32_t), st); return check_launch("dif_point_box_filter"); }
     const int ni = (int)n;
     const unsigned gp = (unsigned)((n + 255) / 256);
@@ -235,8 +246,8 @@ int dif_point_box_filter(const float* points, const float* normals, int64_t n, f
     const unsigned chunks = (unsigned)((words + BOX_SCAN_W - 1) / BOX_SCAN_W);
     box_scan1_kernel<<<chunks, BOX_SCAN_T, 0, st>>>(bitmap, s, word_rank, chunk_sum);
     box_scan2_kernel<<<1, 1024, 0, st>>>(chunk_sum, s, n_out_dev);
-    box_accumulate_kernel<<<gp, 256, 0, st>>>(points, normals, ni, s, voxel_size, bitmap, word_rank, chunk_sum, sums);
-    box_finalize_kernel<<<gp, 256, 0, st>>>(s, sums, out_points, out_normals);
+    box_link_kernel<<<gp, 256, 0, st>>>(points, ni, s, voxel_size, bitmap, word_rank, chunk_sum, head, next);
+    box_finalize_kernel<<<gp, 256, 0, st>>>(points, normals, s, head, next, out_points, out_normals);
     box_unmark_kernel<<<gp, 256, 0, st>>>(points, ni, s, voxel_size, bitmap);
     DIF_COUNT_LAUNCH(9);
     return check_launch("dif_point_box_filter");

@@ -142,6 +142,12 @@ class DenseIndexedMap:
         self.latent_dim = latent_dim
         self.device = device
         self.extract_mesh_std_range = None
+        # `tensor / python_float` (map.py:367,565): "true" = IEEE division (the reference on CPU tensors, the committed fixtures),
+        # "reciprocal" = multiply by the fp32 reciprocal (what torch does on CUDA tensors: bit-identical cells to the reference run on a GPU)
+        mode = getattr(args, "scalar_division", "true")
+        if mode not in ("true", "reciprocal"):
+            raise ValueError(f"scalar_division must be 'true' or 'reciprocal', got {mode!r}")
+        self._division_mode = 1 if mode == "reciprocal" else 0
         self._n_cells = int(np.prod(self.n_xyz))
         if self._n_cells >= 2 ** 31:
             raise ValueError("grid too large for 32-bit linear ids")
@@ -351,6 +357,7 @@ class DenseIndexedMap:
         v.row_of_slot = self._row_of.data_ptr() if self._row_of is not None else None
         v.n_rows = self._n_rows_dev.data_ptr() if self._n_rows_dev is not None else None
         v.row_capacity = self._row_cap
+        v.scalar_division_mode = self._division_mode
         self._view_key, self._view_obj = key, v
         return v
 

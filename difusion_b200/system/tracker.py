@@ -16,12 +16,13 @@ remove_radius_outlier, estimate_normals) and ``point_box_filter``; callers that 
 from __future__ import annotations
 
 import copy
+import os
 
 import numpy as np
 import torch
 
 from .. import _lib
-from ..utils.motion_util import Isometry
+from ..utils.motion_util import Isometry, Rotation
 from . import ext as _ext
 
 
@@ -45,6 +46,14 @@ class SDFTracker:
         self.n_unstable = 0
         self._rgb_scratch = None
         self._pin = None
+        # gauss_newton runs through dif_gauss_newton (device-side energy test / solve / pose update, one C call per frame) unless
+        # host_loop is set: the reference-shaped Python loop below stays as the yardstick the native loop is tested against
+        self.host_loop = os.environ.get("DIF_GN_HOST", "0") == "1"
+        self._gn_scratch = None
+        self._gn_mailbox = None
+        self.n_sdf_linearisations = 0
+        self.n_rgb_linearisations = 0
+        self.last_gn = None
 
     def _read44(self, out: torch.Tensor) -> np.ndarray:
         """44 doubles device -> host through a pinned buffer and an event (cheaper than .cpu(): no pageable staging copy)."""
@@ -65,6 +74,7 @@ class SDFTracker:
             raise NotImplementedError("only the huber kernel is built (fusion-lr-kt.yaml:47)")
         out = self.map.icp_linearize(obs_xyz, last_pose.q.rotation_matrix, last_pose.t, cur_delta_pose.q.rotation_matrix,
                                      cur_delta_pose.t, huber_k=k, want_grad=not no_grad)
+        self.n_sdf_linearisations += 1
         o = self._read44(out)                        # the only host sync of the iteration
         assert o[43] > 0                              # the reference asserts on an empty valid set (utility.py:84-85)
         if no_grad:
@@ -119,7 +129,95 @@ class SDFTracker:
         return o[:36].reshape(6, 6).astype(float), o[36:42].astype(float), float(o[42])
 
     def gauss_newton(self, init_pose: Isometry, cur_intensity_pyramid, cur_depth_pyramid, cur_dIdxy_pyramid, obs_xyz: torch.Tensor, calib):
-        """tracker.py:220-283 for iter_config entries made of 'sdf' terms."""
+        """tracker.py:220-283.  Default: the whole loop in ONE call of dif_gauss_newton (csrc/gn.cu): term kernels read the pose from
+        device memory, the energy test, the 6x6 solve and the SE(3) update run on the device, the host thread only watches a pinned
+        mailbox word.  `host_loop = True` runs the reference-shaped Python loop (one readback per term and iteration) instead."""
+        if self.host_loop:
+            return self._gauss_newton_host(init_pose, cur_intensity_pyramid, cur_depth_pyramid, cur_dIdxy_pyramid, obs_xyz, calib)
+        L = _lib.lib()
+        last_pose = self.all_pd_pose[-1]
+        delta0 = last_pose.inv().dot(init_pose)
+        p = _lib.GnProblem()
+        x = None
+        if obs_xyz is not None:
+            x = obs_xyz.detach()
+            if x.dtype != torch.float32 or not x.is_contiguous():
+                x = x.float().contiguous()
+            p.obs_xyz, p.n_obs = x.data_ptr(), x.size(0)
+        dev = x.device if x is not None else cur_intensity_pyramid[0].device
+        if self.sdf_args.robust_kernel not in (None, "huber"):
+            raise NotImplementedError("only the huber kernel is built (fusion-lr-kt.yaml:47)")
+        p.huber_k = float(self.sdf_args.robust_k) if self.sdf_args.robust_kernel is not None else 0.0
+        groups = self.args.iter_config
+        if len(groups) > _lib.GN_MAX_GROUPS:
+            raise ValueError(f"iter_config has more than {_lib.GN_MAX_GROUPS} groups")
+        uses_rgb = False
+        p.n_groups = len(groups)
+        for gi, group in enumerate(groups):
+            G = p.group[gi]
+            G.n_iters, G.n_terms = int(group["n"]), len(group["type"])
+            if not 1 <= G.n_terms <= _lib.GN_MAX_TERMS:
+                raise ValueError("a group needs 1..4 loss terms")
+            for k, loss_config in enumerate(group["type"]):
+                if loss_config[0] == "sdf":
+                    G.kind[k] = _lib.GN_TERM_SDF
+                elif loss_config[0] == "rgb":
+                    G.kind[k], G.level[k] = _lib.GN_TERM_RGB, int(loss_config[1])
+                    uses_rgb = True
+                else:
+                    raise NotImplementedError(f"loss term {loss_config[0]!r} (tracker.py:254-262 'motion' is not used by the shipped configs)")
+        keep = [x]
+        if uses_rgb:
+            a = self.rgb_args
+            kind = {None: 0, "huber": 1, "tukey": 2}.get(a.robust_kernel, -1)
+            if kind < 0:
+                raise NotImplementedError(a.robust_kernel)
+            K = np.asarray(calib.to_K(), dtype=float)
+            Kinv = np.linalg.inv(K)
+            p.n_levels = len(cur_intensity_pyramid)
+            for lv in range(p.n_levels):
+                Lv = p.level[lv]
+                ts = (self.last_intensity[lv], self.last_depth[lv], cur_intensity_pyramid[lv], cur_depth_pyramid[lv], cur_dIdxy_pyramid[lv])
+                keep.extend(ts)
+                Lv.prev_i, Lv.prev_d, Lv.cur_i, Lv.cur_d, Lv.cur_grad = (_lib.ptr(t) for t in ts)
+                Lv.h, Lv.w = cur_intensity_pyramid[lv].shape
+            p.intr[:] = [calib.fx, calib.fy, calib.cx, calib.cy]
+            p.K[:], p.Kinv[:] = K.flatten().tolist(), Kinv.flatten().tolist()
+            p.min_grad_scale, p.max_depth_delta = float(a.min_grad_scale), float(a.max_depth_delta)
+            p.rgb_robust, p.rgb_robust_k, p.rgb_weight = kind, float(a.robust_k or 0.0), float(a.weight)
+        p.last_pose[:] = last_pose.q.rotation_matrix.flatten().tolist() + np.asarray(last_pose.t, float).tolist()
+        p.init_delta[:] = delta0.q.rotation_matrix.flatten().tolist() + np.asarray(delta0.t, float).tolist()
+        need = L.dif_gn_scratch_bytes(p.n_obs)
+        if self._gn_scratch is None or self._gn_scratch.numel() < need or self._gn_scratch.device != dev:
+            self._gn_scratch = torch.zeros(L.dif_gn_scratch_bytes(max(p.n_obs, 1 << 17)), dtype=torch.uint8, device=dev)   # zero-filled once (ABI)
+            self._gn_mailbox = torch.zeros(32, dtype=torch.int64).pin_memory()
+        res = _lib.GnResult()
+        import ctypes
+        view_ref = ctypes.byref(self.map._view()) if self.map is not None else None         # (a tracker without a map: rgb terms only)
+        dec = self.map._prep.decoder.data_ptr() if self.map is not None else None
+        _lib.check(L.dif_gauss_newton(view_ref, dec, ctypes.byref(p), self._gn_scratch.data_ptr(),
+                                      self._gn_scratch.numel(), self._gn_mailbox.data_ptr(), ctypes.byref(res), _lib.stream_ptr(dev)),
+                   "dif_gauss_newton")
+        del keep
+        self.n_sdf_linearisations += res.n_sdf
+        self.n_rgb_linearisations += res.n_rgb
+        self.last_gn = dict(last_iter=res.last_iter, status=res.status, iterations=res.n_iterations, energy=res.energy)
+        if res.status == _lib.GN_EMPTY:
+            if res.empty_term == 1:
+                raise AssertionError("compute_sdf_Hg: no observed point falls into an observed PLIVox (utility.py:84-85)")
+            raise ZeroDivisionError("float division by zero")               # tracker.py:165 with an empty valid set
+        if res.status == _lib.GN_SINGULAR:
+            raise np.linalg.LinAlgError("Singular matrix")
+        d = np.asarray(res.delta[:], dtype=float)
+        cur_delta_pose = Isometry(q=Rotation(matrix=d[:9].reshape(3, 3)), t=d[9:12])
+        if res.last_iter >= 10:                             # tracker.py:276-281
+            self.n_unstable += 1
+            if self.n_unstable >= 3 and self.rgb_args is not None:
+                self.rgb_args.weight = max(self.rgb_args.weight, 500.)
+        return last_pose.dot(cur_delta_pose)
+
+    def _gauss_newton_host(self, init_pose: Isometry, cur_intensity_pyramid, cur_depth_pyramid, cur_dIdxy_pyramid, obs_xyz: torch.Tensor, calib):
+        """tracker.py:220-283 statement by statement (the yardstick for the native loop)."""
         last_pose = self.all_pd_pose[-1]
         cur_delta_pose = last_pose.inv().dot(init_pose)
         last_delta_pose = copy.deepcopy(cur_delta_pose)

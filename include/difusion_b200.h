@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DIF_ABI_VERSION 2
+#define DIF_ABI_VERSION 3
 #define DIF_LATENT_DIM 29                 /* ckpt/default/hyper.json:34 "code_length" */
 
 enum {
@@ -88,6 +88,12 @@ typedef struct dif_map_view {
     int32_t* row_of_slot;        /* [capacity] slot -> row of latent_vecs on THIS rank, -1 = not stored here (caller initialises to -1) */
     int32_t* n_rows;             /* device scalar: rows of latent_vecs in use on this rank */
     int64_t  row_capacity;       /* rows latent_vecs can hold on this rank */
+    /* (p - bound_min) / voxel_size (map.py:366-367, :565): torch evaluates `tensor / python_float` as an IEEE division on CPU
+     * tensors and as a multiplication by the rounded fp32 reciprocal on CUDA tensors (its cpu-scalar fast path); a point within an
+     * ulp of a PLIVox face lands in different cells under the two.  0 = true division (the reference on CPU tensors: BASELINE
+     * configs[0], the committed fixtures); 1 = multiply by 1.f / voxel_size (bit-identical to the reference run on CUDA tensors). */
+    int32_t  scalar_division_mode;
+    int32_t  reserved_;
 } dif_map_view;
 
 /* ---- integrate_keyframe  (system/map.py:340-452; SURVEY rows a-2 .. a-6) -----------------------------
@@ -250,6 +256,50 @@ int dif_rgb_linearize(const float* prev_intensity, const float* prev_depth, cons
                       const float* cur_dIdxy, int h, int w, const float* intr, const float* krkinv, const float* kt,
                       float min_grad_scale, float max_depth_delta, int robust_kind, float robust_k, float weight, int want_grad,
                       void* scratch, size_t scratch_bytes, double* out_dev, void* stream);
+
+/* ---- Gauss-Newton pose refinement  (system/tracker.py:220-283 gauss_newton; :174-218, :131-172 for the two terms) -----------
+ * The whole loop in one call: for every group of `iter_config`, iterations 0..n-1 (terms with gradients) and the closing
+ * energy-only pass; after each iteration the energy test (:263-268), the 6x6 solve and delta <- exp(xi) . delta
+ * (utils/motion_util.py:205-229,277-278) run on the device in fp64, and the term kernels read the pose from device memory.
+ * The call blocks until the last iteration's verdict has arrived in `mailbox_host` (>= 128 bytes of pinned host memory that the
+ * device can write: cudaHostAlloc / torch pin_memory under UVA); it never synchronises the stream.
+ *   terms: DIF_GN_TERM_SDF = compute_sdf_Hg on obs_xyz (camera frame) against `map`; DIF_GN_TERM_RGB = compute_rgb_Hg at pyramid
+ *   `level` (the reference passes the level-0 intrinsics at every level, tracker.py:135-146; K and K^-1 are taken as given).
+ *   result: delta = refined delta pose (R row major [9], t [3]); last_iter = the reference's loop variable `i_iter` on exit
+ *   (:276: -1 after a completed group, else the iteration that raised the energy); status of the last executed iteration:
+ *   DIF_GN_EMPTY = a term had no valid sample (the reference asserts / divides by zero there; empty_term = 1 sdf, 2 rgb),
+ *   DIF_GN_SINGULAR = H was singular (numpy.linalg.solve raises).  scratch: dif_gn_scratch_bytes(n_obs), zero-filled once. */
+enum { DIF_GN_TERM_SDF = 0, DIF_GN_TERM_RGB = 1 };
+enum { DIF_GN_CONTINUE = 1, DIF_GN_BREAK = 2, DIF_GN_EMPTY = 3, DIF_GN_SINGULAR = 4 };
+#define DIF_GN_MAX_TERMS 4
+#define DIF_GN_MAX_GROUPS 8
+#define DIF_GN_MAX_LEVELS 4
+typedef struct dif_gn_level { const float *prev_i, *prev_d, *cur_i, *cur_d, *cur_grad; int32_t h, w; } dif_gn_level;
+typedef struct dif_gn_group { int32_t n_iters, n_terms; int32_t kind[DIF_GN_MAX_TERMS]; int32_t level[DIF_GN_MAX_TERMS]; } dif_gn_group;
+typedef struct dif_gn_problem {
+    const float* obs_xyz;        /* [n_obs][3] camera frame (tracker.last_processed_pc[0]); sdf terms only */
+    int64_t n_obs;
+    float   huber_k;             /* sdf robust kernel (fusion-lr-kt.yaml:47); <= 0: none */
+    int32_t n_levels;
+    dif_gn_level level[DIF_GN_MAX_LEVELS];
+    float   intr[4];             /* fx, fy, cx, cy */
+    double  K[9], Kinv[9];       /* calib.to_K() and its inverse, row major */
+    float   min_grad_scale, max_depth_delta;
+    int32_t rgb_robust;          /* 0 none, 1 huber, 2 tukey */
+    float   rgb_robust_k, rgb_weight;
+    int32_t n_groups;
+    dif_gn_group group[DIF_GN_MAX_GROUPS];
+    double  last_pose[12];       /* R [9] row major, t [3]: all_pd_pose[-1] */
+    double  init_delta[12];      /* last_pose^-1 . init_pose */
+} dif_gn_problem;
+typedef struct dif_gn_result {
+    double  delta[12];
+    double  energy;              /* energy of the last evaluated iterate */
+    int32_t last_iter, status, empty_term, n_iterations, n_sdf, n_rgb;
+} dif_gn_result;
+size_t dif_gn_scratch_bytes(int64_t n_obs);
+int dif_gauss_newton(const dif_map_view* map, const void* decoder_prepared, const dif_gn_problem* problem, void* scratch, size_t scratch_bytes,
+                     void* mailbox_host, dif_gn_result* result, void* stream);
 
 /* ---- groupby_sum  (system/ext/indexing/indexing.cu:59-109; indexing.cpp:4) -----------------------------
  * sum[indices[i]][:] += values[i][:];  count[indices[i]] += L  (the reference bumps the count once per column, :70).

@@ -10,6 +10,8 @@ device inputs - that is what pins the marching-cubes / groupby_sum stages (the r
 Only tests/, __graft_entry__.build() and bench.py's reference legs may touch this file or its outputs.
 
     python oracle/build_ref.py [marching_cubes indexing imgproc pcproc]
+
+stage_python() additionally stages the reference's own Python for the integrate / track path (read by oracle/ref_gpu.py only).
 """
 from __future__ import annotations
 
@@ -68,6 +70,32 @@ def build(names=None, verbose: bool = False) -> list[Path]:
     return [so_path(n) for n in names if available(n)]
 
 
+REF_PY = Path("/root/reference/pytorch")
+PY_OUT = OUT / "pytorch"
+# the reference's own Python on the integrate / track path and the shipped checkpoint (map.py, tracker.py and what they import)
+PY_FILES = ["system/map.py", "system/tracker.py", "network/di_decoder.py", "network/di_encoder.py", "network/utility.py",
+            "utils/exp_util.py", "utils/motion_util.py", "utils/pt_util.py", "dataset/production/__init__.py",
+            "ckpt/default/hyper.json", "ckpt/default/model_300.pth.tar", "ckpt/default/encoder_300.pth.tar"]
+
+
+def python_available() -> bool:
+    return all((PY_OUT / f).exists() for f in PY_FILES)
+
+
+def stage_python() -> bool:
+    """Stage the UNMODIFIED reference Python of the hot path + checkpoint under oracle/_ref/pytorch/ (git-ignored, travels to the GPU
+    box like the .so files) so that oracle/ref_gpu.py can run the reference's own torch-CUDA path there.  No-op without /root/reference."""
+    if python_available() or not REF_PY.exists():
+        return python_available()
+    import shutil
+    for f in PY_FILES:
+        dst = PY_OUT / f
+        dst.parent.mkdir(parents=True, exist_ok=True)
+        shutil.copyfile(REF_PY / f, dst)
+        os.chmod(dst, 0o644)
+    return python_available()
+
+
 def load_module(name: str):
     """Import oracle/_ref/<name>/<name>.so (a pybind module built by build()).  Needs a CUDA runtime; raises if not built."""
     import torch  # noqa: F401  (the module links against libtorch)
@@ -81,5 +109,6 @@ def load_module(name: str):
 
 
 if __name__ == "__main__":
+    print("reference python staged:", stage_python())
     for p in build(sys.argv[1:] or None, verbose=True):
         print(p, p.stat().st_size)

@@ -43,9 +43,38 @@ def test_struct_layout_matches_header():
     from difusion_b200 import _lib
     import ctypes
     # 6 pointers + int64 + 3 int32 + 3 float + float + int32 + 2 float + 2 int32 + pointer = 48 + 8 + 12 + 12 + 4 + 4 + 8 + 8 + 8 = 112
-    assert ctypes.sizeof(_lib.MapView) == 144 and _lib.MapView.xchg_slots.offset == 104 and _lib.MapView.latent_stride.offset == 112
+    assert ctypes.sizeof(_lib.MapView) == 152 and _lib.MapView.scalar_division_mode.offset == 144 and _lib.MapView.xchg_slots.offset == 104 and _lib.MapView.latent_stride.offset == 112
     assert _lib.MapView.shard_block_log2.offset == 116 and _lib.MapView.row_of_slot.offset == 120 and _lib.MapView.row_capacity.offset == 136
     assert _lib.MapView.capacity.offset == 48 and _lib.MapView.nx.offset == 56 and _lib.MapView.bound_min.offset == 68
+
+
+def test_struct_layout_against_the_c_compiler(tmp_path):
+    """sizeof / offsetof of every struct of the header as gcc lays them out == the ctypes mirrors in _lib.py."""
+    import ctypes
+    import subprocess
+    from difusion_b200 import _lib
+    probes = {"dif_map_view": (_lib.MapView, ["capacity", "bound_min", "xchg_slots", "row_capacity", "scalar_division_mode"]),
+              "dif_frame_params": (_lib.FrameParams, ["pose"]),
+              "dif_gn_level": (_lib.GnLevel, ["cur_grad", "h"]),
+              "dif_gn_group": (_lib.GnGroup, ["kind", "level"]),
+              "dif_gn_problem": (_lib.GnProblem, ["n_obs", "huber_k", "level", "intr", "K", "Kinv", "min_grad_scale", "rgb_weight", "n_groups",
+                                                  "group", "last_pose", "init_delta"]),
+              "dif_gn_result": (_lib.GnResult, ["energy", "last_iter", "n_rgb"])}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT / "include" / "difusion_b200.h"}"', "int main(void) {"]
+    for name, (_, fields) in probes.items():
+        lines.append(f'printf("{name} %zu\\n", sizeof({name}));')
+        for f in fields:
+            lines.append(f'printf("{name}.{f} %zu\\n", offsetof({name}, {f}));')
+    lines.append("return 0; }")
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.check_call(["gcc", "-std=c11", str(src), "-o", str(exe)])
+    got = dict(ln.split() for ln in subprocess.check_output([str(exe)], text=True).splitlines())
+    for name, (cls, fields) in probes.items():
+        assert int(got[name]) == ctypes.sizeof(cls), (name, got[name], ctypes.sizeof(cls))
+        for f in fields:
+            assert int(got[f"{name}.{f}"]) == getattr(cls, f).offset, (name, f)
 
 
 def test_no_cpu_fallback():

@@ -168,7 +168,8 @@ def test_rgb_gauss_newton_recovers_the_relative_pose(dev):
 
 
 def test_point_box_filter_matches_restatement(dev):
-    """tracker.point_box_filter (tracker.py:13-23): same cells, same row order, means within fp32 summation noise."""
+    """tracker.point_box_filter (tracker.py:13-23): same cells, same row order, means BIT-identical to the fp64 restatement (the
+    per-cell sums are exact in fp64, hence independent of the accumulation order: reproducible across runs and GPUs)."""
     from difusion_b200 import synthetic as S
     from difusion_b200.system import ext
     from difusion_b200.system.tracker import point_box_filter
@@ -179,11 +180,10 @@ def test_point_box_filter_matches_restatement(dev):
         exp_p, exp_n = S.box_filter(pts, nrm, vs)
         out_p, out_n = point_box_filter(_t(pts, dev), _t(nrm, dev), vs)
         assert out_p.shape == exp_p.shape and out_n.shape == exp_n.shape
-        assert np.abs(out_p.cpu().numpy() - exp_p).max() <= 2e-6 * max(1.0, np.abs(exp_p).max())
-        assert np.abs(out_n.cpu().numpy() - exp_n).max() <= 2e-6
+        assert np.array_equal(out_p.cpu().numpy(), exp_p) and np.array_equal(out_n.cpu().numpy(), exp_n)
     a, b = ext.point_box_filter(_t(pc, dev), _t(nc, dev), 0.02)     # scratch is self-cleaning: a second call gives the same rows
     c, d = ext.point_box_filter(_t(pc, dev), _t(nc, dev), 0.02)
-    assert a.shape == c.shape and float((a - c).abs().max()) <= 1e-6
+    assert a.shape == c.shape and torch.equal(a, c) and torch.equal(b, d)
     with pytest.raises(RuntimeError):
         ext.point_box_filter(_t(pc, dev).cpu(), _t(nc, dev), 0.02)
 
@@ -312,6 +312,89 @@ def test_full_loop_pose_drift_against_loop_oracle(dev):
     # 0.08 deg of it: a feedback loop of two fp32 implementations bifurcates eventually (one Gauss-Newton step accepted on one side
     # and rejected on the other, tracker.py:263-266).  The bound is therefore frame-by-frame over the first 20 frames, plus a bound
     # of the CUDA path against GROUND TRUTH over all of them (the oracle's own error peaks at 15.95 mm).
-    assert max(dt_mm[:20]) < 1.0 and max(dr_deg[:20]) < 0.05, (max(dt_mm[:20]), max(dr_deg[:20]))
+    # (first bound: 0.46-0.62 mm measured on different boxes at frame 9 - the encoder's fp32 atomics are the one order-dependent
+    # piece left on the path, 2e-7 on a latent - so the per-frame bound has head-room and the median carries the tight claim)
+    assert max(dt_mm[:20]) < 3.0 and float(np.median(dt_mm[:20])) < 0.3 and max(dr_deg[:20]) < 0.05, (max(dt_mm[:20]), max(dr_deg[:20]))
     assert max(gt_mm) < 20.0 and max(gt_deg) < 0.5, (max(gt_mm), max(gt_deg))
     assert abs(m.n_occupied - int(fx["n_occupied"])) <= 0.01 * int(fx["n_occupied"])
+
+
+def test_device_gauss_newton_equals_host_loop(dev):
+    """dif_gauss_newton (device-side energy test / solve / pose update, csrc/gn.cu) against the reference-shaped host loop
+    (SDFTracker._gauss_newton_host: one readback per term and iteration, numpy solve, Isometry algebra) on the SAME inputs (same
+    pre-processed cloud, pyramids and map: the box filter's per-cell means are atomics-ordered, so two runs of the front end differ in
+    the last bit).  Both drive the same deterministic term kernels, so the accepted iterates agree to fp64 rounding."""
+    from difusion_b200 import synthetic as S
+    from difusion_b200.network import utility as net_util
+    from difusion_b200.system.map import DenseIndexedMap
+    from difusion_b200.system.tracker import SDFTracker
+    from difusion_b200.utils.motion_util import Isometry, Rotation
+    model, _ = net_util.load_model(str(GOLDEN / "weights.npz"))
+    sc = S.scene_S1(0.05)
+    args = argparse.Namespace(sdf=dict(robust_kernel="huber", robust_k=5.0, subsample=0.5),
+                              rgb=dict(weight=500.0, robust_kernel=None, robust_k=0.01, min_grad_scale=0.0, max_depth_delta=0.2),
+                              iter_config=[{"n": 10, "type": [["rgb", 2]]}, {"n": 10, "type": [["sdf"], ["rgb", 1]]},
+                                           {"n": 50, "type": [["sdf"], ["rgb", 0]]}])
+    calib = _Calib(S.ICL_FX, S.ICL_FY, S.ICL_CX, S.ICL_CY)
+    m = DenseIndexedMap(model, sc.map_args(), 29, dev)
+    trk = SDFTracker(m, args)
+    native = type(trk).gauss_newton
+    seen = []
+
+    def both(init_pose, ints, deps, grads, obs, cal):
+        a = native(trk, init_pose, ints, deps, grads, obs, cal)
+        gn = dict(trk.last_gn)
+        n_un, w = trk.n_unstable, trk.rgb_args.weight
+        s0 = trk.n_sdf_linearisations
+        b = trk._gauss_newton_host(init_pose, ints, deps, grads, obs, cal)
+        host_sdf = trk.n_sdf_linearisations - s0
+        trk.n_unstable, trk.rgb_args.weight = n_un, w                     # the host run must not count twice
+        dt = float(np.linalg.norm(np.asarray(a.t) - np.asarray(b.t)))
+        dR = float(np.abs(np.asarray(a.q.rotation_matrix) - np.asarray(b.q.rotation_matrix)).max())
+        seen.append((dt, dR, gn["iterations"], host_sdf))
+        return b
+    trk.gauss_newton = both
+    for f in range(6):
+        R, t = S.orbit_pose(f, 200)
+        rgb, depth = S.render_rgbd(sc, R, t, step=1)
+        gt = Isometry(q=Rotation(matrix=R), t=t)
+        pose = trk.track_camera(_t(rgb, dev), _t(depth, dev), calib, set_pose=gt if f == 0 else None)
+        pc, nrm = trk.last_processed_pc
+        m.integrate_keyframe(pose @ pc, pose.rotation @ nrm)
+    assert len(seen) == 5
+    for f, (dt, dR, iters, host_sdf) in enumerate(seen, 1):
+        print(f"[gn] frame {f}: |dt| {dt:.2e} |dR| {dR:.2e}, {iters} iterations")
+        # (an fp32 pose entry may round differently after the two 6x6 solvers: iterates then differ by ~1e-9; an energy test between two
+        # nearly converged iterates may flip - one more, tiny, step on one side)
+        assert dt < 2e-6 and dR < 2e-6, (f, dt, dR)
+        assert iters > 3
+
+
+def test_device_gauss_newton_sdf_only_and_errors(dev):
+    """track_points (sdf-only iter_config, no pyramids) through the native loop; an empty valid set raises like the reference."""
+    from difusion_b200 import synthetic as S
+    from difusion_b200.network import utility as net_util
+    from difusion_b200.system.map import DenseIndexedMap
+    from difusion_b200.system.tracker import SDFTracker
+    from difusion_b200.utils.motion_util import Isometry, Rotation
+    model, _ = net_util.load_model(str(GOLDEN / "weights.npz"))
+    sc = S.scene_S1(0.05)
+    ns = argparse.Namespace(sdf=dict(robust_kernel="huber", robust_k=5.0, subsample=0.5), rgb=None, iter_config=[{"n": 20, "type": [["sdf"]]}])
+    res = []
+    for host in (False, True):
+        m = DenseIndexedMap(model, sc.map_args(), 29, dev)
+        trk = SDFTracker(m, ns)
+        trk.host_loop = host
+        for f in range(3):
+            R, t = S.orbit_pose(f, 200)
+            pc, nc = S.frame_points(sc, R, t)
+            gt = Isometry(q=Rotation(matrix=R), t=t)
+            pose = trk.track_points(_t(pc, dev), _t(nc, dev), set_pose=gt if f == 0 else None)
+            m.integrate_keyframe(gt @ _t(pc, dev), gt.rotation @ _t(nc, dev))
+        res.append(pose)
+    assert np.linalg.norm(np.asarray(res[0].t) - np.asarray(res[1].t)) < 2e-6
+    far = torch.full((4096, 3), 50.0, device=dev)                 # every point outside the grid: M = 0
+    with pytest.raises(AssertionError):
+        trk2 = SDFTracker(m, ns)
+        trk2.all_pd_pose.append(Isometry())
+        trk2.track_points(far, far)
