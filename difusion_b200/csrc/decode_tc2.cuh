@@ -29,7 +29,7 @@ namespace tc {
 constexpr uint32_t D2_OFF_BAR = OFF_X + 4 * X_PLANE_B;
 constexpr uint32_t D2_SMEM_B = D2_OFF_BAR + 176 + 16;           // 21 barriers (168 B) + TMEM base pointer
 static_assert(D2_SMEM_B <= 232448, "shared memory budget");
-enum { D2_W = 0, D2_X = 1, D2_XF = 3, D2_E = 5, D2_ACCA = 7, D2_ACCB = 9, D2_G = 11 };      // per-slot barriers: index + slot; G: 11 + 4*slot + g (.. 18)
+enum { D2_W = 0, D2_X = 1, D2_XF = 3, D2_E = 5, D2_ACCA = 7, D2_ACCB = 9, D2_G = 11, D2_W1 = 19, D2_W2 = 20, D2_W3 = 21 };      // per-slot barriers: index + slot; G: 11 + 4*slot + g (.. 18); W, W1..W3: weight groups
 
 #ifndef DIF_D2_ISSUERS
 #define DIF_D2_ISSUERS 1               // 1: one issuer, slots strictly alternating (default); 2: one issuer warp per slot (A/B)
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_tc2_kernel(const unsigned c
     int tn = 0; (void)tn;
 
     if (threadIdx.x == 0) {
-        mbar_init(bar0 + 8 * D2_W, 1);
+        mbar_init(bar0 + 8 * D2_W, 1); mbar_init(bar0 + 8 * D2_W1, 1); mbar_init(bar0 + 8 * D2_W2, 1); mbar_init(bar0 + 8 * D2_W3, 1);
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             mbar_init(bar0 + 8 * (D2_X + s), 1);          // producer warp -> issuer: layer-0 A tile ready
@@ -121,14 +121,27 @@ __global__ void __launch_bounds__(THREADS, 1) decode_tc2_kernel(const unsigned c
         // alone and catches up), so both slots converted at the same time and both wanted the tensor pipe at the same time -
         // measured ~5 k cycles per layer pair for 3.1 k cycles of MMA work.  Alternation puts them in anti-phase: while slot A's
         // layer l+1 is issued group by group behind its epilogue, slot B's epilogue warps have the ALUs to themselves, and vice versa.
+        // The weight image arrives in four groups with their own barriers (biases + W0, W1, W2, W3: as icp_tc2_kernel): L0 of the first
+        // tile starts after 18 KB of the 198 KB; the rest streams in behind the first layers (a small batch is ONE round of tiles, so
+        // the prologue is a large part of the launch).
         if (lane == 0) {
-            mbar_expect_tx(bar0 + 8 * D2_W, IMAGE_B);
-            constexpr uint32_t CH = 32768;
-            for (uint32_t off = 0; off < IMAGE_B; off += CH) bulk_g2s(sbase + off, image + off, (IMAGE_B - off) < CH ? (IMAGE_B - off) : CH, bar0 + 8 * D2_W);
+            mbar_expect_tx(bar0 + 8 * D2_W, BIAS_B + 2 * W0_B);
+            bulk_g2s(sbase + OFF_BIAS, image + OFF_BIAS, BIAS_B, bar0 + 8 * D2_W);
+            bulk_g2s(sbase + OFF_W0, image + OFF_W0, W0_B, bar0 + 8 * D2_W);
+            bulk_g2s(sbase + PLANE_B + OFF_W0, image + PLANE_B + OFF_W0, W0_B, bar0 + 8 * D2_W);
+            mbar_expect_tx(bar0 + 8 * D2_W1, 2 * W1_B);
+            bulk_g2s(sbase + OFF_W1, image + OFF_W1, W1_B, bar0 + 8 * D2_W1);
+            bulk_g2s(sbase + PLANE_B + OFF_W1, image + PLANE_B + OFF_W1, W1_B, bar0 + 8 * D2_W1);
+            mbar_expect_tx(bar0 + 8 * D2_W2, 2 * W2_B);
+            bulk_g2s(sbase + OFF_W2, image + OFF_W2, W2_B, bar0 + 8 * D2_W2);
+            bulk_g2s(sbase + PLANE_B + OFF_W2, image + PLANE_B + OFF_W2, W2_B, bar0 + 8 * D2_W2);
+            mbar_expect_tx(bar0 + 8 * D2_W3, 2 * W3_B);
+            bulk_g2s(sbase + OFF_W3, image + OFF_W3, W3_B, bar0 + 8 * D2_W3);
+            bulk_g2s(sbase + PLANE_B + OFF_W3, image + PLANE_B + OFF_W3, W3_B, bar0 + 8 * D2_W3);
         }
         __syncwarp();
         mbar_wait(bar0 + 8 * D2_W, 0);
-        TC_ACC(0, tcur);                                   // [0] weight image load
+        TC_ACC(0, tcur);                                   // [0] first weight group
         const uint64_t w0h = smem_desc(sbase + OFF_W0, 128 * 16, 128), w0l = smem_desc(sbase + PLANE_B + OFF_W0, 128 * 16, 128);
         const uint64_t w1h = smem_desc(sbase + OFF_W1, 128 * 16, 128), w1l = smem_desc(sbase + PLANE_B + OFF_W1, 128 * 16, 128);
         const uint64_t w2h = smem_desc(sbase + OFF_W2, 96 * 16, 128), w2l = smem_desc(sbase + PLANE_B + OFF_W2, 96 * 16, 128);
@@ -171,10 +184,13 @@ __global__ void __launch_bounds__(THREADS, 1) decode_tc2_kernel(const unsigned c
             }
             l0A = l0B = false;
             // ---- L1 (R0 -> R1), L2 (R1 -> R0, N = 96), L3 (R0 -> R1): four hand-off groups each, constant operands
+            if (it == 0) mbar_wait_spin(bar0 + 8 * D2_W1, 0);
             issue_hidden_layer<1>(A0, A1, w1h, w1l, bgA, ph_g, bar0 + 8 * D2_ACCB, bar0 + 8 * D2_E, it > 0, ph_eA, trace);
             if (liveB) issue_hidden_layer<1>(B0, B1, w1h, w1l, bgB, ph_g, bar0 + 8 * (D2_ACCB + 1), bar0 + 8 * (D2_E + 1), it > 0, ph_eB, trace);
+            if (it == 0) mbar_wait_spin(bar0 + 8 * D2_W2, 0);
             issue_hidden_layer<2>(A0, A1, w2h, w2l, bgA, ph_g ^ 1u, bar0 + 8 * D2_ACCA, 0u, false, ph_eA, trace);
             if (liveB) issue_hidden_layer<2>(B0, B1, w2h, w2l, bgB, ph_g ^ 1u, bar0 + 8 * (D2_ACCA + 1), 0u, false, ph_eB, trace);
+            if (it == 0) mbar_wait_spin(bar0 + 8 * D2_W3, 0);
             issue_hidden_layer<3>(A0, A1, w3h, w3l, bgA, ph_g, bar0 + 8 * D2_ACCB, 0u, false, ph_eA, trace);
             if (nextA && __all_sync(0xffffffffu, mbar_test(bar0 + 8 * D2_X, ph_xA))) { ph_xA ^= 1; TC_TRACE(1); issue_l0(0); TC_TRACE(2); l0A = true; }
             if (liveB) {

@@ -315,7 +315,7 @@ constexpr uint32_t E2OFF_BAR = EOFF_SLOT + 4 * TILE * 4;
 constexpr uint32_t E2SMEM_B = E2OFF_BAR + 272 + 16;
 static_assert(E2SMEM_B <= 232448, "shared memory layout");
 // barriers: 0 W; per slot s (index + s): X 1, XF 3, ACC0 5, ACC1 7, ACC2 9, ACC3 11, A0 13, A1 15, E 17; G 19 + 4 s + g  (.. 26)
-enum { E2_W = 0, E2_X = 1, E2_XF = 3, E2_ACC0 = 5, E2_ACC1 = 7, E2_ACC2 = 9, E2_ACC3 = 11, E2_A0 = 13, E2_A1 = 15, E2_E = 17, E2_G = 19 };
+enum { E2_W = 0, E2_X = 1, E2_XF = 3, E2_ACC0 = 5, E2_ACC1 = 7, E2_ACC2 = 9, E2_ACC3 = 11, E2_A0 = 13, E2_A1 = 15, E2_E = 17, E2_G = 19, E2_W2 = 27, E2_W3 = 28 };
 
 __global__ void __launch_bounds__(THREADS, 1) encode_tc2_kernel(const unsigned char* __restrict__ image, EncodeArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(THREADS, 1) encode_tc2_kernel(const unsigned c
     if ((int64_t)blockIdx.x >= n_tiles) return;                   // nothing to do: skip the weight load altogether
 
     if (threadIdx.x == 0) {
-        mbar_init(bar0 + 8 * E2_W, 1);
+        mbar_init(bar0 + 8 * E2_W, 1); mbar_init(bar0 + 8 * E2_W2, 1); mbar_init(bar0 + 8 * E2_W3, 1);
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             mbar_init(bar0 + 8 * (E2_X + s), 2);                  // two producer warps fill one x buffer
@@ -357,10 +357,18 @@ __global__ void __launch_bounds__(THREADS, 1) encode_tc2_kernel(const unsigned c
 
     if (warp == MMA_WARP) {
         // ===================================================== weight load + MMA issuer (warp-uniform, instructions elected)
+        // three weight groups with their own barriers: biases + W0 + W1 (11.5 KB: L0 and L1 start on them), W2 (64 KB), W3 (32 KB)
         if (lane == 0) {
-            mbar_expect_tx(bar0 + 8 * E2_W, EIMAGE_B);
-            constexpr uint32_t CH = 32768;
-            for (uint32_t off = 0; off < EIMAGE_B; off += CH) bulk_g2s(sbase + off, image + off, (EIMAGE_B - off) < CH ? (EIMAGE_B - off) : CH, bar0 + 8 * E2_W);
+            mbar_expect_tx(bar0 + 8 * E2_W, EBIAS_B + 2 * (EW0_B + EW1_B));
+            bulk_g2s(sbase + EOFF_BIAS, image + EOFF_BIAS, EBIAS_B, bar0 + 8 * E2_W);
+            bulk_g2s(sbase + EOFF_W0, image + EOFF_W0, EW0_B + EW1_B, bar0 + 8 * E2_W);
+            bulk_g2s(sbase + EPLANE_B + EOFF_W0, image + EPLANE_B + EOFF_W0, EW0_B + EW1_B, bar0 + 8 * E2_W);
+            mbar_expect_tx(bar0 + 8 * E2_W2, 2 * EW2_B);
+            bulk_g2s(sbase + EOFF_W2, image + EOFF_W2, EW2_B, bar0 + 8 * E2_W2);
+            bulk_g2s(sbase + EPLANE_B + EOFF_W2, image + EPLANE_B + EOFF_W2, EW2_B, bar0 + 8 * E2_W2);
+            mbar_expect_tx(bar0 + 8 * E2_W3, 2 * EW3_B);
+            bulk_g2s(sbase + EOFF_W3, image + EOFF_W3, EW3_B, bar0 + 8 * E2_W3);
+            bulk_g2s(sbase + EPLANE_B + EOFF_W3, image + EPLANE_B + EOFF_W3, EW3_B, bar0 + 8 * E2_W3);
         }
         __syncwarp();
         mbar_wait(bar0 + 8 * E2_W, 0);
@@ -411,6 +419,7 @@ __global__ void __launch_bounds__(THREADS, 1) encode_tc2_kernel(const unsigned c
                 __syncwarp();
             }
             // ---- L2a: A1 (4 K chunks) -> P, rows 0..127 of W2
+            if (it == 0) mbar_wait_spin(bar0 + 8 * E2_W2, 0);
 #pragma unroll 1
             for (int s = 0; s < nslots; ++s) {
                 mbar_wait_spin(bar0 + 8 * (E2_A1 + s), ph_t);
@@ -419,6 +428,7 @@ __global__ void __launch_bounds__(THREADS, 1) encode_tc2_kernel(const unsigned c
                 __syncwarp();
             }
             // ---- L3a: P (8 K chunks, two group pairs) -> Q, then L2b right behind it
+            if (it == 0) mbar_wait_spin(bar0 + 8 * E2_W3, 0);
 #pragma unroll 1
             for (int s = 0; s < nslots; ++s) {
                 const uint32_t A1 = tmem + 256 * s, P = A1 + 64, Q = A1 + 192, bg = bar0 + 8 * (E2_G + 4 * s);

@@ -584,7 +584,9 @@ namespace dif {
 // integrate chain with strided point rows and an optional device-side frame block (dif_integrate: stride 3; dif_frame: stride 9)
 int integrate_launch(const dif_map_view* map, const void* encoder_prepared, const float* xyz, const float* normal, int stride, int64_t n,
                      const dif_frame_params* frame, uint8_t* unq_mask, void* persist, size_t persist_sz, void* scratch, size_t scratch_sz,
-                     int32_t* stats_dev, cudaStream_t st) {
+                     int32_t* stats_dev, cudaStream_t st, cudaEvent_t readers_done) {
+    // readers_done (nullable): recorded on another stream behind kernels that still READ latent_vecs / voxel_obs_count (dif_frame runs the
+    // tracker linearisation beside the index kernels); the only kernel of this chain that writes them, fuse_kernel, waits for it.
     if (!map || !encoder_prepared || !persist || !scratch || !stats_dev || n < 0 || n >= (int64_t(1) << 27)) return DIF_E_INVALID;
     const MapDev m = to_dev(map);
     const int64_t n_cells = m.g.cells();
@@ -630,8 +632,13 @@ int integrate_launch(const dif_map_view* map, const void* encoder_prepared, cons
             prof_end(DIF_PROF_ENCODE, st);
             DIF_COUNT_LAUNCH(3);
         }
-        launch_pdl(fuse_kernel, DIF_NUM_SMS * 8, 256, 0, st, m, S.touched, S.ctr, P.slot_cnt, P.slot_sum, stats_dev);
+        if (readers_done) {        // cross-stream join + plain launch (a programmatic edge cannot carry the second dependency)
+            cudaStreamWaitEvent(st, readers_done, 0);
+            fuse_kernel<<<DIF_NUM_SMS * 8, 256, 0, st>>>(m, S.touched, S.ctr, P.slot_cnt, P.slot_sum, stats_dev);
+            readers_done = nullptr;
+        } else launch_pdl(fuse_kernel, DIF_NUM_SMS * 8, 256, 0, st, m, S.touched, S.ctr, P.slot_cnt, P.slot_sum, stats_dev);
     }
+    if (readers_done) cudaStreamWaitEvent(st, readers_done, 0);       // nothing was fused: still rejoin the caller's stream
     return check_launch("dif_integrate");
 }
 }  // namespace dif
@@ -645,7 +652,7 @@ int dif_integrate(const dif_map_view* map, const void* encoder_prepared, const f
                   const dif_frame_params* frame_dev, uint8_t* unq_mask, void* persist, size_t persist_sz, void* scratch, size_t scratch_sz,
                   int32_t* stats_dev, void* stream) {
     return integrate_launch(map, encoder_prepared, xyz, normal, 3, n, frame_dev, unq_mask, persist, persist_sz, scratch, scratch_sz, stats_dev,
-                            (cudaStream_t)stream);
+                            (cudaStream_t)stream, nullptr);
 }
 
 int dif_map_query(const dif_map_view* map, const float* xyz, int64_t n, int32_t* slot_out, float* rel_out, int32_t* n_valid_dev, void* stream) {
