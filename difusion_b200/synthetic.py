@@ -264,3 +264,23 @@ def s3_view(frame: int, extent: float = S3_EXTENT, n_frames: int = 200):
     pc, nc = box_filter(pc, nc, 0.02)
     nc = nc / np.maximum(np.linalg.norm(nc, axis=1, keepdims=True), 1e-12)
     return pc.astype(np.float32), nc.astype(np.float32), R, t
+
+
+class ReproducibleNoise:
+    """Stand-in for the `torch.randn(n, device=...)` of the reference's latent-optimisation sampling (map.py:486) that two
+    implementations can share: the k-th request of n samples returns numpy default_rng(1000 + k).standard_normal(n) as float32."""
+
+    def __init__(self):
+        self.k = 0
+
+    def numpy(self, n: int) -> np.ndarray:
+        v = np.random.default_rng(1000 + self.k).standard_normal(int(n)).astype(np.float32)
+        self.k += 1
+        return v
+
+    def torch_randn(self, n, device=None, dtype=None, **_):
+        import torch
+        return torch.from_numpy(self.numpy(n)).to(device=device)
+
+    def __call__(self, n, device):
+        return self.torch_randn(n, device=device)

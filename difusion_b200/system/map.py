@@ -11,7 +11,8 @@ Deliberate differences (documented in DESIGN.md):
   * ``n_occupied`` lives on the device; the host value is fetched lazily (the reference syncs ~25 times per integrate);
   * points outside the grid are dropped, counted (``n_frames_with_dropped_points``, ``last_integrate_stats["flags"] & 1``) and
     logged instead of indexing out of range (map.py:313 "will not check index overflow");
-  * the disabled latent-optimisation branch (do_optimize, map.py:456-516, never enabled by main.py:85-86) is not built.
+  * the latent-optimisation branch (do_optimize, map.py:456-516, never enabled by main.py:85-86) is built for the synchronous mode only
+    (``_optimize_latents`` / ``optimize_latent_rows`` over ``dif_latent_grad``); ``async_optimize`` (a forked process) raises.
 """
 from __future__ import annotations
 
@@ -385,8 +386,9 @@ class DenseIndexedMap:
                            async_optimize: bool = False):
         assert surface_xyz.device == surface_normal.device == self.device, \
             f"Device of map {self.device} and input observation {surface_xyz.device, surface_normal.device} must be the same."
-        if do_optimize and getattr(self.args, "optim_n_iters", 0) > 0:
-            raise NotImplementedError("latent optimisation (map.py:456-516) is outside the hot path and not built")
+        if do_optimize and async_optimize:
+            raise NotImplementedError("async_optimize forks a second process with its own decoder copy (map.py:28-78); only the "
+                                      "synchronous latent optimisation is built")
         xyz, nrm = _as_f32(surface_xyz), _as_f32(surface_normal)
         n = xyz.size(0)
         with self.modifying_lock:
@@ -420,7 +422,105 @@ class DenseIndexedMap:
             ev.record(torch.cuda.current_stream(self.device))
             self._stats_inflight.append((self._stats_next, worst))
             self._stats_next = (self._stats_next + 1) % len(self._stats_ring)
-        return unq.view(torch.bool) if prune else None
+            mask = unq.view(torch.bool) if prune else None
+            if do_optimize and getattr(self.args, "optim_n_iters", 0) > 0:       # map.py:456 (the optimise process is never busy in sync mode)
+                self._optimize_latents(xyz, nrm, mask)
+        return mask
+
+    # ------------------------------------------------------------------ latent optimisation (map.py:453-516, 80-117)
+    optim_noise_fn = None       # callable(n, device) -> (n,) f32 standard-normal samples; None = torch.randn (map.py:486)
+
+    def _normalize(self, xyz: torch.Tensor) -> torch.Tensor:
+        """(xyz - bound_min) / voxel_size with the map's scalar-division rule (see scalar_division in __init__)."""
+        z = xyz - self.bound_min.unsqueeze(0)
+        vs = torch.tensor(self.voxel_size, dtype=torch.float32, device=self.device)
+        return z * (1.0 / vs) if self._division_mode == 1 else z / vs          # tensor / tensor is a true division on CUDA too
+
+    def _expand_flatten_id(self, base: torch.Tensor) -> torch.Tensor:
+        """map.py:545-557 with ensure_valid=False: the cells and their (grid-clamped) 6 face neighbours, sorted unique."""
+        pos = self._unlinearize_id(base)
+        out = [base]
+        for off in ((-1, 0, 0), (1, 0, 0), (0, -1, 0), (0, 1, 0), (0, 0, -1), (0, 0, 1)):
+            q = pos + torch.tensor([off], device=self.device)
+            for dim in range(3):
+                q[:, dim].clamp_(0, self.n_xyz[dim] - 1)
+            out.append(self._linearize_id(q))
+        return torch.unique(torch.cat(out))
+
+    def _optimize_latents(self, xyz: torch.Tensor, nrm: torch.Tensor, mask):
+        """Step 3 of integrate_keyframe (map.py:453-516) in synchronous mode: PLIVoxes whose confidence reached encoder_count_th and
+        that were not optimised yet get their latents refined by `optim_n_iters` Adam steps on the decoder's log-likelihood of
+        noisy samples around the frame's surface points.  Index work as torch ops (this branch is disabled in the shipped loop,
+        main.py:85-86); the decoder forward + backward of every iteration is dif_latent_grad."""
+        a = self.args
+        n_occ = self.n_occupied
+        cap = self._cap_ref()
+        obs, pos, opt = self._obs[:cap], self._pos[:cap], self._optimized[:cap]
+        optim_pos = pos[torch.logical_and(obs >= a.encoder_count_th, ~opt)]
+        optim_pos = optim_pos[optim_pos > 0]                                   # (sic, map.py:459: '> 0', cell 0 never qualifies)
+        if optim_pos.size(0) == 0:
+            return
+        p_norm = self._normalize(xyz)
+        if mask is not None:
+            p_norm, nrm = p_norm[mask], nrm[mask]
+        grid_id = self._linearize_id(torch.ceil(p_norm).long() - 1)
+        status = torch.zeros(self._n_cells, dtype=torch.uint8, device=self.device)
+        status[optim_pos] = 1
+        focus = torch.zeros(self._n_cells, dtype=torch.bool, device=self.device)
+        focus[self._expand_flatten_id(optim_pos)] = True
+        fm = focus[grid_id]                                                     # get_pruned_surface (map.py:389-399)
+        p_norm, nrm = p_norm[fm], nrm[fm]
+        noise_fn = self.optim_noise_fn or (lambda n, dev: torch.randn(n, device=dev, dtype=torch.float32))
+        inds, rels, sdfs = [], [], []
+        for off in ((-0.5, -0.5, -0.5), (-0.5, -0.5, 0.5), (-0.5, 0.5, -0.5), (-0.5, 0.5, 0.5),
+                    (0.5, -0.5, -0.5), (0.5, -0.5, 0.5), (0.5, 0.5, -0.5), (0.5, 0.5, 0.5)):
+            gid = torch.ceil(p_norm + torch.tensor(off, device=self.device, dtype=torch.float32)) - 1
+            for dim in range(3):
+                gid[:, dim].clamp_(0, self.n_xyz[dim] - 1)
+            rel = p_norm - gid - 0.5
+            lin = self._linearize_id(gid.long())
+            m = status[lin] >= self.STATUS_CONF_BIT
+            cur_rel, cur_n = rel[m], nrm[m]
+            cur_sdf = noise_fn(cur_rel.size(0), self.device) * 0.05
+            inds.append(self._indexer[lin][m])
+            rels.append(cur_rel + cur_sdf.unsqueeze(-1) * cur_n)
+            sdfs.append(cur_sdf)
+        inds, rels, sdfs = torch.cat(inds), torch.cat(rels).contiguous(), torch.cat(sdfs).contiguous()
+        if inds.numel() == 0:
+            return
+        uniq, inv = torch.unique(inds, return_inverse=True)
+        new_vecs = self.optimize_latent_rows(self._latent[uniq, :LATENT_DIM].contiguous(), inv.contiguous(), sdfs, rels)
+        self._latent[uniq, :LATENT_DIM] = new_vecs                             # _update_optimize_result_set(deintegrate_old=False), map.py:320-336
+        self._dirty[uniq] = 1
+        self._optimized[uniq] = True
+        del n_occ
+
+    def optimize_latent_rows(self, latent_vecs_unique: torch.Tensor, latent_id_inv_mapping: torch.Tensor, gathered_sdf: torch.Tensor,
+                             gathered_relative_xyz: torch.Tensor) -> torch.Tensor:
+        """OptimizeProcess.do_optimize (map.py:80-117): Adam (lr 1e-2, torch defaults) on the unique latent rows; loss = decoder
+        log-likelihood / n_samples (+ code_reg_lambda * sum ||row|| / n_samples per forward_model chunk if code_regularization)."""
+        a = self.args
+        lat = latent_vecs_unique.detach().clone().float().contiguous()
+        inv = latent_id_inv_mapping.long().contiguous()
+        sdf, rel = _as_f32(gathered_sdf), _as_f32(gathered_relative_xyz)
+        n = inv.size(0)
+        n_chunks = max(1, -(-n // int(1.5e6)))                                 # forward_model(max_sample=1.5e6): loss_func runs per chunk
+        m1, m2 = torch.zeros_like(lat), torch.zeros_like(lat)
+        grad = torch.empty_like(lat)
+        lr, b1, b2, eps = 1.0e-2, 0.9, 0.999, 1e-8
+        st = _lib.stream_ptr(self.device)
+        for it in range(1, int(a.optim_n_iters) + 1):
+            grad.zero_()
+            _lib.check(self._L.dif_latent_grad(self._prep.decoder.data_ptr(), lat.data_ptr(), inv.data_ptr(), rel.data_ptr(), sdf.data_ptr(),
+                                               n, n, grad.data_ptr(), None, st), "dif_latent_grad")
+            if getattr(a, "code_regularization", False):                       # d/d row of lambda * ||row|| / n_samples, once per chunk (sic)
+                nrm_r = torch.norm(lat, dim=1, keepdim=True)
+                grad += (float(a.code_reg_lambda) * n_chunks / n) * torch.where(nrm_r > 0, lat / nrm_r, torch.zeros_like(lat))
+            m1.mul_(b1).add_(grad, alpha=1 - b1)                               # torch.optim.Adam, default betas / eps, no weight decay
+            m2.mul_(b2).addcmul_(grad, grad, value=1 - b2)
+            denom = (m2.sqrt() / (1 - b2 ** it) ** 0.5).add_(eps)
+            lat.addcdiv_(m1, denom, value=-lr / (1 - b1 ** it))
+        return lat
 
     # ------------------------------------------------------------------ get_sdf (map.py:559-579)
     def get_sdf(self, xyz: torch.Tensor):

@@ -301,6 +301,14 @@ size_t dif_gn_scratch_bytes(int64_t n_obs);
 int dif_gauss_newton(const dif_map_view* map, const void* decoder_prepared, const dif_gn_problem* problem, void* scratch, size_t scratch_bytes,
                      void* mailbox_host, dif_gn_result* result, void* stream);
 
+/* ---- latent optimisation  (system/map.py:80-117 OptimizeProcess.do_optimize; disabled in the shipped loop) ------
+ * One backward pass of the refinement loss  sum_i -log N(clamp(gt_sdf_i, +-0.2); clamp(sdf_i, +-0.2), std_i) / n_div  through the
+ * decoder into the unique latent rows: sample i decodes latent_u[inv[i]] at rel_xyz[i]; grad_u[inv[i]][:] += d loss / d latent
+ * (grad_u zero-filled by the caller, map.py:102 optimizer.zero_grad); *loss_out += loss (nullable).  n_div = the reference's
+ * n_samples (map.py:86: all gathered samples, also when forward_model splits them into chunks).  Exact fp32. */
+int dif_latent_grad(const void* decoder_prepared, const float* latent_u /*[U][29]*/, const int64_t* inv /*[n]*/, const float* rel_xyz /*[n][3]*/,
+                    const float* gt_sdf /*[n]*/, int64_t n, int64_t n_div, float* grad_u /*[U][29]*/, double* loss_out, void* stream);
+
 /* ---- groupby_sum  (system/ext/indexing/indexing.cu:59-109; indexing.cpp:4) -----------------------------
  * sum[indices[i]][:] += values[i][:];  count[indices[i]] += L  (the reference bumps the count once per column, :70).
  * sum/count must be zero-filled by the caller (the reference allocates zeros, :96-97). */

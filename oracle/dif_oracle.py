@@ -406,3 +406,33 @@ def se3_exp(xi: np.ndarray):
         R = c * np.eye(3) + (1 - c) * np.outer(ax, ax) + s * wedge(ax)
         Jl = (s / ang) * np.eye(3) + (1 - s / ang) * np.outer(ax, ax) + ((1 - c) / ang) * wedge(ax)
     return R, Jl @ rho
+
+
+def optimize_latent_rows(dec, latent_vecs_unique, latent_id_inv_mapping, gathered_sdf, gathered_relative_xyz, n_iters: int,
+                         code_regularization: bool = False, code_reg_lambda: float = 0.0, max_sample: int = int(1.5e6)):
+    """map.py:80-117 (OptimizeProcess.do_optimize) restated on torch CPU autograd: Adam(lr 1e-2) on the unique latent rows;
+    per forward_model chunk (utility.py:86-118) loss = sum(-Normal(clamp(pd_sdf), pd_std).log_prob(clamp(gt))) / n_samples
+    (+ lambda * sum ||row|| / n_samples when code_regularization), gradients of the chunks accumulate.  Pinned against the executed
+    reference function by tests/golden/make_golden_opt.py (tests/golden/latent_opt.npz)."""
+    lat = torch.as_tensor(np.asarray(latent_vecs_unique), dtype=torch.float32).clone().requires_grad_(True)
+    inv = torch.as_tensor(np.asarray(latent_id_inv_mapping), dtype=torch.long)
+    gt_all = torch.as_tensor(np.asarray(gathered_sdf), dtype=torch.float32)
+    xyz = torch.as_tensor(np.asarray(gathered_relative_xyz), dtype=torch.float32)
+    opt = torch.optim.Adam([lat], lr=1.0e-2)
+    n = inv.shape[0]
+    n_chunks = max(1, -(-n // max_sample))
+    for _ in range(n_iters):
+        opt.zero_grad()
+        vec = lat[inv]
+        head = 0
+        for x_chunk, v_chunk in zip(torch.chunk(xyz, n_chunks), torch.chunk(vec, n_chunks)):
+            sdf, std = decoder_forward(dec, v_chunk, x_chunk)
+            gt = torch.clamp(gt_all[head:head + sdf.shape[0]], -0.2, 0.2)
+            ll = -torch.distributions.Normal(loc=torch.clamp(sdf, -0.2, 0.2), scale=std).log_prob(gt)
+            loss = ll.sum() / n
+            if code_regularization:
+                loss = loss + code_reg_lambda * torch.sum(torch.norm(lat, dim=1)) / n
+            loss.backward(retain_graph=True)
+            head += sdf.shape[0]
+        opt.step()
+    return lat.detach().numpy()
