@@ -607,7 +607,19 @@ int integrate_launch(const dif_map_view* map, const void* encoder_prepared, cons
     }
     DIF_COUNT_LAUNCH(1);
     {
-        const int grid = n_chunks < ALLOC_GRID_MAX ? n_chunks : ALLOC_GRID_MAX;
+        // alloc_kernel's CTAs wait for each other (grid-wide spin barrier): the grid must be co-resident.  Bound it by what THIS
+        // device can hold (SM count x occupancy, queried once) instead of assuming a 148-SM part (MIG slices, smaller parts).
+        static int coresident = 0;
+        if (!coresident) {
+            int dev = 0, sms = DIF_NUM_SMS, per_sm = 1;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, alloc_kernel, SCAN_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+            coresident = sms * (per_sm < 4 ? per_sm : 4);
+            if (coresident < 1) coresident = 1;
+            if (coresident > ALLOC_GRID_MAX) coresident = ALLOC_GRID_MAX;
+        }
+        const int grid = n_chunks < coresident ? n_chunks : coresident;
         const int per = (n_chunks + grid - 1) / grid;
         launch_pdl(alloc_kernel, (n_chunks + per - 1) / per, SCAN_THREADS, 0, st, m, P.bitmap, n_words, n_chunks, per, P.alloc_sync, S.ctr, stats_dev);
     }

@@ -95,7 +95,7 @@ def unproject_depth(depth: torch.Tensor, fx: float, fy: float, cx: float, cy: fl
 
 
 _BOX_MAX_CELLS = 1 << 27                 # 2 cm cells: a ~10 m cube of bounding box (16 MB bitmap + 16 MB ranks)
-_box_scratch = {}                        # device -> (zero-filled scratch, points it was sized for)
+_box_scratch = {}                        # (device, stream) -> [zero-filled scratch, points it was sized for, cell budget]
 
 
 def point_box_filter(points: torch.Tensor, normals: torch.Tensor, voxel_size: float):
@@ -103,48 +103,99 @@ def point_box_filter(points: torch.Tensor, normals: torch.Tensor, voxel_size: fl
     _check_input(points, "points")
     _check_input(normals, "normals")
     L, dev, n = _lib.lib(), points.device, points.size(0)
-    sc = _box_scratch.get(dev)
-    if sc is None or sc[1] < n:
-        cap = max(n, 1 << 17)
-        sc = (torch.zeros(L.dif_box_filter_scratch_bytes(cap, _BOX_MAX_CELLS), dtype=torch.uint8, device=dev), cap)
-        _box_scratch[dev] = sc
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
     out_p = torch.empty((n, 3), dtype=torch.float32, device=dev)
     out_n = torch.empty((n, 3), dtype=torch.float32, device=dev)
     n_out = torch.zeros(1, dtype=torch.int32, device=dev)
-    _lib.check(L.dif_point_box_filter(points.data_ptr(), normals.data_ptr(), n, float(voxel_size), _BOX_MAX_CELLS, out_p.data_ptr(),
-                                      out_n.data_ptr(), n_out.data_ptr(), sc[0].data_ptr(), sc[0].numel(), _lib.stream_ptr(dev)), "dif_point_box_filter")
-    m = int(n_out.item())                        # host sync: output shape (the reference syncs at tracker.py:18 and inside unique)
-    if m < 0:
-        raise RuntimeError("point_box_filter: the frame's bounding box exceeds the cell budget of the filter scratch")
-    return out_p[:m], out_n[:m]
+    cells = _BOX_MAX_CELLS
+    for attempt in range(2):
+        sc = _box_scratch.get(key)
+        if sc is None or sc[1] < n or sc[2] < cells:
+            cap = max(n, 1 << 17, sc[1] if sc else 0)
+            sc = [torch.zeros(L.dif_box_filter_scratch_bytes(cap, max(cells, sc[2] if sc else 0)), dtype=torch.uint8, device=dev), cap,
+                  max(cells, sc[2] if sc else 0)]
+            _box_scratch[key] = sc
+        _lib.check(L.dif_point_box_filter(points.data_ptr(), normals.data_ptr(), n, float(voxel_size), sc[2], out_p.data_ptr(),
+                                          out_n.data_ptr(), n_out.data_ptr(), sc[0].data_ptr(), sc[0].numel(), _lib.stream_ptr(dev)), "dif_point_box_filter")
+        m = int(n_out.item())                    # host sync: output shape (the reference syncs at tracker.py:18 and inside unique)
+        if m >= 0:
+            return out_p[:m], out_n[:m]
+        # the frame's bounding box does not fit the bitmap: size it from the actual extent (tracker.py:18 adds 16 cells per axis) and retry once
+        ext_ = (points.amax(dim=0) - points.amin(dim=0)).double().cpu().numpy()
+        need = 1
+        for e in ext_:
+            need *= int(e / float(voxel_size)) + 18
+        cells = 1 << max(need - 1, 1).bit_length()
+        if attempt == 1 or cells > (1 << 29):
+            break
+    raise RuntimeError("point_box_filter: the frame's bounding box exceeds the cell budget of the filter scratch")
 
 
 _KNN_MAX_CELLS = 1 << 23                 # cell edge = search radius: 5 cm cells cover a ~10 m cube of bounding box
-_knn_scratch = {}
+_KNN_CELLS_LIMIT = 1 << 30               # hard ceiling of the on-demand growth below (a ~50 m cube at 5 cm)
+_knn_scratch = {}                        # (device, stream) -> [zero-filled scratch, points it was sized for, cell budget]
 
 
-def _knn_buffers(dev, n):
+def _knn_key(dev):
+    return (dev, torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _knn_buffers(dev, n, min_cells=_KNN_MAX_CELLS):
+    """Scratch of the neighbour grid for `n` points: per (device, stream), grown on demand.  -> (tensor, cell budget)"""
     L = _lib.lib()
-    sc = _knn_scratch.get(dev)
-    if sc is None or sc[1] < n:
-        cap = max(n, 1 << 17)
-        sc = (torch.zeros(L.dif_knn_scratch_bytes(cap, _KNN_MAX_CELLS), dtype=torch.uint8, device=dev), cap)
-        _knn_scratch[dev] = sc
-    return sc[0]
+    key = _knn_key(dev)
+    sc = _knn_scratch.get(key)
+    if sc is None or sc[1] < n or sc[2] < min_cells:
+        cap = max(n, 1 << 17, sc[1] if sc else 0)
+        cells = max(min_cells, sc[2] if sc else 0)
+        sc = [torch.zeros(L.dif_knn_scratch_bytes(cap, cells), dtype=torch.uint8, device=dev), cap, cells]
+        _knn_scratch[key] = sc
+    return sc[0], sc[2]
+
+
+def _knn_cells_needed(input_pc: torch.Tensor, cell: float) -> int:
+    """Cells of edge `cell` covering the finite points' bounding box (with the kernels' one-cell margin): the overflow path only."""
+    p = input_pc[:, :3]
+    ok = torch.isfinite(p).all(dim=1)
+    if not bool(ok.any()):
+        return 1
+    p = p[ok]
+    ext_ = (p.amax(dim=0) - p.amin(dim=0)).double().cpu().numpy()
+    n = 1
+    for e in ext_:
+        n *= int(e / cell) + 4
+    return n
+
+
+def _knn_call(fn_name, input_pc, cell, call):
+    """Run a neighbour-grid kernel; if the cloud's bounding box does not fit the cell budget of the scratch (a single far or noisy depth
+    pixel is enough: the reference's kd-tree has no such limit), size the budget from the actual extent and run again."""
+    dev, n = input_pc.device, input_pc.size(0)
+    sc, cells = _knn_buffers(dev, n)
+    status = call(sc, cells)
+    if int(status.item()):
+        need = _knn_cells_needed(input_pc, cell)
+        if need > _KNN_CELLS_LIMIT:
+            raise RuntimeError(f"{fn_name}: the cloud's bounding box needs {need} neighbour cells (limit {_KNN_CELLS_LIMIT})")
+        sc, cells = _knn_buffers(dev, n, 1 << max(need - 1, 1).bit_length())
+        status = call(sc, cells)
+        if int(status.item()):
+            raise RuntimeError(f"{fn_name}: the cloud's bounding box exceeds the neighbour grid budget")
 
 
 def remove_radius_outlier(input_pc: torch.Tensor, nb_points: int, radius: float):
     """(N,4) [or (N,3)] f32 -> (N,) bool: the nb_points-th nearest point (self included) lies within `radius` (pcproc.cu:172-196)."""
     _check_input(input_pc, "input_pc")
     dev, n = input_pc.device, input_pc.size(0)
-    sc = _knn_buffers(dev, n)
     mask = torch.empty(n, dtype=torch.uint8, device=dev)
-    status = torch.zeros(1, dtype=torch.int32, device=dev)
-    _lib.check(_lib.lib().dif_remove_radius_outlier(input_pc.data_ptr(), input_pc.size(1), n, int(nb_points), float(radius), _KNN_MAX_CELLS,
-                                                    mask.data_ptr(), status.data_ptr(), sc.data_ptr(), sc.numel(), _lib.stream_ptr(dev)),
-               "dif_remove_radius_outlier")
-    if int(status.item()):
-        raise RuntimeError("remove_radius_outlier: the cloud's bounding box exceeds the neighbour grid budget")
+
+    def call(sc, cells):
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        _lib.check(_lib.lib().dif_remove_radius_outlier(input_pc.data_ptr(), input_pc.size(1), n, int(nb_points), float(radius), cells,
+                                                        mask.data_ptr(), status.data_ptr(), sc.data_ptr(), sc.numel(), _lib.stream_ptr(dev)),
+                   "dif_remove_radius_outlier")
+        return status
+    _knn_call("remove_radius_outlier", input_pc, float(radius), call)
     return mask.view(torch.bool)
 
 
@@ -153,12 +204,13 @@ def estimate_normals(input_pc: torch.Tensor, max_nn: int, radius: float, cam_xyz
     cam_xyz; NaN rows where fewer than 5 neighbours exist (pcproc.cu:107-170,198-220)."""
     _check_input(input_pc, "input_pc")
     dev, n = input_pc.device, input_pc.size(0)
-    sc = _knn_buffers(dev, n)
     normals = torch.empty((n, 3), dtype=torch.float32, device=dev)
-    status = torch.zeros(1, dtype=torch.int32, device=dev)
-    _lib.check(_lib.lib().dif_estimate_normals(input_pc.data_ptr(), input_pc.size(1), n, int(max_nn), float(radius), _lib.host_floats(cam_xyz),
-                                               _KNN_MAX_CELLS, normals.data_ptr(), status.data_ptr(), sc.data_ptr(), sc.numel(),
-                                               _lib.stream_ptr(dev)), "dif_estimate_normals")
-    if int(status.item()):
-        raise RuntimeError("estimate_normals: the cloud's bounding box exceeds the neighbour grid budget")
+
+    def call(sc, cells):
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        _lib.check(_lib.lib().dif_estimate_normals(input_pc.data_ptr(), input_pc.size(1), n, int(max_nn), float(radius), _lib.host_floats(cam_xyz),
+                                                   cells, normals.data_ptr(), status.data_ptr(), sc.data_ptr(), sc.numel(),
+                                                   _lib.stream_ptr(dev)), "dif_estimate_normals")
+        return status
+    _knn_call("estimate_normals", input_pc, float(radius), call)
     return normals
