@@ -535,8 +535,6 @@ def main():
         k_next = p.upload(src[0], n_pts[0])
         for f in range(K):
             k = k_next
-            if f + 1 < K:                                              # the next frame's copy overlaps with this frame's kernels
-                k_next = p.upload(src[f + 1], n_pts[f + 1])
             if timed_events is not None:
                 flush.zero_()
                 timed_events[f][0].record(main_s)
@@ -547,6 +545,8 @@ def main():
             p.launch(k, track=f >= 1)
             if timed_events is not None:
                 timed_events[f][1].record(main_s)
+            if f + 1 < K:                                              # the next frame's copy (issued right behind this frame's launch, so that
+                k_next = p.upload(src[f + 1], n_pts[f + 1])            # its host-side cost is off the launch path) overlaps with this frame's kernels
             if sync_each or collect is not None:
                 icp, st = p.sync()
                 if collect is not None:
