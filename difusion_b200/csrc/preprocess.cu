@@ -39,6 +39,8 @@ struct BoxState {                       // lives in the scratch buffer
     int n_cells;                        // occupied cells = output rows
 };
 
+__device__ __forceinline__ bool row_is_nan(const float* q) { return q[0] != q[0] || q[1] != q[1] || q[2] != q[2]; }
+
 __device__ __forceinline__ void atomic_min_f(float* a, float v) {
     int old = __float_as_int(*a);
     while (v < __int_as_float(old)) { const int assumed = old; old = atomicCAS((int*)a, assumed, __float_as_int(v)); if (old == assumed) break; }
@@ -93,7 +95,7 @@ __device__ __forceinline__ long long box_key(const BoxState* s, const float* p, 
 
 __global__ void box_mark_kernel(const float* __restrict__ p, int n, const BoxState* __restrict__ s, float voxel, uint32_t* __restrict__ bitmap) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || s->overflow) return;
+    if (i >= n || s->overflow || row_is_nan(p + 3 * i)) return;
     const long long key = box_key(s, p + 3 * i, voxel);
     atomicOr(bitmap + (key >> 5), 1u << (key & 31));
 }
@@ -159,7 +161,7 @@ __global__ void box_link_kernel(const float* __restrict__ p, int n, const BoxSta
                                 const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ word_rank,
                                 const uint32_t* __restrict__ chunk_sum, int* __restrict__ head, int* __restrict__ next) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || s->overflow) return;
+    if (i >= n || s->overflow || row_is_nan(p + 3 * i)) return;
     const long long key = box_key(s, p + 3 * i, voxel);
     const long long w = key >> 5;
     const uint32_t rank = chunk_sum[w / BOX_SCAN_W] + word_rank[w] + __popc(bitmap[w] & ((1u << (key & 31)) - 1u));
@@ -191,7 +193,7 @@ __global__ void box_finalize_kernel(const float* __restrict__ p, const float* __
 
 __global__ void box_unmark_kernel(const float* __restrict__ p, int n, const BoxState* __restrict__ s, float voxel, uint32_t* __restrict__ bitmap) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || s->overflow) return;
+    if (i >= n || s->overflow || row_is_nan(p + 3 * i)) return;
     const long long key = box_key(s, p + 3 * i, voxel);
     bitmap[key >> 5] = 0u;
 }
@@ -298,6 +300,7 @@ __device__ __forceinline__ int knn_cell(const BoxState* s, const float* p, float
 __global__ void knn_count_kernel(const float* __restrict__ p, int stride, int n, const BoxState* __restrict__ s, float cell, uint32_t* __restrict__ cell_count) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || s->overflow) return;
+    if (row_is_nan(p + (size_t)stride * i)) return;                  // a NaN row is "no point here" (un-compacted clouds, see dif_*  docs)
     atomicAdd(cell_count + knn_cell(s, p + (size_t)stride * i, cell), 1u);
 }
 
@@ -365,6 +368,7 @@ __global__ void knn_fill_kernel(const float* __restrict__ p, int stride, int n, 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || s->overflow) return;
     const float* q = p + (size_t)stride * i;
+    if (row_is_nan(q)) return;
     const uint32_t dst = atomicAdd(cell_fill + knn_cell(s, q, cell), 1u);
     sorted_idx[dst] = i;
     sorted_pt[dst] = make_float4(q[0], q[1], q[2], __int_as_float(i));
@@ -391,6 +395,7 @@ __global__ void radius_count_kernel(const float* __restrict__ p, int stride, int
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || s->overflow) return;
     const float* q = p + (size_t)stride * i;
+    if (row_is_nan(q)) { mask[i] = 0; return; }
     const float qx = q[0], qy = q[1], qz = q[2];
     const int cx = knn_axis(s, qx, 0, cell), cy = knn_axis(s, qy, 1, cell), cz = knn_axis(s, qz, 2, cell);
     int found = 0;
@@ -457,6 +462,7 @@ __global__ void __launch_bounds__(NRM_WARPS * 32) estimate_normals_kernel(const 
     const int i = blockIdx.x * NRM_WARPS + (threadIdx.x >> 5);
     if (i >= n || s->overflow) return;                              // warp-uniform
     const float* q = p + (size_t)stride * i;
+    if (row_is_nan(q)) { if (lane < 3) normal_out[3 * i + lane] = __int_as_float(0x7fc00000); return; }      // warp-uniform
     const float qx = q[0], qy = q[1], qz = q[2];
     const int cx = knn_axis(s, qx, 0, cell), cy = knn_axis(s, qy, 1, cell), cz = knn_axis(s, qz, 2, cell);
     const float inf = __int_as_float(0x7f800000);

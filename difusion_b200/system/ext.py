@@ -98,8 +98,10 @@ _BOX_MAX_CELLS = 1 << 27                 # 2 cm cells: a ~10 m cube of bounding 
 _box_scratch = {}                        # (device, stream) -> [zero-filled scratch, points it was sized for, cell budget]
 
 
-def point_box_filter(points: torch.Tensor, normals: torch.Tensor, voxel_size: float):
-    """tracker.point_box_filter (tracker.py:13-23): (N,3),(N,3) -> (M,3),(M,3) per-cell means, cells in ascending key order."""
+def point_box_filter(points: torch.Tensor, normals: torch.Tensor, voxel_size: float, deferred: bool = False):
+    """tracker.point_box_filter (tracker.py:13-23): (N,3),(N,3) -> (M,3),(M,3) per-cell means, cells in ascending key order.
+    Rows with a NaN coordinate are skipped.  deferred=True: no host sync - returns (out_p (N,3), out_n (N,3), n_out device int32[1]);
+    the first n_out rows are valid, n_out < 0 flags a bounding box beyond the scratch's cell budget."""
     _check_input(points, "points")
     _check_input(normals, "normals")
     L, dev, n = _lib.lib(), points.device, points.size(0)
@@ -117,6 +119,8 @@ def point_box_filter(points: torch.Tensor, normals: torch.Tensor, voxel_size: fl
             _box_scratch[key] = sc
         _lib.check(L.dif_point_box_filter(points.data_ptr(), normals.data_ptr(), n, float(voxel_size), sc[2], out_p.data_ptr(),
                                           out_n.data_ptr(), n_out.data_ptr(), sc[0].data_ptr(), sc[0].numel(), _lib.stream_ptr(dev)), "dif_point_box_filter")
+        if deferred:
+            return out_p, out_n, n_out
         m = int(n_out.item())                    # host sync: output shape (the reference syncs at tracker.py:18 and inside unique)
         if m >= 0:
             return out_p[:m], out_n[:m]
@@ -183,8 +187,11 @@ def _knn_call(fn_name, input_pc, cell, call):
             raise RuntimeError(f"{fn_name}: the cloud's bounding box exceeds the neighbour grid budget")
 
 
-def remove_radius_outlier(input_pc: torch.Tensor, nb_points: int, radius: float):
-    """(N,4) [or (N,3)] f32 -> (N,) bool: the nb_points-th nearest point (self included) lies within `radius` (pcproc.cu:172-196)."""
+def remove_radius_outlier(input_pc: torch.Tensor, nb_points: int, radius: float, status_out: list = None):
+    """(N,4) [or (N,3)] f32 -> (N,) bool: the nb_points-th nearest point (self included) lies within `radius` (pcproc.cu:172-196).
+    Rows with a NaN coordinate are "no point": they are nobody's neighbour and their mask is False (an un-compacted cloud gives the
+    same masks for its valid rows as the compacted one).  status_out (list): no host sync - the overflow flag (device int32) is
+    appended for the caller to check later instead of growing the cell budget here."""
     _check_input(input_pc, "input_pc")
     dev, n = input_pc.device, input_pc.size(0)
     mask = torch.empty(n, dtype=torch.uint8, device=dev)
@@ -195,13 +202,17 @@ def remove_radius_outlier(input_pc: torch.Tensor, nb_points: int, radius: float)
                                                         mask.data_ptr(), status.data_ptr(), sc.data_ptr(), sc.numel(), _lib.stream_ptr(dev)),
                    "dif_remove_radius_outlier")
         return status
-    _knn_call("remove_radius_outlier", input_pc, float(radius), call)
+    if status_out is not None:
+        status_out.append(call(*_knn_buffers(dev, n)))
+    else:
+        _knn_call("remove_radius_outlier", input_pc, float(radius), call)
     return mask.view(torch.bool)
 
 
-def estimate_normals(input_pc: torch.Tensor, max_nn: int, radius: float, cam_xyz):
+def estimate_normals(input_pc: torch.Tensor, max_nn: int, radius: float, cam_xyz, status_out: list = None):
     """(N,4) [or (N,3)] f32 -> (N,3) f32 PCA normals over the <= max_nn-1 nearest neighbours within `radius`, oriented towards
-    cam_xyz; NaN rows where fewer than 5 neighbours exist (pcproc.cu:107-170,198-220)."""
+    cam_xyz; NaN rows where fewer than 5 neighbours exist (pcproc.cu:107-170,198-220).  NaN input rows are "no point" (NaN normal);
+    status_out as in remove_radius_outlier."""
     _check_input(input_pc, "input_pc")
     dev, n = input_pc.device, input_pc.size(0)
     normals = torch.empty((n, 3), dtype=torch.float32, device=dev)
@@ -212,5 +223,8 @@ def estimate_normals(input_pc: torch.Tensor, max_nn: int, radius: float, cam_xyz
                                                    cells, normals.data_ptr(), status.data_ptr(), sc.data_ptr(), sc.numel(),
                                                    _lib.stream_ptr(dev)), "dif_estimate_normals")
         return status
-    _knn_call("estimate_normals", input_pc, float(radius), call)
+    if status_out is not None:
+        status_out.append(call(*_knn_buffers(dev, n)))
+    else:
+        _knn_call("estimate_normals", input_pc, float(radius), call)
     return normals

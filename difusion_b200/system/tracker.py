@@ -42,7 +42,8 @@ class SDFTracker:
         self.all_pd_pose = []
         self.last_processed_pc = None
         self.cur_gt_pose = None
-        self.last_colored_pcd = None
+        self._colored = None
+        self.compacting_front_end = os.environ.get("DIF_FRONT_END", "masked") == "compacting"     # reference-shaped front end (6 host syncs)
         self.n_unstable = 0
         self._rgb_scratch = None
         self._pin = None
@@ -269,14 +270,12 @@ class SDFTracker:
         self.all_pd_pose.append(final_pose)
         return final_pose
 
-    def track_camera(self, rgb_data: torch.Tensor, depth_data: torch.Tensor, calib, set_pose: Isometry = None) -> Isometry:
-        """tracker.py:74-129.  rgb (H,W,3) f32, depth (H,W) f32 with NaN = invalid, calib: fx/fy/cx/cy + to_K()."""
+    def _preprocess_compacting(self, cur_depth0: torch.Tensor, rgb_data: torch.Tensor, calib):
+        """tracker.py:88-117 statement by statement: three boolean-mask compactions + the ops' own status checks = 6 host syncs."""
         F = torch.nn.functional
-        cur_intensity = torch.mean(rgb_data, dim=-1)
-        cur_intensity, cur_depth, cur_dIdxy = self._make_image_pyramid(cur_intensity, depth_data)
         cur_rgb = rgb_data.permute(2, 0, 1)
         pc_scale = self.sdf_args.subsample
-        pc_data = F.interpolate(cur_depth[0].unsqueeze(0).unsqueeze(0), scale_factor=pc_scale, mode="nearest",
+        pc_data = F.interpolate(cur_depth0.unsqueeze(0).unsqueeze(0), scale_factor=pc_scale, mode="nearest",
                                 recompute_scale_factor=False).squeeze(0).squeeze(0).contiguous()
         cur_rgb = F.interpolate(cur_rgb.unsqueeze(0), scale_factor=pc_scale, mode="bilinear", recompute_scale_factor=False).squeeze(0)
         pc_data = _ext.unproject_depth(pc_data, calib.fx * pc_scale, calib.fy * pc_scale, calib.cx * pc_scale, calib.cy * pc_scale)
@@ -284,14 +283,69 @@ class SDFTracker:
         cur_rgb = cur_rgb.permute(1, 2, 0).reshape(-1, 3)
         nan_mask = ~torch.isnan(pc_data[..., 0])
         pc_data, cur_rgb = pc_data[nan_mask], cur_rgb[nan_mask]
-        with torch.cuda.device(self.map.device):
+        with torch.cuda.device(pc_data.device):
             valid = _ext.remove_radius_outlier(pc_data.contiguous(), 16, 0.05)
             pc_data, cur_rgb = pc_data[valid], cur_rgb[valid]
             normal_data = _ext.estimate_normals(pc_data.contiguous(), 16, 0.1, [0.0, 0.0, 0.0])
             normal_valid = ~torch.isnan(normal_data[..., 0])
             normal_data, cur_rgb, pc_data = normal_data[normal_valid], cur_rgb[normal_valid], pc_data[normal_valid, :3]
-        self.last_colored_pcd = [pc_data, cur_rgb]
-        pc_data, normal_data = point_box_filter(pc_data, normal_data, 0.02)
+        self._colored = (pc_data, cur_rgb, None)
+        return point_box_filter(pc_data, normal_data, 0.02)
+
+    def _preprocess_masked(self, cur_depth0: torch.Tensor, rgb_data: torch.Tensor, calib):
+        """The same front end without compaction: invalid pixels, outliers and points without a normal stay in place as NaN rows
+        (the kernels treat a NaN row as "no point": the neighbour sets, the (distance, index) tie-breaks and the exact per-cell sums
+        of the valid rows are those of the compacted cloud, so the result is bit-identical), the ops' overflow flags and the row
+        count stay on the device, and ONE readback at the end returns them: 1 host sync instead of 6.  Returns None when a flag is
+        set (the caller then runs the compacting path, which grows the cell budgets)."""
+        F = torch.nn.functional
+        pc_scale = self.sdf_args.subsample
+        d = F.interpolate(cur_depth0.unsqueeze(0).unsqueeze(0), scale_factor=pc_scale, mode="nearest",
+                          recompute_scale_factor=False).squeeze(0).squeeze(0).contiguous()
+        pc3 = _ext.unproject_depth(d, calib.fx * pc_scale, calib.fy * pc_scale, calib.cx * pc_scale, calib.cy * pc_scale).reshape(-1, 3)
+        nan3 = torch.full_like(pc3, float("nan"))
+        status = []
+        with torch.cuda.device(pc3.device):
+            valid = _ext.remove_radius_outlier(pc3, 16, 0.05, status_out=status)
+            pc3 = torch.where(valid.unsqueeze(-1), pc3, nan3)
+            normals = _ext.estimate_normals(pc3, 16, 0.1, [0.0, 0.0, 0.0], status_out=status)
+            ok = ~torch.isnan(normals[:, 0])
+            pc3 = torch.where(ok.unsqueeze(-1), pc3, nan3)
+            out_p, out_n, n_out = _ext.point_box_filter(pc3, normals, 0.02, deferred=True)
+            flags = torch.cat([n_out] + status).cpu().tolist()          # the front end's only host sync
+        if flags[0] < 0 or flags[1] or flags[2]:
+            return None
+        self._colored = (pc3, rgb_data, pc_scale)                       # last_colored_pcd is compacted on demand
+        return out_p[:flags[0]], out_n[:flags[0]]
+
+    @property
+    def last_colored_pcd(self):
+        """tracker.py:115: [points (M,3), colours (M,3)] of the cloud before the box filter (texture export); built on first access."""
+        c = self._colored
+        if c is None:
+            return None
+        if c[2] is None:
+            return [c[0], c[1]]
+        pc3, rgb_data, pc_scale = c
+        F = torch.nn.functional
+        cur_rgb = F.interpolate(rgb_data.permute(2, 0, 1).unsqueeze(0), scale_factor=pc_scale, mode="bilinear",
+                                recompute_scale_factor=False).squeeze(0).permute(1, 2, 0).reshape(-1, 3)
+        keep = ~torch.isnan(pc3[:, 0])
+        self._colored = (pc3[keep], cur_rgb[keep], None)
+        return [self._colored[0], self._colored[1]]
+
+    @last_colored_pcd.setter
+    def last_colored_pcd(self, v):
+        self._colored = None if v is None else (v[0], v[1], None)
+
+    def track_camera(self, rgb_data: torch.Tensor, depth_data: torch.Tensor, calib, set_pose: Isometry = None) -> Isometry:
+        """tracker.py:74-129.  rgb (H,W,3) f32, depth (H,W) f32 with NaN = invalid, calib: fx/fy/cx/cy + to_K()."""
+        cur_intensity = torch.mean(rgb_data, dim=-1)
+        cur_intensity, cur_depth, cur_dIdxy = self._make_image_pyramid(cur_intensity, depth_data)
+        res = None if self.compacting_front_end else self._preprocess_masked(cur_depth[0], rgb_data, calib)
+        if res is None:
+            res = self._preprocess_compacting(cur_depth[0], rgb_data, calib)
+        pc_data, normal_data = res
         self.last_processed_pc = [pc_data, normal_data]
         if set_pose is not None:
             final_pose = set_pose

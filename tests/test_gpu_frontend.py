@@ -426,3 +426,33 @@ def test_far_point_does_not_break_the_front_end(dev):
     assert p2.size(0) == q2.size(0) + 1
     e_p, e_n = S.box_filter(far, np.concatenate([nc[:20000], nc[:1]], 0), 0.02)
     assert np.array_equal(p2.cpu().numpy(), e_p) and np.array_equal(n2.cpu().numpy(), e_n)
+
+
+def test_masked_front_end_equals_compacting_front_end(dev):
+    """track_camera's default front end keeps invalid pixels / outliers / normal-less points in place as NaN rows and reads ONE
+    device block back (row count + overflow flags); the reference-shaped one compacts three times (6 host syncs).  The kernels treat
+    a NaN row as "no point", so the processed cloud, its normals and the coloured cloud are bit-identical."""
+    from difusion_b200 import synthetic as S
+    from difusion_b200.system.tracker import SDFTracker
+    sc = S.scene_S1(0.05)
+    args = argparse.Namespace(sdf=dict(robust_kernel="huber", robust_k=5.0, subsample=0.5),
+                              rgb=dict(weight=500.0, robust_kernel=None, robust_k=0.01, min_grad_scale=0.0, max_depth_delta=0.2),
+                              iter_config=[{"n": 2, "type": [["sdf"]]}])
+    calib = _Calib(S.ICL_FX, S.ICL_FY, S.ICL_CX, S.ICL_CY)
+    from difusion_b200.utils.motion_util import Isometry, Rotation
+    for f in (0, 40):
+        R, t = S.orbit_pose(f, 200)
+        rgb, depth = S.render_rgbd(sc, R, t, step=1)
+        depth = depth.copy()
+        depth[100:140, 200:260] = np.nan                             # a hole, plus the scene's own invalid pixels
+        gt = Isometry(q=Rotation(matrix=R), t=t)
+        out = []
+        for compacting in (False, True):
+            trk = SDFTracker(None, args)
+            trk.compacting_front_end = compacting
+            trk.track_camera(_t(rgb, dev), _t(depth, dev), calib, set_pose=gt)
+            out.append((trk.last_processed_pc, trk.last_colored_pcd))
+        (pa, ca), (pb, cb) = out
+        assert pa[0].shape == pb[0].shape and pa[0].size(0) > 15000
+        assert torch.equal(pa[0], pb[0]) and torch.equal(pa[1], pb[1])
+        assert torch.equal(ca[0], cb[0]) and torch.equal(ca[1], cb[1])
