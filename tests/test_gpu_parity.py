@@ -620,3 +620,31 @@ def test_device_mesh_cache_merge_matches_reference_host_merge(golden, model, dev
     b = set(map(bytes, np.unique(v_full[np.isin(id_full, upd_ids)], axis=0)))
     assert a.shape[0] > 500 and sum(bytes(r) in b for r in a) > 0.8 * a.shape[0]
     assert set(np.unique(id_inc[np.isin(id_inc, upd_ids)]).tolist()) <= set(upd_ids.tolist())
+
+
+def test_config5_terrain_against_oracle(model, dev, oracle_weights):
+    """BASELINE configs[4] / SURVEY 8(d) scene S3 (the 5 cm height field the sharded stream runs on), built with bulk integrate_keyframe
+    calls exactly as bench.py's config-5 extra builds it, against the CPU oracle: integer state bit-exact, latents at the stated bar.
+    Default: the FULL map (50 m x 50 m, 1000 x 1000 x 40 grid, 6.15 M points, 2.98 M allocated / 2.49 M observed PLIVoxes; ~35 s, nearly
+    all of it the CPU oracle; measured max |latent - oracle| 1.1e-5); DIF_TEST_S3_EXTENT=25 runs a quarter of the area in ~10 s."""
+    import os
+    from difusion_b200 import synthetic as S
+    from difusion_b200.system.map import DenseIndexedMap
+    from oracle import dif_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    ext = float(os.environ.get("DIF_TEST_S3_EXTENT", "50"))
+    sc = S.scene_S3(extent=ext)
+    m = DenseIndexedMap(model, sc.map_args(), 29, dev, initial_capacity=1 << 20)
+    o = O.OracleMap(oracle_weights, sc.map_args())
+    for p, n in S.s3_terrain_points(extent=ext, rows_per_batch=200):
+        mask = m.integrate_keyframe(torch.from_numpy(p).to(dev), torch.from_numpy(n).to(dev))
+        o_mask = o.integrate_keyframe(p, n)
+        assert np.array_equal(mask.cpu().numpy(), o_mask)
+    n_occ = o.n_occupied
+    assert m.n_occupied == n_occ and n_occ > 700_000 * (ext / 25.0) ** 2
+    assert np.array_equal(m.indexer.cpu().numpy(), o.indexer)
+    assert np.array_equal(m.latent_vecs_pos.cpu().numpy()[:n_occ], o.latent_vecs_pos[:n_occ])
+    assert np.array_equal(m.voxel_obs_count.cpu().numpy()[:n_occ], o.voxel_obs_count[:n_occ])
+    lat, ref = m.latent_vecs.cpu().numpy()[:n_occ], o.latent_vecs[:n_occ]
+    assert close(lat, ref), float(np.abs(lat - ref).max())
+    print(f"[config 5] extent {ext} m: {n_occ} PLIVoxes, {int((o.voxel_obs_count[:n_occ] > 0).sum())} observed; max |latent - oracle| {np.abs(lat - ref).max():.2e}")
