@@ -15,6 +15,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 namespace dif {
 int icp_launch(const dif_map_view* map, const void* decoder_prepared, const float* obs_xyz, int obs_stride, int64_t n, const float* pose_host,
@@ -228,15 +229,23 @@ int dif_gauss_newton(const dif_map_view* map, const void* decoder_prepared, cons
             if (rc) return rc;
             // wait for this iteration's verdict: spin on the mailbox word the update kernel posts (no stream synchronisation)
             unsigned long long w = 0;
+            timespec t_start; clock_gettime(CLOCK_MONOTONIC, &t_start);
             for (unsigned long long spins = 0;; ++spins) {
                 w = mb[0];
                 if ((w >> 8) == seq) break;
-                if ((spins & 0xfffff) == 0xfffff) {                 // every ~1 M polls: has the stream died or drained without posting?
+                if ((spins & 0xfffff) == 0xfffff) {                 // every ~1 M polls: has the stream died, drained without posting, or hung?
                     const cudaError_t q = cudaStreamQuery(st);
                     if (q != cudaErrorNotReady) {
                         w = mb[0];
                         if ((w >> 8) == seq) break;
+                        snprintf(g_last_error, sizeof(g_last_error), "dif_gauss_newton: the stream %s before iteration %llu posted its verdict",
+                                 q == cudaSuccess ? "drained" : cudaGetErrorString(q), seq);
                         if (q != cudaSuccess) { (void)cudaGetLastError(); }
+                        return DIF_E_LAUNCH;
+                    }
+                    timespec now; clock_gettime(CLOCK_MONOTONIC, &now);
+                    if ((now.tv_sec - t_start.tv_sec) > 30) {        // one iteration is tens of microseconds
+                        snprintf(g_last_error, sizeof(g_last_error), "dif_gauss_newton: no verdict for iteration %llu after 30 s", seq);
                         return DIF_E_LAUNCH;
                     }
                 }
