@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(MLP_THREADS) icp_linearize_kernel(
                 const float r = r_s[t];
                 float w = 1.f;
                 if (huber_k > 0.f) { const float ar = fabsf(r); if (ar > huber_k) w = huber_k / ar; }       // tracker.py:59-65
+                else if (huber_k < 0.f) { const float q = r / -huber_k, t1 = 1.f - q * q; w = fabsf(r) <= -huber_k ? t1 * t1 : 0.f; }   // Tukey (:66-69)
                 v[27] = r * (r * w);                             // energy term  (:210)
                 v[28] = 1.f;
                 if (want_grad) {

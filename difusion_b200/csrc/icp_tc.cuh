@@ -366,6 +366,7 @@ __global__ void __launch_bounds__(THREADS, 1) icp_tc_kernel(const unsigned char*
                 if (valid) {
                     float w = 1.f;
                     if (a.huber_k > 0.f) { const float ar = fabsf(r); if (ar > a.huber_k) w = a.huber_k / ar; }
+                    else if (a.huber_k < 0.f) { const float q = r / -a.huber_k, t1 = 1.f - q * q; w = fabsf(r) <= -a.huber_k ? t1 * t1 : 0.f; }      // Tukey (tracker.py:66-69)
                     v[27] = r * (r * w);
                     v[28] = 1.f;
                     if (a.want_grad) {

@@ -67,12 +67,21 @@ class SDFTracker:
         self._pin_ev.synchronize()
         return self._pin_np.copy()
 
+    def _sdf_robust_k(self) -> float:
+        """tracker.py:58-71 for the sdf term, in the ABI's encoding: > 0 Huber(k), < 0 Tukey(-k), 0 no robust kernel."""
+        kind, k = self.sdf_args.robust_kernel, float(self.sdf_args.robust_k or 0.0)
+        if kind is None:
+            return 0.0
+        if kind not in ("huber", "tukey"):
+            raise NotImplementedError(kind)                                 # as tracker.py:70-71
+        if not k > 0.0:
+            raise ValueError("robust_k must be positive")
+        return k if kind == "huber" else -k
+
     # -------------------------------------------------------------------------------------------------
     def compute_sdf_Hg(self, n_iter: int, last_pose: Isometry, cur_delta_pose: Isometry, obs_xyz: torch.Tensor, no_grad: bool = False):
         """tracker.py:174-218.  Returns (H (6,6) float64 ndarray, g (6,) float64, energy float); (None, None, energy) if no_grad."""
-        k = self.sdf_args.robust_k if self.sdf_args.robust_kernel is not None else 0.0
-        if self.sdf_args.robust_kernel not in (None, "huber"):
-            raise NotImplementedError("only the huber kernel is built (fusion-lr-kt.yaml:47)")
+        k = self._sdf_robust_k()
         out = self.map.icp_linearize(obs_xyz, last_pose.q.rotation_matrix, last_pose.t, cur_delta_pose.q.rotation_matrix,
                                      cur_delta_pose.t, huber_k=k, want_grad=not no_grad)
         self.n_sdf_linearisations += 1
@@ -146,9 +155,7 @@ class SDFTracker:
                 x = x.float().contiguous()
             p.obs_xyz, p.n_obs = x.data_ptr(), x.size(0)
         dev = x.device if x is not None else cur_intensity_pyramid[0].device
-        if self.sdf_args.robust_kernel not in (None, "huber"):
-            raise NotImplementedError("only the huber kernel is built (fusion-lr-kt.yaml:47)")
-        p.huber_k = float(self.sdf_args.robust_k) if self.sdf_args.robust_kernel is not None else 0.0
+        p.huber_k = self._sdf_robust_k()
         groups = self.args.iter_config
         if len(groups) > _lib.GN_MAX_GROUPS:
             raise ValueError(f"iter_config has more than {_lib.GN_MAX_GROUPS} groups")

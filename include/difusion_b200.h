@@ -154,7 +154,7 @@ int dif_map_query(const dif_map_view* map, const float* xyz, int64_t n, int32_t*
 
 /* ---- compute_sdf_Hg  (system/tracker.py:174-218; SURVEY a-9) ------------------------------------------
  * Fused: transform obs by last*delta, lookup, decoder fwd (+bwd wrt xyz), r = sdf/std, J = [G R_last^T, q x .],
- * Huber(k) (huber_k <= 0: no robust kernel), normal equations.  pose = {R_last[9], t_last[3], R_delta[9], t_delta[3]}
+ * robust kernel (tracker.py:58-71: huber_k > 0 Huber(k); huber_k < 0 Tukey(-huber_k); 0 none), normal equations.  pose = {R_last[9], t_last[3], R_delta[9], t_delta[3]}
  * row-major fp32 (host memory, copied at call time).  out_dev[44] (fp64): H[36] row-major, g[6], energy, M (valid count);
  * already divided by M as the reference does.  want_grad = 0 reproduces no_grad=True (only energy and M are written).
  * `scratch` must be zero-filled ONCE by the caller; every call leaves it zero-filled again.
@@ -279,7 +279,7 @@ typedef struct dif_gn_group { int32_t n_iters, n_terms; int32_t kind[DIF_GN_MAX_
 typedef struct dif_gn_problem {
     const float* obs_xyz;        /* [n_obs][3] camera frame (tracker.last_processed_pc[0]); sdf terms only */
     int64_t n_obs;
-    float   huber_k;             /* sdf robust kernel (fusion-lr-kt.yaml:47); <= 0: none */
+    float   huber_k;             /* sdf robust kernel (fusion-lr-kt.yaml:47): > 0 Huber(k), < 0 Tukey(-k), 0 none */
     int32_t n_levels;
     dif_gn_level level[DIF_GN_MAX_LEVELS];
     float   intr[4];             /* fx, fy, cx, cy */

@@ -355,8 +355,15 @@ def huber_weight(x: torch.Tensor, k: float) -> torch.Tensor:             # track
     return w
 
 
+def tukey_weight(x: torch.Tensor, k: float) -> torch.Tensor:             # tracker.py:66-69
+    w = torch.zeros_like(x)
+    m = x.abs() <= k
+    w[m] = (1 - (x[m] / k) ** 2) ** 2
+    return w
+
+
 def compute_sdf_Hg(omap: OracleMap, R_last, t_last, R_delta, t_delta, obs_xyz: np.ndarray, robust_k: float | None = 5.0,
-                   no_grad: bool = False):
+                   no_grad: bool = False, robust_kernel: str = "huber"):
     """tracker.py:174-218.  Poses as float64 (R, t); obs_xyz (N,3) fp32 camera frame.
     Returns (H 6x6 f64, g (6,) f64, energy float) or (None, None, energy) when no_grad."""
     Rc, tc = compose(R_last, t_last, R_delta, t_delta)
@@ -378,7 +385,7 @@ def compute_sdf_Hg(omap: OracleMap, R_last, t_last, R_delta, t_delta, obs_xyz: n
         JW = J
     Wf = r
     if robust_k is not None:
-        w = huber_weight(r, robust_k)
+        w = huber_weight(r, robust_k) if robust_kernel == "huber" else tukey_weight(r, robust_k)
         Wf = Wf * w
         JW = JW * w.unsqueeze(1) if JW is not None else None
     scale = 1.0 / Wf.size(0)

@@ -648,3 +648,37 @@ def test_config5_terrain_against_oracle(model, dev, oracle_weights):
     lat, ref = m.latent_vecs.cpu().numpy()[:n_occ], o.latent_vecs[:n_occ]
     assert close(lat, ref), float(np.abs(lat - ref).max())
     print(f"[config 5] extent {ext} m: {n_occ} PLIVoxes, {int((o.voxel_obs_count[:n_occ] > 0).sum())} observed; max |latent - oracle| {np.abs(lat - ref).max():.2e}")
+
+
+def test_icp_tukey_kernel(golden, model, dev, monkeypatch, oracle_weights):
+    """The sdf term with the Tukey robust kernel (tracker.py:66-69; the shipped config uses Huber): tensor-core path vs exact-fp32 SIMT
+    path vs the CPU oracle, on the S0 fixture map (robust_k small enough that a third of the residuals fall outside the kernel)."""
+    import argparse
+    from difusion_b200.system.map import DenseIndexedMap
+    from difusion_b200.system.tracker import SDFTracker
+    from difusion_b200.utils.motion_util import Isometry, Rotation
+    from oracle import dif_oracle as O
+    fx = golden["s0_map"]
+    m = DenseIndexedMap(model, fixture_args(fx), 29, dev)
+    o = O.OracleMap(oracle_weights, fixture_args(fx))
+    for f in range(int(fx["n_frames"])):
+        m.integrate_keyframe(_t(fx[f"f{f}.xyz"], dev), _t(fx[f"f{f}.normal"], dev))
+        o.integrate_keyframe(fx[f"f{f}.xyz"], fx[f"f{f}.normal"])
+    k = 1.0
+    trk = SDFTracker(m, argparse.Namespace(sdf=dict(robust_kernel="tukey", robust_k=k, subsample=0.5), rgb=None, iter_config=[]))
+    last = Isometry(q=Rotation(matrix=fx["hg.R_last"]), t=fx["hg.t_last"])
+    delta = Isometry.from_twist(np.asarray([0.004, -0.003, 0.002, 0.003, -0.002, 0.001]))
+    obs = _t(fx["hg.obs"], dev)
+    assert obs.size(0) >= 2048                                   # tensor-core path
+    H, g, E = trk.compute_sdf_Hg(0, last, delta, obs, no_grad=False)
+    monkeypatch.setenv("DIF_ICP_PATH", "simt")
+    H2, g2, E2 = trk.compute_sdf_Hg(0, last, delta, obs, no_grad=False)
+    monkeypatch.delenv("DIF_ICP_PATH", raising=False)
+    oH, og, oE = O.compute_sdf_Hg(o, fx["hg.R_last"], fx["hg.t_last"], delta.q.rotation_matrix, delta.t, fx["hg.obs"], k, robust_kernel="tukey")
+    hH, hg_, hE = O.compute_sdf_Hg(o, fx["hg.R_last"], fx["hg.t_last"], delta.q.rotation_matrix, delta.t, fx["hg.obs"], k, robust_kernel="huber")
+    assert abs(oE - hE) > 1e-3 * abs(hE)                          # the two kernels differ on this data
+    assert hg_errors(H, g, E, H2, g2, E2)[0] <= 1.0 and close(E, E2, 1e-5)
+    assert hg_errors(H, g, E, oH, og, oE)[0] <= 1.0 and close(E, oE, 1e-4)
+    with pytest.raises(NotImplementedError):
+        SDFTracker(m, argparse.Namespace(sdf=dict(robust_kernel="cauchy", robust_k=k, subsample=0.5), rgb=None, iter_config=[])) \
+            .compute_sdf_Hg(0, last, delta, obs)
