@@ -549,6 +549,8 @@ def main():
                 if f >= 1:
                     L.dif_profile_hook(1, hooks[f][0].cuda_event, hooks[f][1].cuda_event)
                 L.dif_profile_hook(0, hooks[f][2].cuda_event, hooks[f][3].cuda_event)
+                L.dif_profile_hook(4, hooks[f][4].cuda_event, hooks[f][5].cuda_event)
+                L.dif_profile_hook(5, hooks[f][6].cuda_event, hooks[f][7].cuda_event)
             p.launch(k, track=f >= 1)
             if timed_events is not None:
                 timed_events[f][1].record(main_s)
@@ -569,17 +571,25 @@ def main():
     torch.cuda.synchronize(dev)
 
     # ------------------------------------------------------------------ kernel pass: direct launches with per-kernel CUDA-event hooks
-    hook_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    hook_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(8)] for _ in range(K)]
     for row in hook_ev:                  # torch creates the CUDA event lazily: record once so .cuda_event is a live handle
         for e in row:
             e.record()
     counts = []
     L.dif_launch_count(1)
+    ov_was = os.environ.get("DIF_FRAME_OVERLAP")
+    os.environ["DIF_FRAME_OVERLAP"] = "0"       # kernel times are taken with the frame's kernels in ONE stream (no tracker term beside the index chain)
     run_pass(d_packed, pipe_direct, hooks=hook_ev, collect=counts)
     torch.cuda.synchronize(dev)
+    if ov_was is None:
+        os.environ.pop("DIF_FRAME_OVERLAP", None)
+    else:
+        os.environ["DIF_FRAME_OVERLAP"] = ov_was
     launches_per_pass = int(L.dif_launch_count(1))
     icp_ms = [hook_ev[f][0].elapsed_time(hook_ev[f][1]) for f in range(1, K)]
     enc_ms = [hook_ev[f][2].elapsed_time(hook_ev[f][3]) for f in range(K)]
+    idx_ms = [hook_ev[f][4].elapsed_time(hook_ev[f][5]) for f in range(K)]
+    fuse_ms = [hook_ev[f][6].elapsed_time(hook_ev[f][7]) for f in range(K)]
     icp_samples = [c[0] for c in counts[1:]]
     enc_samples = [c[1] for c in counts]
     n_occ = m.n_occupied
@@ -655,6 +665,14 @@ def main():
                 "avg_launch_ms": 1e3 * dt / max(dn, 1), "algorithmic_flop_per_launch": dflop / max(dn, 1),
                 "share_of_step": dt / (total_ms * 1e-3),
                 "kernel_ms_sum_per_step": (enc_t + icp_t) * 1e3 / K,
+                "step_breakdown_us": {"icp_tc2_kernel": 1e3 * sum(icp_ms) / K, "index_chain (voxelize + prune_mark + alloc + gather)": 1e3 * sum(idx_ms) / K,
+                                      "encode_tc2_kernel": 1e3 * sum(enc_ms) / K, "fuse_kernel": 1e3 * sum(fuse_ms) / K,
+                                      "sum": 1e3 * (sum(icp_ms) + sum(idx_ms) + sum(enc_ms) + sum(fuse_ms)) / K, "step (graph replay)": 1e3 * total_ms / K,
+                                      "what": "per-step averages, CUDA events around the kernels in a direct-launch pass with the frame's kernels in one "
+                                              "stream; the timed step replays the graph with the tracker term on a side stream beside the index chain "
+                                              "(a few us less than the sum); the index chain moves ~4 MB per frame "
+                                              "(24N + 36N + 248V bytes, SURVEY 8d) through 3-4 dependent DRAM round trips per kernel on an L2-flushed map: "
+                                              "latency-bound, ~2 % of HBM"},
                 "note": "tcgen05 kernels, ALGORITHMIC FLOPs per SURVEY 8(d) (decoder fwd 98816 + bwd 91904, encoder 52096 per sample); the tensor pipe issues "
                         "3x that (fp16 hi/lo split passes).  Kernel durations from CUDA events around the kernel in a direct-launch pass over the same "
                         "frames (event hooks cannot sit inside a replayed graph).  A frame is only ~250 tiles of 128 samples, so these launches are "

@@ -600,6 +600,7 @@ int integrate_launch(const dif_map_view* map, const void* encoder_prepared, cons
     if (n == 0) cudaMemsetAsync(S.ctr, 0, CTR_COUNT * sizeof(int32_t), st);      // (otherwise zeroed by voxelize_kernel)
     const int PT = 64;                                             // small blocks: a 30k-point frame must still fill 148 SMs
     const int nb = (int)((n + PT - 1) / PT);
+    prof_begin(DIF_PROF_INDEX, st);
     if (n > 0) {
         launch_pdl(voxelize_kernel, nb, PT, 0, st, m, xyz, stride, (int)n, frame, S.p_hat, S.cell, P.cell_count, stats_dev, S.ctr);
         launch_pdl(prune_mark_kernel, nb, PT, 0, st, m, (int)n, frame, S.cell, P.cell_count, S.kept, unq_mask, P.bitmap, stats_dev);
@@ -626,6 +627,7 @@ int integrate_launch(const dif_map_view* map, const void* encoder_prepared, cons
     if (n > 0) {
         launch_pdl(gather_kernel, nb, PT, 0, st, m, (int)n, frame, S.p_hat, S.cell, S.kept, P.cell_count, P.slot_cnt, S.s_pt, S.s_slot, S.s_off,
                    S.touched, S.ctr, stats_dev);
+        prof_end(DIF_PROF_INDEX, st);
         const char* enc_env = getenv("DIF_ENCODE_PATH");                 // "simt" forces the exact-fp32 kernel (tests compare both)
         if (!(enc_env && enc_env[0] == 's') && n >= 256) {
             const int rc = launch_encode_accumulate_tc(encoder_prepared, m.g, S.p_hat, normal, stride, S.s_pt, S.s_slot, S.s_off, S.ctr + CTR_N_SAMPLES,
@@ -646,10 +648,15 @@ int integrate_launch(const dif_map_view* map, const void* encoder_prepared, cons
         }
         if (readers_done) {        // cross-stream join + plain launch (a programmatic edge cannot carry the second dependency)
             cudaStreamWaitEvent(st, readers_done, 0);
+            prof_begin(DIF_PROF_FUSE, st);
             fuse_kernel<<<DIF_NUM_SMS * 8, 256, 0, st>>>(m, S.touched, S.ctr, P.slot_cnt, P.slot_sum, stats_dev);
             readers_done = nullptr;
-        } else launch_pdl(fuse_kernel, DIF_NUM_SMS * 8, 256, 0, st, m, S.touched, S.ctr, P.slot_cnt, P.slot_sum, stats_dev);
-    }
+        } else {
+            prof_begin(DIF_PROF_FUSE, st);
+            launch_pdl(fuse_kernel, DIF_NUM_SMS * 8, 256, 0, st, m, S.touched, S.ctr, P.slot_cnt, P.slot_sum, stats_dev);
+        }
+        prof_end(DIF_PROF_FUSE, st);
+    } else prof_end(DIF_PROF_INDEX, st);
     if (readers_done) cudaStreamWaitEvent(st, readers_done, 0);       // nothing was fused: still rejoin the caller's stream
     return check_launch("dif_integrate");
 }

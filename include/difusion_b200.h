@@ -319,7 +319,8 @@ int dif_groupby_sum(const float* values /*[n][L]*/, const int64_t* indices /*[n]
  * dif_profile_hook: bracket the NEXT launch of the named kernel on this host thread with the two CUDA events
  *   (cudaEvent_t handles, recorded on the launch stream); one-shot, NULL/NULL disarms.
  * dif_launch_count: kernels launched by this host thread since the last reset. */
-enum { DIF_PROF_ENCODE = 0, DIF_PROF_ICP = 1, DIF_PROF_DECODE = 2, DIF_PROF_MC = 3, DIF_PROF_COUNT = 4 };
+enum { DIF_PROF_ENCODE = 0, DIF_PROF_ICP = 1, DIF_PROF_DECODE = 2, DIF_PROF_MC = 3,
+       DIF_PROF_INDEX = 4 /* voxelize .. gather of dif_integrate */, DIF_PROF_FUSE = 5, DIF_PROF_COUNT = 6 };
 int dif_profile_hook(int which, void* start_event, void* stop_event);
 uint64_t dif_launch_count(int reset);
 /* dif_debug_tc_timing: dev_buf = uint64[148*20*8] or NULL; when set, the tensor-core decoder records per-warp phase cycles
