@@ -399,6 +399,15 @@ def test_device_gauss_newton_sdf_only_and_errors(dev):
             m.integrate_keyframe(gt @ _t(pc, dev), gt.rotation @ _t(nc, dev))
         res.append(pose)
     assert np.linalg.norm(np.asarray(res[0].t) - np.asarray(res[1].t)) < 2e-6
+    # fewer than 2048 points: the exact-fp32 SIMT kernel serves the sdf term, reading pose and count from the same device block
+    small = []
+    for host in (False, True):
+        trk = SDFTracker(m, ns)
+        trk.host_loop = host
+        trk.all_pd_pose.append(gt)
+        small.append(trk.track_points(_t(pc[:1500], dev), _t(nc[:1500], dev)))
+    assert np.linalg.norm(np.asarray(small[0].t) - np.asarray(small[1].t)) < 2e-6
+    assert np.abs(np.asarray(small[0].q.rotation_matrix) - np.asarray(small[1].q.rotation_matrix)).max() < 2e-6
     far = torch.full((4096, 3), 50.0, device=dev)                 # every point outside the grid: M = 0
     with pytest.raises(AssertionError):
         trk2 = SDFTracker(m, ns)
