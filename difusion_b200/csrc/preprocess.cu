@@ -455,6 +455,10 @@ __device__ float3 smallest_eigenvector(float3 x1, float3 x2, float3 x3) {
 constexpr int KNN_MAX = 32;
 constexpr int NRM_WARPS = 8;
 
+// REACH: the grid's cell edge is radius / REACH and a query scans (2 REACH + 1)^2 z-runs of 2 REACH + 1 cells: with REACH = 2 the scanned
+// volume is 15.6 r^3 instead of 27 r^3 (the ball itself: 4.2 r^3), i.e. 42 % fewer candidates per query; the k nearest by
+// (distance, index) do not depend on the visiting order, so the normals are bit-identical for any REACH.
+template <int REACH>
 __global__ void __launch_bounds__(NRM_WARPS * 32) estimate_normals_kernel(const float* __restrict__ p, int stride, int n, const BoxState* __restrict__ s,
         float cell, const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end, const float4* __restrict__ sorted_pt,
         int max_nn, float r2, float3 cam, float* __restrict__ normal_out) {
@@ -469,10 +473,11 @@ __global__ void __launch_bounds__(NRM_WARPS * 32) estimate_normals_kernel(const 
     float e_d = inf; int e_i = 0x7fffffff; float4 e_p = make_float4(0.f, 0.f, 0.f, 0.f);      // list entry `lane` (valid if lane < cnt)
     int cnt = 0;
     float worst_d = inf; int worst_i = 0x7fffffff;                  // entry max_nn - 1 once the list is full
-    for (int oxy = 0; oxy < 9; ++oxy) {
-        const int x = cx + oxy / 3 - 1, y = cy + oxy % 3 - 1;
+    constexpr int W = 2 * REACH + 1;
+    for (int oxy = 0; oxy < W * W; ++oxy) {
+        const int x = cx + oxy / W - REACH, y = cy + oxy % W - REACH;
         if (x < 0 || x >= s->n[0] || y < 0 || y >= s->n[1]) continue;
-        const int z0 = max(cz - 1, 0), z1 = min(cz + 1, s->n[2] - 1);
+        const int z0 = max(cz - REACH, 0), z1 = min(cz + REACH, s->n[2] - 1);
         const int c0 = (x * s->n[1] + y) * s->n[2];
         const uint32_t b = cell_start[c0 + z0], e = cell_end[c0 + z1];
         for (uint32_t j0 = b; j0 < e; j0 += 32) {
@@ -590,8 +595,11 @@ int dif_estimate_normals(const float* pc, int stride, int64_t n, int max_nn, flo
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) { cudaMemsetAsync(status_dev, 0, 4, st); return check_launch("dif_estimate_normals"); }
     const unsigned gp = (unsigned)((n + 255) / 256);
-    dif::KnnPlan k = dif::knn_build(pc, stride, (int)n, radius, max_cells, scratch, st);
-    dif::estimate_normals_kernel<<<(unsigned)((n + dif::NRM_WARPS - 1) / dif::NRM_WARPS), dif::NRM_WARPS * 32, 0, st>>>(pc, stride, (int)n, k.s, radius, k.cell_start, k.cell_fill, k.sorted_pt,
+    constexpr int REACH = 1;                 // measured on a 76.8 k-point frame: REACH 1 = 671 us, REACH 2 = 781 us (25 short z-runs leave most of
+                                             // a 32-lane batch empty and the 8x larger grid costs more to scan and clear)
+    const float cell = radius / (float)REACH;
+    dif::KnnPlan k = dif::knn_build(pc, stride, (int)n, cell, max_cells, scratch, st);
+    dif::estimate_normals_kernel<REACH><<<(unsigned)((n + dif::NRM_WARPS - 1) / dif::NRM_WARPS), dif::NRM_WARPS * 32, 0, st>>>(pc, stride, (int)n, k.s, cell, k.cell_start, k.cell_fill, k.sorted_pt,
                                                                                 max_nn, radius * radius, make_float3(cam_xyz[0], cam_xyz[1], cam_xyz[2]), normal_out);
     dif::knn_clear_kernel<<<(unsigned)((max_cells + 255) / 256), 256, 0, st>>>(k.s, k.cell_start, k.cell_fill);
     cudaMemcpyAsync(status_dev, &k.s->overflow, 4, cudaMemcpyDeviceToDevice, st);
