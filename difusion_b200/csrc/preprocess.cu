@@ -8,6 +8,7 @@
 // float atomics.  Everything is sized on the device; the caller reads back one count.  HBM-bound: 24 B in per point, bitmap
 // traffic, 24 B out per occupied cell.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace dif {
 
@@ -455,9 +456,9 @@ __device__ float3 smallest_eigenvector(float3 x1, float3 x2, float3 x3) {
 constexpr int KNN_MAX = 32;
 constexpr int NRM_WARPS = 8;
 
-// REACH: the grid's cell edge is radius / REACH and a query scans (2 REACH + 1)^2 z-runs of 2 REACH + 1 cells: with REACH = 2 the scanned
-// volume is 15.6 r^3 instead of 27 r^3 (the ball itself: 4.2 r^3), i.e. 42 % fewer candidates per query; the k nearest by
-// (distance, index) do not depend on the visiting order, so the normals are bit-identical for any REACH.
+// REACH: the grid's cell edge is radius / REACH.  REACH 1: one ring (27 cells of edge `radius`).  REACH 2: inner ring first (27 cells of
+// edge radius / 2), the outer shell only when the inner ring cannot prove completeness (see below).  The k nearest by (distance, index)
+// do not depend on the visiting order, so the normals are bit-identical for any REACH.
 template <int REACH>
 __global__ void __launch_bounds__(NRM_WARPS * 32) estimate_normals_kernel(const float* __restrict__ p, int stride, int n, const BoxState* __restrict__ s,
         float cell, const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end, const float4* __restrict__ sorted_pt,
@@ -473,11 +474,11 @@ __global__ void __launch_bounds__(NRM_WARPS * 32) estimate_normals_kernel(const 
     float e_d = inf; int e_i = 0x7fffffff; float4 e_p = make_float4(0.f, 0.f, 0.f, 0.f);      // list entry `lane` (valid if lane < cnt)
     int cnt = 0;
     float worst_d = inf; int worst_i = 0x7fffffff;                  // entry max_nn - 1 once the list is full
-    constexpr int W = 2 * REACH + 1;
-    for (int oxy = 0; oxy < W * W; ++oxy) {
-        const int x = cx + oxy / W - REACH, y = cy + oxy % W - REACH;
-        if (x < 0 || x >= s->n[0] || y < 0 || y >= s->n[1]) continue;
-        const int z0 = max(cz - REACH, 0), z1 = min(cz + REACH, s->n[2] - 1);
+    // One z-run of cells (x, y, z0..z1): 32 consecutive candidates per step.
+    auto scan_run = [&](int x, int y, int z0, int z1) {
+        if (x < 0 || x >= s->n[0] || y < 0 || y >= s->n[1]) return;
+        z0 = max(z0, 0); z1 = min(z1, s->n[2] - 1);
+        if (z0 > z1) return;
         const int c0 = (x * s->n[1] + y) * s->n[2];
         const uint32_t b = cell_start[c0 + z0], e = cell_end[c0 + z1];
         for (uint32_t j0 = b; j0 < e; j0 += 32) {
@@ -505,6 +506,30 @@ __global__ void __launch_bounds__(NRM_WARPS * 32) estimate_normals_kernel(const 
                 else if (lane > pos) { e_d = up_d; e_i = up_i; e_p = up_p; }
                 if (cnt < max_nn) ++cnt;
                 if (cnt == max_nn) { worst_d = __shfl_sync(0xffffffffu, e_d, max_nn - 1); worst_i = __shfl_sync(0xffffffffu, e_i, max_nn - 1); }
+            }
+        }
+    };
+    // z-runs are visited nearest first (the query's own column, its 4 edge neighbours, the 4 corners): the list's worst entry
+    // shrinks early, so far fewer candidates are inserted (ncu: the insertion loop was ~40 % of this kernel's instructions, issue
+    // slots 88 % busy); the k nearest by (distance, index) do not depend on the visiting order.
+    for (int o_ = 0; o_ < 9; ++o_) {
+        const int oxy = (int)((0x862075314ull >> (4 * o_)) & 15);                         // 4, 1, 3, 5, 7, 0, 2, 6, 8
+        scan_run(cx + oxy / 3 - 1, cy + oxy % 3 - 1, cz - 1, cz + 1);
+    }
+    if (REACH == 2) {
+        // TWO RINGS (cell edge = radius / 2): the inner 3 x 3 x 3 block above holds every point within one cell edge of the query.  If
+        // the list is full and its worst entry lies within 0.99 cell edges, no point outside the block can enter it and the result is
+        // complete; that is the case wherever the surface is sampled densely (16 neighbours within 5 cm), i.e. almost everywhere,
+        // at a quarter of the candidates of a one-ring search with cell edge = radius.  Otherwise the outer shell of the
+        // 5 x 5 x 5 block (everything within `radius`) is scanned as well.  Warp-uniform decision.
+        const float lim = 0.99f * cell;
+        if (!(cnt == max_nn && worst_d <= lim * lim)) {
+            for (int o_ = 0; o_ < 25; ++o_) {
+                const int dx = o_ / 5 - 2, dy = o_ % 5 - 2;
+                if (dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1) {           // column of the inner block: only its two end cells are new
+                    scan_run(cx + dx, cy + dy, cz - 2, cz - 2);
+                    scan_run(cx + dx, cy + dy, cz + 2, cz + 2);
+                } else scan_run(cx + dx, cy + dy, cz - 2, cz + 2);
             }
         }
     }
@@ -595,12 +620,17 @@ int dif_estimate_normals(const float* pc, int stride, int64_t n, int max_nn, flo
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) { cudaMemsetAsync(status_dev, 0, 4, st); return check_launch("dif_estimate_normals"); }
     const unsigned gp = (unsigned)((n + 255) / 256);
-    constexpr int REACH = 1;                 // measured on a 76.8 k-point frame: REACH 1 = 671 us, REACH 2 = 781 us (25 short z-runs leave most of
-                                             // a 32-lane batch empty and the 8x larger grid costs more to scan and clear)
-    const float cell = radius / (float)REACH;
+    // two-ring search on cells of radius / 2 with an early exit after the inner ring (default), or the one-ring search on cells of
+    // `radius` (DIF_NORMALS_REACH=1: the yardstick of the bitwise comparison test).  Measured on a 76.8 k-point frame: one ring 565 us;
+    // two rings WITHOUT the early exit 781 us (25 short z-runs leave most of a 32-lane batch empty).
+    const char* re = getenv("DIF_NORMALS_REACH");
+    const int reach = (re && re[0] == '1') ? 1 : 2;
+    const float cell = radius / (float)reach;
     dif::KnnPlan k = dif::knn_build(pc, stride, (int)n, cell, max_cells, scratch, st);
-    dif::estimate_normals_kernel<REACH><<<(unsigned)((n + dif::NRM_WARPS - 1) / dif::NRM_WARPS), dif::NRM_WARPS * 32, 0, st>>>(pc, stride, (int)n, k.s, cell, k.cell_start, k.cell_fill, k.sorted_pt,
-                                                                                max_nn, radius * radius, make_float3(cam_xyz[0], cam_xyz[1], cam_xyz[2]), normal_out);
+    const unsigned gq = (unsigned)((n + dif::NRM_WARPS - 1) / dif::NRM_WARPS);
+    const float3 cam = make_float3(cam_xyz[0], cam_xyz[1], cam_xyz[2]);
+    if (reach == 1) dif::estimate_normals_kernel<1><<<gq, dif::NRM_WARPS * 32, 0, st>>>(pc, stride, (int)n, k.s, cell, k.cell_start, k.cell_fill, k.sorted_pt, max_nn, radius * radius, cam, normal_out);
+    else dif::estimate_normals_kernel<2><<<gq, dif::NRM_WARPS * 32, 0, st>>>(pc, stride, (int)n, k.s, cell, k.cell_start, k.cell_fill, k.sorted_pt, max_nn, radius * radius, cam, normal_out);
     dif::knn_clear_kernel<<<(unsigned)((max_cells + 255) / 256), 256, 0, st>>>(k.s, k.cell_start, k.cell_fill);
     cudaMemcpyAsync(status_dev, &k.s->overflow, 4, cudaMemcpyDeviceToDevice, st);
     DIF_COUNT_LAUNCH(2);

@@ -226,5 +226,5 @@ def estimate_normals(input_pc: torch.Tensor, max_nn: int, radius: float, cam_xyz
     if status_out is not None:
         status_out.append(call(*_knn_buffers(dev, n)))
     else:
-        _knn_call("estimate_normals", input_pc, float(radius), call)
+        _knn_call("estimate_normals", input_pc, 0.5 * float(radius), call)             # two-ring search: the grid's cells are radius / 2
     return normals

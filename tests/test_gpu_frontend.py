@@ -465,3 +465,25 @@ def test_masked_front_end_equals_compacting_front_end(dev):
         assert pa[0].shape == pb[0].shape and pa[0].size(0) > 15000
         assert torch.equal(pa[0], pb[0]) and torch.equal(pa[1], pb[1])
         assert torch.equal(ca[0], cb[0]) and torch.equal(ca[1], cb[1])
+
+
+def test_two_ring_normals_equal_one_ring_normals(dev, monkeypatch):
+    """estimate_normals searches the inner 3x3x3 block of a radius/2 grid first and only falls back to the outer shell when the 16
+    nearest found so far do not prove completeness; the one-ring search on cells of `radius` (DIF_NORMALS_REACH=1) is the yardstick:
+    bit-identical normals, on dense frames, on a frame thinned to a tenth (fallback everywhere) and on an un-compacted cloud."""
+    from difusion_b200 import synthetic as S
+    from difusion_b200.system import ext
+    sc = S.scene_S1(0.05)
+    for f, thin in ((0, 1), (30, 1), (60, 1), (10, 10), (10, 3)):
+        R, t = S.orbit_pose(f, 200)
+        pc, _ = S.frame_points(sc, R, t, box=0.0)
+        pc = pc[::thin]
+        if f == 30:                                                 # NaN rows in place (the masked front end's input)
+            pc = pc.copy(); pc[::7] = np.nan
+        cloud = _t(pc, dev)
+        monkeypatch.setenv("DIF_NORMALS_REACH", "1")
+        one = ext.estimate_normals(cloud, 16, 0.1, [0.0, 0.0, 0.0])
+        monkeypatch.delenv("DIF_NORMALS_REACH", raising=False)
+        two = ext.estimate_normals(cloud, 16, 0.1, [0.0, 0.0, 0.0])
+        assert torch.equal(one.view(torch.int32), two.view(torch.int32)), (f, thin)
+        assert int((~torch.isnan(two[:, 0])).sum()) > 0.5 * (pc.shape[0] if f != 30 else pc.shape[0] * 6 // 7) or thin == 10
