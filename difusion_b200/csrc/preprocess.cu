@@ -358,10 +358,11 @@ __global__ void __launch_bounds__(1024) knn_scan2_kernel(uint32_t* __restrict__ 
 // cell_start[c] = chunk offset + in-chunk offset; cell_fill[c] = same (cursor used by the fill pass)
 __global__ void knn_offsets_kernel(uint32_t* __restrict__ cell_start, uint32_t* __restrict__ cell_fill, const uint32_t* __restrict__ chunk_sum,
                                    const BoxState* __restrict__ s) {
-    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= s->n_cells) return;
-    const uint32_t v = cell_start[c] + chunk_sum[c / BOX_SCAN_W];
-    cell_start[c] = v; cell_fill[c] = v;
+    // grid-stride over the cells of THIS cloud's bounding box (the launch no longer covers the scratch's whole cell budget)
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < s->n_cells; c += (long long)gridDim.x * blockDim.x) {
+        const uint32_t v = cell_start[c] + chunk_sum[c / BOX_SCAN_W];
+        cell_start[c] = v; cell_fill[c] = v;
+    }
 }
 
 __global__ void knn_fill_kernel(const float* __restrict__ p, int stride, int n, const BoxState* __restrict__ s, float cell,
@@ -378,9 +379,9 @@ __global__ void knn_fill_kernel(const float* __restrict__ p, int stride, int n, 
 // after the fill pass cell_fill[c] == end of cell c.  The last kernel of a call zeroes both cell arrays over the bounding box again
 // (the scan wrote a prefix into every cell of the box, occupied or not), so the scratch is all-zero between calls.
 __global__ void knn_clear_kernel(const BoxState* __restrict__ s, uint32_t* __restrict__ cell_start, uint32_t* __restrict__ cell_fill) {
-    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= s->n_cells) return;
-    cell_start[c] = 0u; cell_fill[c] = 0u;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < s->n_cells; c += (long long)gridDim.x * blockDim.x) {
+        cell_start[c] = 0u; cell_fill[c] = 0u;
+    }
 }
 
 __device__ __forceinline__ float knn_d2(float qx, float qy, float qz, float4 b) {
@@ -557,6 +558,9 @@ __global__ void __launch_bounds__(NRM_WARPS * 32) estimate_normals_kernel(const 
     if (lane == 0) { normal_out[3 * i] = nrm.x; normal_out[3 * i + 1] = nrm.y; normal_out[3 * i + 2] = nrm.z; }
 }
 
+// blocks of the per-cell kernels: enough to fill the GPU, independent of the cell budget (they stride over s->n_cells)
+static unsigned knn_cell_grid(int64_t max_cells) { const int64_t g = (max_cells + 255) / 256; return (unsigned)(g < DIF_NUM_SMS * 8 ? g : DIF_NUM_SMS * 8); }
+
 struct KnnPlan { BoxState* s; uint32_t *cell_start, *cell_fill, *chunk_sum; int* sorted_idx; float4* sorted_pt; long long max_cells; };
 
 static size_t knn_scratch_bytes(int64_t n, int64_t max_cells) {
@@ -582,7 +586,7 @@ static KnnPlan knn_build(const float* p, int stride, int n, float cell, int64_t 
     const unsigned chunks = (unsigned)((max_cells + BOX_SCAN_W - 1) / BOX_SCAN_W);
     knn_scan1_kernel<<<chunks, BOX_SCAN_T, 0, st>>>(k.cell_start, k.s, k.chunk_sum);
     knn_scan2_kernel<<<1, 1024, 0, st>>>(k.chunk_sum, k.s);
-    knn_offsets_kernel<<<(unsigned)((max_cells + 255) / 256), 256, 0, st>>>(k.cell_start, k.cell_fill, k.chunk_sum, k.s);
+    knn_offsets_kernel<<<knn_cell_grid(max_cells), 256, 0, st>>>(k.cell_start, k.cell_fill, k.chunk_sum, k.s);
     knn_fill_kernel<<<gp, 256, 0, st>>>(p, stride, n, k.s, cell, k.cell_fill, k.sorted_idx, k.sorted_pt);
     DIF_COUNT_LAUNCH(8);
     return k;
@@ -605,7 +609,7 @@ int dif_remove_radius_outlier(const float* pc, int stride, int64_t n, int nb_poi
     dif::KnnPlan k = dif::knn_build(pc, stride, (int)n, radius, max_cells, scratch, st);
     dif::radius_count_kernel<<<gp, 256, 0, st>>>(pc, stride, (int)n, k.s, radius, k.cell_start, k.cell_fill, k.sorted_pt, nb_points,
                                                  radius * radius, mask_out);
-    dif::knn_clear_kernel<<<(unsigned)((max_cells + 255) / 256), 256, 0, st>>>(k.s, k.cell_start, k.cell_fill);
+    dif::knn_clear_kernel<<<dif::knn_cell_grid(max_cells), 256, 0, st>>>(k.s, k.cell_start, k.cell_fill);
     cudaMemcpyAsync(status_dev, &k.s->overflow, 4, cudaMemcpyDeviceToDevice, st);
     DIF_COUNT_LAUNCH(2);
     return check_launch("dif_remove_radius_outlier");
@@ -631,7 +635,7 @@ int dif_estimate_normals(const float* pc, int stride, int64_t n, int max_nn, flo
     const float3 cam = make_float3(cam_xyz[0], cam_xyz[1], cam_xyz[2]);
     if (reach == 1) dif::estimate_normals_kernel<1><<<gq, dif::NRM_WARPS * 32, 0, st>>>(pc, stride, (int)n, k.s, cell, k.cell_start, k.cell_fill, k.sorted_pt, max_nn, radius * radius, cam, normal_out);
     else dif::estimate_normals_kernel<2><<<gq, dif::NRM_WARPS * 32, 0, st>>>(pc, stride, (int)n, k.s, cell, k.cell_start, k.cell_fill, k.sorted_pt, max_nn, radius * radius, cam, normal_out);
-    dif::knn_clear_kernel<<<(unsigned)((max_cells + 255) / 256), 256, 0, st>>>(k.s, k.cell_start, k.cell_fill);
+    dif::knn_clear_kernel<<<dif::knn_cell_grid(max_cells), 256, 0, st>>>(k.s, k.cell_start, k.cell_fill);
     cudaMemcpyAsync(status_dev, &k.s->overflow, 4, cudaMemcpyDeviceToDevice, st);
     DIF_COUNT_LAUNCH(2);
     return check_launch("dif_estimate_normals");
