@@ -114,6 +114,7 @@ SIGNATURES = {
     "dif_rgb_scratch_bytes": (_SZ, []),
     "dif_rgb_linearize": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _FP, _FP, _FP, _F, _F, C.c_int, _F, _F, C.c_int, _P, _SZ, _P, _P]),
     "dif_latent_grad": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P]),
+    "dif_debug_gn_step": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "dif_gn_scratch_bytes": (_SZ, [_I64]),
     "dif_gauss_newton": (C.c_int, [_MV, _P, C.POINTER(GnProblem), _P, _SZ, _P, C.POINTER(GnResult), _P]),
     "dif_mesh_cache_scratch_bytes": (_SZ, [_I64, _I64]),

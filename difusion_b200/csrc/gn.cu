@@ -60,7 +60,7 @@ __global__ void gn_init_kernel(GnState* s, GnInit in, GnCalib c) {
 }
 
 // H xi = -g by Gaussian elimination with partial pivoting (what numpy.linalg.solve / LAPACK gesv does); false if singular
-__device__ inline bool gn_solve6(const double* H, const double* g, double* xi) {
+__host__ __device__ inline bool gn_solve6(const double* H, const double* g, double* xi) {
     double A[6][7];
     for (int i = 0; i < 6; ++i) { for (int j = 0; j < 6; ++j) A[i][j] = H[6 * i + j]; A[i][6] = -g[i]; }
     for (int c = 0; c < 6; ++c) {
@@ -82,7 +82,7 @@ __device__ inline bool gn_solve6(const double* H, const double* g, double* xi) {
 }
 
 // delta <- from_twist(xi) . delta   (motion_util.py:205-229: R = exp(phi), t = J_l(phi) rho; :277-278 composition)
-__device__ inline void gn_apply_twist(const double* xi, double* d) {
+__host__ __device__ inline void gn_apply_twist(const double* xi, double* d) {
     const double rho[3] = {xi[0], xi[1], xi[2]}, phi[3] = {xi[3], xi[4], xi[5]};
     const double angle = sqrt(phi[0] * phi[0] + phi[1] * phi[1] + phi[2] * phi[2]);
     double R[9], J[9];
@@ -155,6 +155,16 @@ __global__ void gn_update_kernel(GnState* s, GnCalib c, GnTermOuts t, int is_fir
 using namespace dif;
 
 extern "C" {
+
+// The update step of one iteration (solve H xi = -g, delta <- exp(xi) . delta) evaluated on the HOST with the very functions
+// gn_update_kernel runs on the device: lets the CPU test-suite pin the fp64 algebra against numpy without a GPU.
+int dif_debug_gn_step(const double* H, const double* g, double* delta_inout) {
+    if (!H || !g || !delta_inout) return DIF_E_INVALID;
+    double xi[6];
+    if (!gn_solve6(H, g, xi)) return DIF_GN_SINGULAR;
+    gn_apply_twist(xi, delta_inout);
+    return DIF_OK;
+}
 
 size_t dif_gn_scratch_bytes(int64_t n_obs) {
     return align_up(sizeof(GnState)) + align_up((size_t)DIF_GN_MAX_TERMS * 44 * sizeof(double))

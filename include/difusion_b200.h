@@ -297,6 +297,9 @@ typedef struct dif_gn_result {
     double  energy;              /* energy of the last evaluated iterate */
     int32_t last_iter, status, empty_term, n_iterations, n_sdf, n_rgb;
 } dif_gn_result;
+/* host evaluation of one update step with the device loop's own functions (H [36], g [6], delta [12] in/out): DIF_OK, or
+ * DIF_GN_SINGULAR; test hook, no GPU needed */
+int dif_debug_gn_step(const double* H, const double* g, double* delta_inout);
 size_t dif_gn_scratch_bytes(int64_t n_obs);
 int dif_gauss_newton(const dif_map_view* map, const void* decoder_prepared, const dif_gn_problem* problem, void* scratch, size_t scratch_bytes,
                      void* mailbox_host, dif_gn_result* result, void* stream);

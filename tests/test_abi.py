@@ -116,3 +116,28 @@ def test_isometry_matches_oracle_se3():
     p = np.random.default_rng(0).normal(size=(5, 3))
     assert np.allclose(iso @ p, p @ R.T + t)
     assert np.allclose((iso @ torch.from_numpy(p).float()).numpy(), (p @ R.T + t).astype(np.float32), atol=1e-6)
+
+
+def test_gauss_newton_update_step_matches_numpy():
+    """The fp64 algebra of the device-driven Gauss-Newton loop (csrc/gn.cu: partial-pivot 6x6 solve, exp map with the left Jacobian,
+    composition), evaluated on the host through dif_debug_gn_step, against numpy.linalg.solve + Isometry.from_twist @ delta
+    (reference system/tracker.py:270-272, utils/motion_util.py:205-229,277-278)."""
+    import ctypes
+    from difusion_b200 import _lib
+    from difusion_b200.utils.motion_util import Isometry
+    L = _lib.lib()
+    rng = np.random.default_rng(5)
+    for trial in range(20):
+        J = rng.normal(size=(200, 6)) * rng.uniform(0.1, 30.0, size=6)
+        H = J.T @ J / 200
+        g = J.T @ rng.normal(size=200) / 200 * (1e-9 if trial == 0 else 1.0)          # trial 0: |phi| ~ 1e-10, the small-angle branch
+        d0 = Isometry.from_twist(rng.normal(size=6) * 0.05)
+        delta = np.concatenate([d0.q.rotation_matrix.ravel(), d0.t]).astype(np.float64)
+        buf = (ctypes.c_double * 12)(*delta)
+        rc = L.dif_debug_gn_step((ctypes.c_double * 36)(*H.ravel()), (ctypes.c_double * 6)(*g), buf)
+        assert rc == 0
+        ref = Isometry.from_twist(np.linalg.solve(H, -g)) @ d0
+        got = np.asarray(buf[:])
+        assert np.abs(got[:9].reshape(3, 3) - ref.q.rotation_matrix).max() < 1e-12 and np.abs(got[9:] - ref.t).max() < 1e-12
+    sing = np.zeros((6, 6)); sing[0, 0] = 1.0
+    assert L.dif_debug_gn_step((ctypes.c_double * 36)(*sing.ravel()), (ctypes.c_double * 6)(*np.ones(6)), buf) == _lib.GN_SINGULAR
